@@ -1,0 +1,396 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = epi( A[M,K] * B[N,K]^T (+ A2 * B2^T) )
+//
+// Replaces the cuBLASLt calls behind the reference's nn.Linear layers on the hot path
+// (timm Block qkv/proj/fc1/fc2, reference call sites src/adapters/lora.py:78-90 and the
+// ResidualAttentionBlock at src/third_party/openai_clip/model.py:177-202) and their dgrads.
+//
+//   * A and B are bf16, K-major (row-major [rows, K]); frozen weights are kept in both [N,K] and
+//     [K,N] copies by the host so forward and dgrad are both "NT" problems.
+//   * warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer (+ TMEM allocator),
+//     warps 2..5 = epilogue (TMEM -> registers -> swizzled smem slab -> TMA store).
+//   * accumulators: 2 x BLOCK_N fp32 columns of TMEM (double buffered so the epilogue of tile i
+//     overlaps the MMAs of tile i+1); smem ring of kStages x (A 128x64 + B BLOCK_Nx64) bf16 tiles
+//     in the 128-byte-swizzle K-major UMMA layout that TMA writes directly.
+//   * optional second operand pair (A2 [M,K2], B2 [N,K2]) is accumulated into the same TMEM tile
+//     as extra K blocks: this is how LoRA's s*(x A^T) B^T rides on the base projection.
+//   * epilogue: + bias, erf-GELU / QuickGELU (optionally also storing the pre-activation for
+//     backward), + residual, or * act'(pre) for the backward through the activation.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ngu {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kNumEpiWarps = 4;
+constexpr int kGemmThreads = 32 * (2 + kNumEpiWarps);
+constexpr int kSlabBytes = 32 * 128;  // 32 rows x 64 bf16
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiBytes = kNumEpiWarps * 2 * kSlabBytes;
+  static constexpr int kBarBytes = 2048;  // mbarriers + tmem ptr (first 1 KB) and per-warp bias staging (second 1 KB)
+  static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/;
+  static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes - kBarBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+};
+
+struct GemmKernelParams {
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmC, tmPre;
+  const float* bias;  // [N] fp32 or nullptr
+  const bf16* aux;    // [M, ldaux] residual / saved pre-activation, or nullptr
+  int ldaux;
+  int M, N, K, K2;
+  int act;       // NGU_ACT_*
+  int aux_mode;  // NGU_AUX_*
+  int save_pre;  // also store (acc + bias) through tmPre
+  float alpha;   // scale on the accumulator before bias
+};
+
+// Epilogue math for one 64-column chunk of one row: v = raw fp32 accumulators, ax = aux row chunk
+// (bf16x2 words), bias_s = smem address of this warp's 64 staged bias floats.  Compile-time
+// ACT/AUX so the hot loop stays small (the runtime switch happens once per chunk, warp-uniform).
+template <int ACT, int AUX>
+NGU_DEVINL void epi_chunk(const uint32_t (&v)[64], const uint4 (&ax)[8], uint32_t bias_s, float alpha,
+                          uint32_t (&outp)[32], uint32_t (&prep)[32]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 16; ++j4) {
+    float b[4];
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]) : "r"(bias_s + j4 * 16));
+    float x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = fmaf(__uint_as_float(v[4 * j4 + i]), alpha, b[i]);
+    prep[2 * j4] = pack_bf16x2(x[0], x[1]);
+    prep[2 * j4 + 1] = pack_bf16x2(x[2], x[3]);
+    const uint32_t* axw = reinterpret_cast<const uint32_t*>(ax);
+    const float2 a01 = unpack_bf16x2(axw[2 * j4]);
+    const float2 a23 = unpack_bf16x2(axw[2 * j4 + 1]);
+    const float a[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (AUX == NGU_AUX_DACT) {
+        if (ACT == NGU_ACT_GELU) x[i] *= gelu_erf_grad(a[i]);
+        else if (ACT == NGU_ACT_QUICKGELU) x[i] *= quick_gelu_grad(a[i]);
+      } else {
+        if (ACT == NGU_ACT_GELU) x[i] = gelu_erf(x[i]);
+        else if (ACT == NGU_ACT_QUICKGELU) x[i] = quick_gelu(x[i]);
+        if (AUX == NGU_AUX_RESIDUAL) x[i] += a[i];
+      }
+    }
+    outp[2 * j4] = pack_bf16x2(x[0], x[1]);
+    outp[2 * j4 + 1] = pack_bf16x2(x[2], x[3]);
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA0 = smem_base;
+  const uint32_t sB0 = smem_base + Cfg::kStages * Cfg::kABytes;
+  const uint32_t sEpi = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t sBar = sEpi + Cfg::kEpiBytes;
+  // barrier slots (8 bytes each)
+  auto full_bar = [&](int s) { return sBar + 8u * s; };
+  auto empty_bar = [&](int s) { return sBar + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return sBar + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return sBar + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t sTmemPtr = sBar + 8u * (2 * Cfg::kStages + 4);
+  const uint32_t sBias = sBar + 1024u;  // 4 warps x 64 fp32
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int kb1 = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb2 = (p.K2 + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb = kb1 + kb2;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmC);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kNumEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(sTmemPtr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmemPtr));
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BLOCK_M;
+        const int n0 = (t % n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), Cfg::kStageBytes);
+          if (kb < kb1) {
+            tma_load_2d(sA0 + s * Cfg::kABytes, &p.tmA, full_bar(s), kb * BLOCK_K, m0, kEvictNormal);
+            tma_load_2d(sB0 + s * Cfg::kBBytes, &p.tmB, full_bar(s), kb * BLOCK_K, n0, kEvictLast);
+          } else {
+            tma_load_2d(sA0 + s * Cfg::kABytes, &p.tmA2, full_bar(s), (kb - kb1) * BLOCK_K, m0, kEvictNormal);
+            tma_load_2d(sB0 + s * Cfg::kBBytes, &p.tmB2, full_bar(s), (kb - kb1) * BLOCK_K, n0, kEvictLast);
+          }
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          // number of valid 16-wide K slices in this block (zero-filled tails are skipped)
+          int kext = (kb < kb1) ? (p.K - kb * BLOCK_K) : (p.K2 - (kb - kb1) * BLOCK_K);
+          kext = kext > BLOCK_K ? BLOCK_K : kext;
+          const int nk = (kext + UMMA_K - 1) / UMMA_K;
+          const uint32_t a_addr = sA0 + s * Cfg::kABytes;
+          const uint32_t b_addr = sB0 + s * Cfg::kBBytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            if (k < nk) {
+              const uint64_t adesc = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+              umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar(s));  // frees the smem slot once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int e = warp - 2;  // slab owner index
+    const uint32_t slab0 = sEpi + (e * 2 + 0) * kSlabBytes;
+    const uint32_t slab1 = sEpi + (e * 2 + 1) * kSlabBytes;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    uint32_t g = 0;  // running chunk counter -> slab parity
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t / n_tiles) * BLOCK_M;
+      const int n0 = (t % n_tiles) * BLOCK_N;
+      const int row = m0 + q * 32 + lane;
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
+      constexpr int kChunks = BLOCK_N / 64;
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c) {
+        const int nc = n0 + c * 64;
+        const bool live = nc < p.N;  // warp-uniform
+        uint32_t v[64];
+        {
+          uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+          uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+          tmem_ld32(t_addr + c * 64, lo);
+          tmem_ld32(t_addr + c * 64 + 32, hi);
+        }
+        // bias chunk: lane l fetches 2 floats, staged in this warp's 256 B of smem, read back broadcast
+        const uint32_t bias_s = sBias + uint32_t(e) * 256u;
+        if (live) {
+          const int n = nc + 2 * lane;
+          float2 bv = make_float2(0.f, 0.f);
+          if (p.bias != nullptr) {
+            bv.x = (n < p.N) ? __ldg(p.bias + n) : 0.f;
+            bv.y = (n + 1 < p.N) ? __ldg(p.bias + n + 1) : 0.f;
+          }
+          __syncwarp();
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_s + lane * 8), "f"(bv.x), "f"(bv.y) : "memory");
+          __syncwarp();
+        }
+        // aux row chunk straight from global (each thread owns one row: 8 x 16 B)
+        uint4 ax[8];
+        const bool has_aux = (p.aux_mode != NGU_AUX_NONE) && live && row < p.M;
+        if (has_aux) {
+          const uint4* ap = reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.ldaux + nc);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (nc + j * 8 < p.N) ax[j] = __ldg(ap + j);
+            else ax[j] = make_uint4(0, 0, 0, 0);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ax[j] = make_uint4(0, 0, 0, 0);
+        }
+        tmem_ld_wait();
+        if (c == kChunks - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if (!live) continue;
+
+        uint32_t outp[32];
+        uint32_t prep[32];
+        {
+          const int mode = p.act * 3 + p.aux_mode;  // warp-uniform
+          switch (mode) {
+            case NGU_ACT_NONE * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_NONE, NGU_AUX_NONE>(v, ax, bias_s, p.alpha, outp, prep); break;
+            case NGU_ACT_NONE * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_NONE, NGU_AUX_RESIDUAL>(v, ax, bias_s, p.alpha, outp, prep); break;
+            case NGU_ACT_GELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_GELU, NGU_AUX_NONE>(v, ax, bias_s, p.alpha, outp, prep); break;
+            case NGU_ACT_GELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_GELU, NGU_AUX_RESIDUAL>(v, ax, bias_s, p.alpha, outp, prep); break;
+            case NGU_ACT_GELU * 3 + NGU_AUX_DACT: epi_chunk<NGU_ACT_GELU, NGU_AUX_DACT>(v, ax, bias_s, p.alpha, outp, prep); break;
+            case NGU_ACT_QUICKGELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_NONE>(v, ax, bias_s, p.alpha, outp, prep); break;
+            case NGU_ACT_QUICKGELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_RESIDUAL>(v, ax, bias_s, p.alpha, outp, prep); break;
+            case NGU_ACT_QUICKGELU * 3 + NGU_AUX_DACT: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_DACT>(v, ax, bias_s, p.alpha, outp, prep); break;
+            default: epi_chunk<NGU_ACT_NONE, NGU_AUX_NONE>(v, ax, bias_s, p.alpha, outp, prep); break;
+          }
+        }
+
+        // registers -> swizzled slab -> TMA store (per-warp 32 x 64 box)
+        const uint32_t slab = (p.save_pre || (g & 1u) == 0) ? slab0 : slab1;
+        if (lane == 0) {
+          if (p.save_pre) tma_store_wait_read<0>();
+          else tma_store_wait_read<1>();
+        }
+        __syncwarp();
+        const uint32_t rbase = slab + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t a = rbase + (uint32_t(j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(outp[4 * j]),
+                       "r"(outp[4 * j + 1]), "r"(outp[4 * j + 2]), "r"(outp[4 * j + 3])
+                       : "memory");
+        }
+        if (p.save_pre) {
+          const uint32_t rb1 = slab1 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = rb1 + (uint32_t(j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(prep[4 * j]),
+                         "r"(prep[4 * j + 1]), "r"(prep[4 * j + 2]), "r"(prep[4 * j + 3])
+                         : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.tmC, slab, nc, m0 + q * 32);
+          if (p.save_pre) tma_store_2d(&p.tmPre, slab1, nc, m0 + q * 32);
+          tma_store_commit();
+        }
+        ++g;
+      }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BLOCK_N>
+int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  GemmKernelParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&p.tmA, a.A, a.M, a.K, a.lda, BLOCK_M, BLOCK_K, true))) return rc;
+  if ((rc = make_tmap_2d_bf16(&p.tmB, a.B, a.N, a.K, a.ldb, BLOCK_N, BLOCK_K, true))) return rc;
+  if (a.K2 > 0) {
+    if ((rc = make_tmap_2d_bf16(&p.tmA2, a.A2, a.M, a.K2, a.lda2, BLOCK_M, BLOCK_K, true))) return rc;
+    if ((rc = make_tmap_2d_bf16(&p.tmB2, a.B2, a.N, a.K2, a.ldb2, BLOCK_N, BLOCK_K, true))) return rc;
+  } else {
+    p.tmA2 = p.tmA;
+    p.tmB2 = p.tmB;
+  }
+  if ((rc = make_tmap_2d_bf16(&p.tmC, a.C, a.M, a.N, a.ldc, 32, 64, true))) return rc;
+  if (a.save_pre) {
+    if ((rc = make_tmap_2d_bf16(&p.tmPre, a.Pre, a.M, a.N, a.ldpre, 32, 64, true))) return rc;
+  } else {
+    p.tmPre = p.tmC;
+  }
+  p.bias = a.bias;
+  p.aux = reinterpret_cast<const bf16*>(a.aux);
+  p.ldaux = a.ldaux;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.K2 = a.K2;
+  p.act = a.act; p.aux_mode = a.aux_mode; p.save_pre = a.save_pre;
+  p.alpha = a.alpha;
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return cuda_status(e, "gemm_tc smem attribute");
+    attr_done = true;
+  }
+  const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
+  int grid = m_tiles * n_tiles;
+  const int sms = sm_count();
+  if (grid > sms) grid = sms;
+  gemm_tc_kernel<BLOCK_N><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
+  return check_launch("gemm_tc");
+}
+
+}  // namespace
+
+int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) { set_last_error("gemm_tc: empty problem M=%d N=%d K=%d", a.M, a.N, a.K); return NGU_ERR_SHAPE; }
+  if ((a.K % 8) || (a.lda % 8) || (a.ldb % 8) || (a.ldc % 8) || (a.K2 % 8)) {
+    set_last_error("gemm_tc: K, K2 and leading dimensions must be multiples of 8 (16-byte rows)");
+    return NGU_ERR_ALIGN;
+  }
+  if (a.aux_mode != NGU_AUX_NONE && (a.aux == nullptr || (a.ldaux % 8) || (a.N % 8))) {
+    set_last_error("gemm_tc: aux operand needs a pointer, ldaux %% 8 == 0 and N %% 8 == 0");
+    return NGU_ERR_ALIGN;
+  }
+  int bn = a.block_n;
+  if (bn == 0) bn = (a.N > 128) ? 256 : (a.N > 64 ? 128 : 64);
+  switch (bn) {
+    case 256: return launch_gemm_tc<256>(a, stream);
+    case 128: return launch_gemm_tc<128>(a, stream);
+    case 64: return launch_gemm_tc<64>(a, stream);
+    default: set_last_error("gemm_tc: unsupported block_n %d", bn); return NGU_ERR_ARG;
+  }
+}
+
+}  // namespace ngu

@@ -82,6 +82,141 @@ typedef struct ngu_gemm_desc {
 } ngu_gemm_desc;
 int ngu_gemm(const ngu_gemm_desc* d, void* stream);
 
+/*
+ * LayerNorm forward (+ optional Mona pre-scale).  One call replaces nn.LayerNorm (timm Block norm1 /
+ * norm2 / trunk.norm, eps 1e-6, pinned dep; CLIP LayerNorm src/third_party/openai_clip/model.py:163-169)
+ * and, with gamma/gammax set, the Mona input mix  src/adapters/mona.py:125
+ *     y = (xhat * w + b) * gamma + x * gammax.
+ * Rows may be strided (ldx / ldy elements) so the CLS rows of [B,N,D] can be normalised in place.
+ * mean / rstd (fp32 [M]) are saved for backward when non-NULL.
+ */
+typedef struct ngu_ln_desc {
+  const void* x; int64_t ldx;
+  void* y;       int64_t ldy;
+  const float* w; const float* b;          /* [D] */
+  const float* gamma; const float* gammax; /* [D] or both NULL */
+  float* mean; float* rstd;                /* [M] or NULL */
+  int M, D; float eps; int dtype;
+} ngu_ln_desc;
+int ngu_ln_fwd(const ngu_ln_desc* d, void* stream);
+
+/* LayerNorm backward with frozen affine: dx = LNbwd(g; x, mean, rstd, w) (+ dres).  The base model's
+ * norms are frozen in Mona/LoRA fine-tuning (src/models/biomedclip/finetune.py:166-175) so no dw/db. */
+typedef struct ngu_ln_bwd_desc {
+  const void* g; int64_t ldg;
+  const void* x; int64_t ldx;
+  const void* dres; int64_t ldr;  /* optional residual-stream gradient added to dx */
+  void* dx; int64_t lddx;
+  const float* mean; const float* rstd; const float* w;
+  int M, D; int dtype;
+} ngu_ln_bwd_desc;
+int ngu_ln_bwd(const ngu_ln_bwd_desc* d, void* stream);
+
+/* Backward of the Mona input mix + residual (src/adapters/mona.py:124-125,150):
+ *   dx = dy + du*gammax + LNbwd(du*gamma);  dw/db/dgamma/dgammax/dycol are fp32 [D], ACCUMULATED (+=). */
+typedef struct ngu_mona_pre_bwd_desc {
+  const void* du; const void* dy; const void* x;
+  const float* mean; const float* rstd;
+  const float* w; const float* b; const float* gamma; const float* gammax;
+  void* dx;
+  float* dw; float* db; float* dgamma; float* dgammax; float* dycol;
+  int M, D; int dtype;
+} ngu_mona_pre_bwd_desc;
+int ngu_mona_pre_bwd(const ngu_mona_pre_bwd_desc* d, void* stream);
+
+/*
+ * Mona bottleneck stage between project1 and project2: merged depthwise 3x3+5x5+7x7 stencil,
+ * 1x1 projector, GELU, dropout — src/adapters/mona.py:85-93 (BaselineMonaOp) and :129-147.
+ * h, g, dg, dh: [B, N, C] with N = has_cls + H*W.  Weights/grads fp32 in the reference's own
+ * parameter shapes (conv{1,2,3}.weight [C,1,k,k], projector.weight [C,C,1,1]); grads ACCUMULATE.
+ * db1 receives the column sum of dh (= d project1.bias).
+ */
+typedef struct ngu_mona_conv_weights {
+  const float* k3; const float* b3; const float* k5; const float* b5; const float* k7; const float* b7;
+  const float* P; const float* bp;
+} ngu_mona_conv_weights;
+typedef struct ngu_mona_conv_grads {
+  float* dk3; float* db3; float* dk5; float* db5; float* dk7; float* db7; float* dP; float* dbp; float* db1;
+} ngu_mona_conv_grads;
+typedef struct ngu_mona_conv_desc {
+  const void* h; void* g;          /* forward: h -> g */
+  const void* dg; void* dh;        /* backward: (h, dg) -> dh + grads */
+  ngu_mona_conv_weights w;
+  ngu_mona_conv_grads gr;
+  int B, N, H, W, C, has_cls;
+  float drop_p; uint64_t seed;     /* dropout p (0 = eval) and Philox seed; backward regenerates the mask */
+  int dtype;
+} ngu_mona_conv_desc;
+int ngu_mona_conv_fwd(const ngu_mona_conv_desc* d, void* stream);
+int ngu_mona_conv_bwd(const ngu_mona_conv_desc* d, void* stream);
+
+/*
+ * Attention core softmax(q k^T * scale) v, forward and backward (recompute from saved LSE).
+ * Replaces F.scaled_dot_product_attention in timm Attention (pinned dep) and
+ * src/adapters/lora.py:188-190, and nn.MultiheadAttention's core in
+ * src/third_party/openai_clip/model.py:195-197.  q/k/v/o are addressed as
+ * ptr + b*bs + n*ts + head*dh (+ d), so the fused timm qkv buffer [B,N,3,H,dh], separate q/k/v
+ * tensors and the sequence-first [N,B,D] layout are all expressible.  lse: fp32 [B,H,N].
+ */
+typedef struct ngu_attn_desc {
+  const void* q; int64_t q_bs, q_ts;
+  const void* k; int64_t k_bs, k_ts;
+  const void* v; int64_t v_bs, v_ts;
+  void* o;       int64_t o_bs, o_ts;
+  float* lse;
+  const void* d_o;            /* backward: grad of o (same strides as o) */
+  void* dq; void* dk; void* dv; /* backward outputs (same strides as q / k / v) */
+  int B, H, N, S, dh;
+  float scale; int causal;
+  int dtype;
+  int impl;                   /* 0 = default for dtype (bf16: tcgen05, fp32: CUDA cores); 1 = force CUDA cores */
+} ngu_attn_desc;
+int ngu_attn_fwd(const ngu_attn_desc* d, void* stream);
+int ngu_attn_bwd(const ngu_attn_desc* d, void* stream);
+
+/*
+ * InfoNCE — src/losses/losses.py:23-47.  Three calls so the all-gather of the normalised features can
+ * sit between them (single GPU: Bg == Bl, r0 == 0):
+ *   ngu_infonce_normalize : xhat (fp32, written at the caller's row offset of the gather buffer), norms
+ *   ngu_infonce_core      : loss (global mean, fp32 scalar) + d loss / d xhat for the local rows
+ *   ngu_infonce_normalize_bwd : d loss / d x for the local rows (times *gscale, the upstream scalar grad)
+ * ws: fp32 workspace of 2*Bg*Bg + 2*Bg elements.
+ */
+int ngu_infonce_normalize(const void* x, float* xhat, float* norm, int B, int E, int dtype, void* stream);
+typedef struct ngu_infonce_desc {
+  const float* ihat; const float* that;   /* [Bg, E] gathered, normalised */
+  float* dihat; float* dthat;             /* [Bl, E] or NULL (forward only) */
+  float* loss; float* ws;
+  int Bg, Bl, r0, E;
+  float temperature;
+} ngu_infonce_desc;
+int ngu_infonce_core(const ngu_infonce_desc* d, void* stream);
+int ngu_infonce_normalize_bwd(const float* dxhat, const float* xhat, const float* norm, const float* gscale,
+                              void* dx, int B, int E, int dtype, void* stream);
+
+/* Weight gradient of a trainable projection: D[Mo,No] += X[T,Mo]^T · Y[T,No]  (fp32 accumulate).
+ * Mona project1/project2 and LoRA A/B grads (autograd of src/adapters/mona.py:127,148, lora.py:86). */
+int ngu_wgrad(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int T, int Mo, int No,
+              int dtype, int impl, void* stream);
+/* out[C] += column sums of X[T,C] (bias gradients) */
+int ngu_colsum(const void* X, int ldx, float* out, int T, int C, int dtype, void* stream);
+
+/* out = (accumulate ? out : 0) + x * keep_mask(seed) / (1-p): LoRA input dropout (src/adapters/lora.py:82-83) and its
+ * backward (same mask from the same seed). */
+int ngu_dropout(const void* x, void* out, int64_t n, float p, uint64_t seed, int accumulate, int dtype, void* stream);
+
+/* Patch-embed im2col (stride == kernel, timm PatchEmbed / CLIP conv1): images fp32 NCHW [B,3,R,R]
+ * -> [B*(R/P)^2, 3*P*P]; and token assembly x0[b,0]=cls+pos[0], x0[b,1+p]=patch[b,p]+pos[1+p]. */
+int ngu_patchify(const float* img, void* out, int B, int R, int P, int dtype, void* stream);
+int ngu_assemble_tokens(const void* patch, const float* cls, const float* pos, void* out, int B, int np, int D,
+                        int dtype, void* stream);
+/* BERT input embeddings (HF BertEmbeddings before its LayerNorm; text tower of open_clip HFTextEncoder, pinned dep):
+ * out[b,s,:] = word[ids[b,s]] + pos[s] + type0.  ids int64 [B,S]; tables fp32. */
+int ngu_embed_tokens(const int64_t* ids, const float* word, const float* pos, const float* type0, void* out, int B, int S,
+                     int D, int vocab, int dtype, void* stream);
+/* out (dtype) = scale * in (fp32 [rows, cols]), optionally transposed to [cols, rows] */
+int ngu_cast_f32(const float* in, void* out, int rows, int cols, int transpose, float scale, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,95 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
+_i64, _u64 = ctypes.c_int64, ctypes.c_uint64
+
+
+class LnDesc(ctypes.Structure):
+    _fields_ = [("x", _c_void_p), ("ldx", _i64), ("y", _c_void_p), ("ldy", _i64),
+                ("w", _c_void_p), ("b", _c_void_p), ("gamma", _c_void_p), ("gammax", _c_void_p),
+                ("mean", _c_void_p), ("rstd", _c_void_p),
+                ("M", _c_int), ("D", _c_int), ("eps", _c_float), ("dtype", _c_int)]
+
+
+class LnBwdDesc(ctypes.Structure):
+    _fields_ = [("g", _c_void_p), ("ldg", _i64), ("x", _c_void_p), ("ldx", _i64),
+                ("dres", _c_void_p), ("ldr", _i64), ("dx", _c_void_p), ("lddx", _i64),
+                ("mean", _c_void_p), ("rstd", _c_void_p), ("w", _c_void_p),
+                ("M", _c_int), ("D", _c_int), ("dtype", _c_int)]
+
+
+class MonaPreBwdDesc(ctypes.Structure):
+    _fields_ = [("du", _c_void_p), ("dy", _c_void_p), ("x", _c_void_p),
+                ("mean", _c_void_p), ("rstd", _c_void_p),
+                ("w", _c_void_p), ("b", _c_void_p), ("gamma", _c_void_p), ("gammax", _c_void_p),
+                ("dx", _c_void_p),
+                ("dw", _c_void_p), ("db", _c_void_p), ("dgamma", _c_void_p), ("dgammax", _c_void_p), ("dycol", _c_void_p),
+                ("M", _c_int), ("D", _c_int), ("dtype", _c_int)]
+
+
+class MonaConvWeights(ctypes.Structure):
+    _fields_ = [(n, _c_void_p) for n in ("k3", "b3", "k5", "b5", "k7", "b7", "P", "bp")]
+
+
+class MonaConvGrads(ctypes.Structure):
+    _fields_ = [(n, _c_void_p) for n in ("dk3", "db3", "dk5", "db5", "dk7", "db7", "dP", "dbp", "db1")]
+
+
+class MonaConvDesc(ctypes.Structure):
+    _fields_ = [("h", _c_void_p), ("g", _c_void_p), ("dg", _c_void_p), ("dh", _c_void_p),
+                ("w", MonaConvWeights), ("gr", MonaConvGrads),
+                ("B", _c_int), ("N", _c_int), ("H", _c_int), ("W", _c_int), ("C", _c_int), ("has_cls", _c_int),
+                ("drop_p", _c_float), ("seed", _u64), ("dtype", _c_int)]
+
+
+class AttnDesc(ctypes.Structure):
+    _fields_ = [("q", _c_void_p), ("q_bs", _i64), ("q_ts", _i64),
+                ("k", _c_void_p), ("k_bs", _i64), ("k_ts", _i64),
+                ("v", _c_void_p), ("v_bs", _i64), ("v_ts", _i64),
+                ("o", _c_void_p), ("o_bs", _i64), ("o_ts", _i64),
+                ("lse", _c_void_p), ("d_o", _c_void_p),
+                ("dq", _c_void_p), ("dk", _c_void_p), ("dv", _c_void_p),
+                ("B", _c_int), ("H", _c_int), ("N", _c_int), ("S", _c_int), ("dh", _c_int),
+                ("scale", _c_float), ("causal", _c_int), ("dtype", _c_int), ("impl", _c_int)]
+
+
+class InfoNceDesc(ctypes.Structure):
+    _fields_ = [("ihat", _c_void_p), ("that", _c_void_p), ("dihat", _c_void_p), ("dthat", _c_void_p),
+                ("loss", _c_void_p), ("ws", _c_void_p),
+                ("Bg", _c_int), ("Bl", _c_int), ("r0", _c_int), ("E", _c_int), ("temperature", _c_float)]
+
+
+# every symbol include/ngu_b200.h declares: name -> (restype, argtypes)
+def _P(t):
+    return ctypes.POINTER(t)
+
+
+PROTOTYPES = {
+    "ngu_version": (_c_int, []),
+    "ngu_last_error": (ctypes.c_char_p, []),
+    "ngu_launch_count": (_i64, []),
+    "ngu_selftest_device": (_c_int, []),
+    "ngu_gemm": (_c_int, [_P(GemmDesc), _c_void_p]),
+    "ngu_ln_fwd": (_c_int, [_P(LnDesc), _c_void_p]),
+    "ngu_ln_bwd": (_c_int, [_P(LnBwdDesc), _c_void_p]),
+    "ngu_mona_pre_bwd": (_c_int, [_P(MonaPreBwdDesc), _c_void_p]),
+    "ngu_mona_conv_fwd": (_c_int, [_P(MonaConvDesc), _c_void_p]),
+    "ngu_mona_conv_bwd": (_c_int, [_P(MonaConvDesc), _c_void_p]),
+    "ngu_attn_fwd": (_c_int, [_P(AttnDesc), _c_void_p]),
+    "ngu_attn_bwd": (_c_int, [_P(AttnDesc), _c_void_p]),
+    "ngu_infonce_normalize": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "ngu_infonce_core": (_c_int, [_P(InfoNceDesc), _c_void_p]),
+    "ngu_infonce_normalize_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "ngu_wgrad": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "ngu_colsum": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "ngu_dropout": (_c_int, [_c_void_p, _c_void_p, _i64, _c_float, _u64, _c_int, _c_int, _c_void_p]),
+    "ngu_patchify": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "ngu_assemble_tokens": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "ngu_embed_tokens": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "ngu_cast_f32": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_int, _c_void_p]),
+}
+
+
 class NguError(RuntimeError):
     pass
 
@@ -50,12 +139,10 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). There is no CPU fallback.")
         h = ctypes.CDLL(LIB_PATH)
-        h.ngu_version.restype = _c_int
-        h.ngu_last_error.restype = ctypes.c_char_p
-        h.ngu_launch_count.restype = ctypes.c_int64
-        h.ngu_selftest_device.restype = _c_int
-        h.ngu_gemm.argtypes = [ctypes.POINTER(GemmDesc), _c_void_p]
-        h.ngu_gemm.restype = _c_int
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(h, name)  # AttributeError here = header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
         _lib = h
     return _lib
 

@@ -1,0 +1,4 @@
+from .mona import (BaselineMona, BaselineMonaOp, BatchFirstMonaWrapper, inject_mona_variant_to_clip,  # noqa: F401
+                   inject_mona_variant_to_open_clip)
+from .lora import (LoRALayer, LinearLoRA, PlainMultiheadAttentionLoRA, inject_lora_to_clip,  # noqa: F401
+                   inject_lora_to_biomedclip)

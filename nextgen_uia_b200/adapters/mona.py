@@ -1,0 +1,221 @@
+"""Mona adapter on the B200 kernels — host-side mirror of the reference's src/adapters/mona.py.
+
+Kept identical to the reference (so it is a drop-in and checkpoints interchange):
+  * class names, constructor signatures, forward(x, hw_shapes) call convention ([N,B,D] in/out for the
+    adapter, [B,N,D] for BatchFirstMonaWrapper) — reference mona.py:38-67, :96-151
+  * parameter names / shapes / creation order / initialisers: project1, project2, adapter_conv.conv{1,2,3},
+    adapter_conv.projector, norm, gamma (1e-6), gammax (1) — mona.py:78-83, :104-113; the modules are
+    real nn.Linear / nn.Conv2d / nn.LayerNorm instances used purely as parameter containers, so the CPU
+    RNG stream consumed at construction and the state-dict keys match the reference bit for bit.
+  * inject_mona_variant_to_{clip,open_clip}(model, variant, bottleneck_dim, num_layers) -> (model, count)
+    — mona.py:495-575, :578-680 (attaches `block.mona`, wraps the *instance* forward, passes **kwargs).
+Different: forward never touches ATen math.  It runs
+  LN+mix kernel -> tcgen05 GEMM (project1) -> one-CTA-per-image stencil/projector/GELU/dropout kernel
+  -> tcgen05 GEMM (project2, residual fused)   and a hand-written backward (see MonaFunction).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .. import ops
+
+_LN_EPS = 1e-5  # nn.LayerNorm default used by the reference adapter (mona.py:111)
+
+
+def _next_seed():
+    # dropout seeds come from torch's CPU generator so torch.manual_seed() makes runs reproducible
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+class MonaFunction(torch.autograd.Function):
+    """y = x + project2(dropout(gelu(convstage(project1(LN(x)*gamma + x*gammax)))))  on [B,N,D]."""
+
+    @staticmethod
+    def forward(ctx, x, norm_w, norm_b, gamma, gammax, w1, b1, k3, b3, k5, b5, k7, b7, pw, pb, w2, b2,
+                hw, has_cls, drop_p, seed):
+        B, N, D = x.shape
+        C = w1.shape[0]
+        x2 = x.contiguous().view(B * N, D)
+        dt = x2.dtype
+        u, mean, rstd = ops.ln_fwd(x2, norm_w, norm_b, _LN_EPS, gamma=gamma, gammax=gammax)
+        h = ops.gemm(u, ops.cast(w1, dt), bias=b1)                                   # [M, C]
+        conv_w = (k3, b3, k5, b5, k7, b7, pw, pb)
+        g = ops.mona_conv_fwd(h.view(B, N, C), conv_w, hw, has_cls, drop_p, seed)     # [B, N, C]
+        y = ops.gemm(g.view(B * N, C), ops.cast(w2, dt), bias=b2, aux=x2, aux_mode=L.AUX_RESIDUAL)
+        ctx.save_for_backward(x2, mean, rstd, u, h, g, norm_w, norm_b, gamma, gammax, w1, k3, b3, k5, b5, k7, b7, pw, pb, w2)
+        ctx.meta = (B, N, D, C, hw, has_cls, drop_p, seed)
+        return y.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2, mean, rstd, u, h, g, norm_w, norm_b, gamma, gammax, w1, k3, b3, k5, b5, k7, b7, pw, pb, w2) = ctx.saved_tensors
+        B, N, D, C, hw, has_cls, drop_p, seed = ctx.meta
+        dev, dt = x2.device, x2.dtype
+        dy2 = dy.contiguous().view(B * N, D)
+        z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        # project2:  y = x + g W2^T + b2
+        dg = ops.gemm(dy2, ops.cast(w2, dt, transpose=True))                          # [M, C] = dy W2
+        g2 = g.view(B * N, C)
+        dw2 = ops.wgrad(dy2, g2)                                                      # [D, C]
+        # conv stage (recomputes z / a from h), also yields d project1.bias
+        dk3, db3, dk5, db5, dk7, db7 = z(*k3.shape), z(C), z(*k5.shape), z(C), z(*k7.shape), z(C)
+        dpw, dpb, db1 = z(*pw.shape), z(C), z(C)
+        dh = ops.mona_conv_bwd(h.view(B, N, C), dg.view(B, N, C), (k3, b3, k5, b5, k7, b7, pw, pb),
+                               (dk3, db3, dk5, db5, dk7, db7, dpw, dpb, db1), hw, has_cls, drop_p, seed)
+        dh2 = dh.view(B * N, C)
+        # project1:  h = u W1^T + b1
+        dw1 = ops.wgrad(u, dh2).t().contiguous()                                      # [C, D]
+        du = ops.gemm(dh2, ops.cast(w1, dt, transpose=True))                          # [M, D] = dh W1
+        # LN mix + residual
+        dnw, dnb, dgam, dgamx, db2 = z(D), z(D), z(D), z(D), z(D)
+        dx = ops.mona_pre_bwd(du, dy2, x2, mean, rstd, norm_w, norm_b, gamma, gammax, dnw, dnb, dgam, dgamx, db2)
+        return (dx.view(B, N, D), dnw, dnb, dgam, dgamx, dw1, db1, dk3, db3, dk5, db5, dk7, db7, dpw, dpb, dw2, db2,
+                None, None, None, None)
+
+
+class BaselineMonaOp(nn.Module):
+    """Parameter container for the multi-scale depthwise stage (reference mona.py:75-93).
+    forward() exists for API parity (NCHW in/out) and runs the same fused stage kernel."""
+
+    def __init__(self, in_features):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_features, in_features, kernel_size=3, padding=1, groups=in_features)
+        self.conv2 = nn.Conv2d(in_features, in_features, kernel_size=5, padding=2, groups=in_features)
+        self.conv3 = nn.Conv2d(in_features, in_features, kernel_size=7, padding=3, groups=in_features)
+        self.projector = nn.Conv2d(in_features, in_features, kernel_size=1)
+
+    def stage_weights(self):
+        return (self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+                self.conv3.weight, self.conv3.bias, self.projector.weight, self.projector.bias)
+
+
+class BaselineMona(nn.Module):
+    """Baseline Mona adapter.  forward(x [N,B,D], hw_shapes) -> [N,B,D]   (reference mona.py:96-151)."""
+
+    def __init__(self, in_dim, bottleneck_dim=64):
+        super().__init__()
+        self.project1 = nn.Linear(in_dim, bottleneck_dim)
+        self.nonlinear = torch.nn.functional.gelu  # attribute kept for parity; the kernel applies exact-erf GELU
+        self.project2 = nn.Linear(bottleneck_dim, in_dim)
+        self.dropout = nn.Dropout(p=0.1)
+        self.adapter_conv = BaselineMonaOp(bottleneck_dim)
+        self.norm = nn.LayerNorm(in_dim)
+        self.gamma = nn.Parameter(torch.ones(in_dim) * 1e-6)
+        self.gammax = nn.Parameter(torch.ones(in_dim))
+
+    def forward_batch_first(self, xb, hw_shapes=None):
+        """[B,N,D] -> [B,N,D]; the layout the kernels work in."""
+        B, N, D = xb.shape
+        if hw_shapes is not None:
+            hw, has_cls = (int(hw_shapes[0]), int(hw_shapes[1])), True
+        else:  # all tokens form a sqrt(n) x sqrt(n) grid, no CLS (reference mona.py:140-144)
+            s = int(math.sqrt(N))
+            hw, has_cls = (s, s), False
+        p = self.dropout.p if (self.training and self.dropout.p > 0) else 0.0
+        seed = _next_seed() if p > 0 else 0
+        c = self.adapter_conv
+        return MonaFunction.apply(xb, self.norm.weight, self.norm.bias, self.gamma, self.gammax,
+                                  self.project1.weight, self.project1.bias,
+                                  c.conv1.weight, c.conv1.bias, c.conv2.weight, c.conv2.bias, c.conv3.weight, c.conv3.bias,
+                                  c.projector.weight, c.projector.bias,
+                                  self.project2.weight, self.project2.bias, hw, has_cls, p, seed)
+
+    def forward(self, x, hw_shapes=None):
+        return self.forward_batch_first(x.permute(1, 0, 2), hw_shapes).permute(1, 0, 2)
+
+
+class BatchFirstMonaWrapper(nn.Module):
+    """[B,N,D] adapter for open_clip-style trunks; attribute name `clip_mona` is part of the checkpoint
+    key format (reference mona.py:38-67)."""
+
+    def __init__(self, mona_adapter):
+        super().__init__()
+        self.clip_mona = mona_adapter
+
+    def forward(self, x, hw_shapes=None):
+        m = self.clip_mona
+        if hasattr(m, "forward_batch_first"):
+            return m.forward_batch_first(x, hw_shapes)  # skip the two cancelling permutes
+        return m(x.permute(1, 0, 2), hw_shapes).permute(1, 0, 2)
+
+
+_VARIANTS = {"baseline": BaselineMona}
+
+
+def register_variant(name, cls):
+    _VARIANTS[name] = cls
+
+
+def _variant_class(variant):
+    if variant not in _VARIANTS:
+        raise ValueError(f"Unknown variant: {variant}. Choose from {list(_VARIANTS.keys())}")
+    return _VARIANTS[variant]
+
+
+def _wrap_block_forward(block, hw_shapes):
+    inner = block.forward
+
+    def forward_with_mona(x, **kwargs):
+        return block.mona(inner(x, **kwargs), hw_shapes)
+
+    block.forward = forward_with_mona
+
+
+def inject_mona_variant_to_clip(model, variant="hybrid", bottleneck_dim=64, num_layers=None):
+    """OpenAI-CLIP layout (visual.transformer.resblocks, [N,B,D]); reference mona.py:495-575."""
+    cls = _variant_class(variant)
+    count = 0
+    visual = getattr(model, "visual", None)
+    if visual is not None and hasattr(visual, "transformer"):
+        tr = visual.transformer
+        if hasattr(visual, "input_resolution"):
+            res = visual.input_resolution
+        elif hasattr(visual, "image_size"):
+            res = visual.image_size[0] if isinstance(visual.image_size, tuple) else visual.image_size
+        else:
+            raise AttributeError("Model does not have input_resolution or image_size attribute")
+        grid = res // visual.conv1.kernel_size[0]
+        if hasattr(tr, "resblocks"):
+            blocks = tr.resblocks
+            n = len(blocks) if num_layers is None else min(num_layers, len(blocks))
+            for i in range(n):
+                blocks[i].mona = cls(tr.width, bottleneck_dim)
+                _wrap_block_forward(blocks[i], (grid, grid))
+                count += 1
+    print(f"✓ Injected {variant} MONA adapters to {count} layers (OpenAI CLIP vision encoder)")
+    return model, count
+
+
+def inject_mona_variant_to_open_clip(model, variant="hybrid", bottleneck_dim=64, num_layers=None):
+    """open_clip layout (visual.trunk.blocks for timm towers, visual.transformer.resblocks otherwise), [B,N,D];
+    reference mona.py:578-680."""
+    cls = _variant_class(variant)
+    count = 0
+    visual = getattr(model, "visual", None)
+    if visual is not None:
+        blocks = dim = hw = None
+        if hasattr(visual, "trunk"):
+            trunk = visual.trunk
+            dim = trunk.embed_dim
+            g = int(math.sqrt(trunk.patch_embed.num_patches))
+            hw = (g, g)
+            blocks = getattr(trunk, "blocks", None)
+        elif hasattr(visual, "transformer"):
+            dim = visual.transformer.width
+            if hasattr(visual, "grid_size"):
+                hw = (visual.grid_size[0], visual.grid_size[0])
+            elif hasattr(visual, "image_size") and hasattr(visual, "patch_size"):
+                im = visual.image_size[0] if isinstance(visual.image_size, tuple) else visual.image_size
+                ps = visual.patch_size[0] if isinstance(visual.patch_size, tuple) else visual.patch_size
+                hw = (im // ps, im // ps)
+            blocks = getattr(visual.transformer, "resblocks", None)
+        if blocks is not None and dim is not None:
+            n = len(blocks) if num_layers is None else min(num_layers, len(blocks))
+            for i in range(n):
+                blocks[i].mona = BatchFirstMonaWrapper(cls(dim, bottleneck_dim))
+                _wrap_block_forward(blocks[i], hw)
+                count += 1
+    print(f"✓ Injected {variant} MONA adapters to {count} layers (open_clip vision encoder)")
+    return model, count

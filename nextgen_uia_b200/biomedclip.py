@@ -1,0 +1,201 @@
+"""BiomedCLIP-shaped model (open_clip CustomTextCLIP layout) assembled on the B200 kernels.
+
+open_clip / timm / transformers' BERT are un-vendored pinned dependencies of the reference
+(`create_model_from_pretrained("hf-hub:microsoft/BiomedCLIP-PubMedBERT_256-vit_base_patch16_224")`,
+src/models/biomedclip/finetune.py:116).  This module restates the *structure* the reference touches:
+    model.visual.trunk (timm ViT-B/16), model.visual.head.proj (768->512, no bias),
+    model.text.transformer (BERT-base: embeddings / encoder.layer[i].attention.{self.{query,key,value},
+    output.{dense,LayerNorm}} / intermediate.dense / output.{dense,LayerNorm}), model.text.proj
+    (CLS pooler + MLP 768->640->GELU->512, no biases), encode_image / encode_text, logit_scale.
+Weights are synthetic unless loaded from a state dict with these (open_clip) key names.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .linear import frozen_copies
+from .vit import VisionTransformer, HeadFunction
+
+
+class _Head(nn.Module):
+    def __init__(self, dim, out_dim):
+        super().__init__()
+        self.proj = nn.Linear(dim, out_dim, bias=False)
+
+
+class TimmVisual(nn.Module):
+    """open_clip TimmModel: trunk + head (pool = CLS token, proj = linear without bias)."""
+
+    def __init__(self, embed_dim=512, **vit_kw):
+        super().__init__()
+        self.trunk = VisionTransformer(**vit_kw)
+        self.head = _Head(self.trunk.embed_dim, embed_dim)
+
+    def forward(self, images):
+        x = self.trunk.forward_features(images)
+        return HeadFunction.apply(x, self.trunk.norm, self.head.proj)
+
+
+# ---- BERT-shaped parameter containers (HF attribute names; forward is the fused kernel pipeline below) ----
+class _BertSelfAttention(nn.Module):
+    def __init__(self, d, heads):
+        super().__init__()
+        self.num_attention_heads = heads
+        self.query, self.key, self.value = nn.Linear(d, d), nn.Linear(d, d), nn.Linear(d, d)
+
+
+class _BertSelfOutput(nn.Module):
+    def __init__(self, d, eps):
+        super().__init__()
+        self.dense = nn.Linear(d, d)
+        self.LayerNorm = nn.LayerNorm(d, eps=eps)
+
+
+class _BertAttention(nn.Module):
+    def __init__(self, d, heads, eps):
+        super().__init__()
+        self.self = _BertSelfAttention(d, heads)
+        self.output = _BertSelfOutput(d, eps)
+
+
+class _BertIntermediate(nn.Module):
+    def __init__(self, d, dm):
+        super().__init__()
+        self.dense = nn.Linear(d, dm)
+
+
+class _BertOutput(nn.Module):
+    def __init__(self, d, dm, eps):
+        super().__init__()
+        self.dense = nn.Linear(dm, d)
+        self.LayerNorm = nn.LayerNorm(d, eps=eps)
+
+
+class _BertLayer(nn.Module):
+    def __init__(self, d, heads, dm, eps):
+        super().__init__()
+        self.attention = _BertAttention(d, heads, eps)
+        self.intermediate = _BertIntermediate(d, dm)
+        self.output = _BertOutput(d, dm, eps)
+
+
+class _BertEncoder(nn.Module):
+    def __init__(self, layers, d, heads, dm, eps):
+        super().__init__()
+        self.layer = nn.ModuleList([_BertLayer(d, heads, dm, eps) for _ in range(layers)])
+
+
+class _BertEmbeddings(nn.Module):
+    def __init__(self, vocab, d, max_pos, eps):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(vocab, d, padding_idx=0)
+        self.position_embeddings = nn.Embedding(max_pos, d)
+        self.token_type_embeddings = nn.Embedding(2, d)
+        self.LayerNorm = nn.LayerNorm(d, eps=eps)
+
+
+class BertModel(nn.Module):
+    def __init__(self, vocab=30522, d=768, layers=12, heads=12, dm=3072, max_pos=512, eps=1e-12):
+        super().__init__()
+        self.embeddings = _BertEmbeddings(vocab, d, max_pos, eps)
+        self.encoder = _BertEncoder(layers, d, heads, dm, eps)
+
+
+class HFTextEncoder(nn.Module):
+    """open_clip HFTextEncoder with `cls_last_hidden_state_pooler` and `mlp` projection (BiomedCLIP config)."""
+
+    def __init__(self, embed_dim=512, d=768, pad_token_id=0, **bert_kw):
+        super().__init__()
+        self.transformer = BertModel(d=d, **bert_kw)
+        hidden = (d + embed_dim) // 2
+        self.proj = nn.Sequential(nn.Linear(d, hidden, bias=False), nn.GELU(), nn.Linear(hidden, embed_dim, bias=False))
+        self.pad_token_id = pad_token_id
+        self.compute_dtype = torch.bfloat16
+
+    def _qkv_weights(self, sa, dt):
+        """Fused [3d, d] q/k/v weight + bias (frozen), cached on the module."""
+        key = (dt, sa.query.weight.device, sa.query.weight._version, sa.key.weight._version, sa.value.weight._version)
+        c = getattr(sa, "_ngu_qkv", None)
+        if c is None or c[0] != key:
+            w = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0).detach().float().contiguous()
+            b = torch.cat([sa.query.bias, sa.key.bias, sa.value.bias], 0).detach().float().contiguous()
+            c = (key, ops.cast(w, dt), b)
+            sa._ngu_qkv = c
+        return c[1], c[2]
+
+    @torch.no_grad()
+    def forward(self, ids):
+        """ids int64 [B,S] -> [B, embed_dim].  Frozen tower: forward only, no autograd graph
+        (src/models/biomedclip/finetune.py:166-167 freezes it; no parameter requires grad)."""
+        if any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("ngu B200 path: the text tower is forward-only (frozen); tune_text_encoder is not on this path")
+        if bool((ids == self.pad_token_id).any()):
+            raise NotImplementedError("padded token batches need the key-padding mask path (not built yet)")
+        tr = self.transformer
+        dt = self.compute_dtype
+        B, S = ids.shape
+        emb = tr.embeddings
+        d = emb.word_embeddings.weight.shape[1]
+        x = ops.embed_tokens(ids.contiguous(), emb.word_embeddings.weight.detach(), emb.position_embeddings.weight.detach(),
+                             emb.token_type_embeddings.weight.detach()[0].contiguous(), dt)
+        x, _, _ = ops.ln_fwd(x, emb.LayerNorm.weight.detach(), emb.LayerNorm.bias.detach(), emb.LayerNorm.eps, save_stats=False)
+        for lyr in tr.encoder.layer:
+            sa = lyr.attention.self
+            H = sa.num_attention_heads
+            Wqkv, bqkv = self._qkv_weights(sa, dt)
+            qkv = ops.gemm(x, Wqkv, bias=bqkv)
+            ao, _ = ops.attn_fwd_packed(qkv, B, S, H, d // H)
+            so = lyr.attention.output
+            y = ops.gemm(ao, frozen_copies(so.dense.weight, dt)[0], bias=so.dense.bias.detach(), aux=x, aux_mode=L.AUX_RESIDUAL)
+            x, _, _ = ops.ln_fwd(y, so.LayerNorm.weight.detach(), so.LayerNorm.bias.detach(), so.LayerNorm.eps, save_stats=False)
+            h = ops.gemm(x, frozen_copies(lyr.intermediate.dense.weight, dt)[0], bias=lyr.intermediate.dense.bias.detach(), act=L.ACT_GELU)
+            y = ops.gemm(h, frozen_copies(lyr.output.dense.weight, dt)[0], bias=lyr.output.dense.bias.detach(), aux=x, aux_mode=L.AUX_RESIDUAL)
+            x, _, _ = ops.ln_fwd(y, lyr.output.LayerNorm.weight.detach(), lyr.output.LayerNorm.bias.detach(), lyr.output.LayerNorm.eps, save_stats=False)
+        cls = x.view(B, S, d)[:, 0, :]                       # CLS pooling: strided rows feed the GEMM directly
+        h = ops.gemm(cls, frozen_copies(self.proj[0].weight, dt)[0], act=L.ACT_GELU)
+        return ops.gemm(h, frozen_copies(self.proj[2].weight, dt)[0])
+
+
+class BiomedCLIP(nn.Module):
+    """CustomTextCLIP-shaped container: .visual (TimmVisual), .text (HFTextEncoder), .logit_scale."""
+
+    def __init__(self, embed_dim=512, vision=None, text=None):
+        super().__init__()
+        self.visual = TimmVisual(embed_dim=embed_dim, **(vision or {}))
+        self.text = HFTextEncoder(embed_dim=embed_dim, **(text or {}))
+        self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
+        self.context_length = 256
+
+    def set_compute_dtype(self, dtype):
+        """torch.bfloat16 = tcgen05 product path; torch.float32 = fp32 check mode (CUDA cores)."""
+        self.visual.trunk.compute_dtype = dtype
+        self.text.compute_dtype = dtype
+        return self
+
+    def encode_image(self, image, normalize: bool = False):
+        f = self.visual(image)
+        return nn.functional.normalize(f, dim=-1) if normalize else f
+
+    def encode_text(self, text, normalize: bool = False):
+        f = self.text(text)
+        return nn.functional.normalize(f, dim=-1) if normalize else f
+
+
+def init_synthetic_(model, seed=1, std=0.02):
+    """Deterministic synthetic base weights: normal(0, std) for matrices/embeddings,
+    LayerNorm = (1, 0), biases normal(0, std).  Call BEFORE injecting adapters."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("logit_scale"):
+                continue
+            if "norm" in name.lower() and name.endswith("weight") and p.dim() == 1:
+                p.fill_(1.0)
+            elif "norm" in name.lower() and name.endswith("bias"):
+                p.zero_()
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * std)
+    return model

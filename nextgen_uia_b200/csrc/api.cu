@@ -36,4 +36,58 @@ int ngu_gemm(const ngu_gemm_desc* d, void* stream) {
   return NGU_ERR_DTYPE;
 }
 
+
+#define NGU_STREAM reinterpret_cast<cudaStream_t>(stream)
+#define NGU_NONNULL(d, name) if (!(d)) { set_last_error(name ": null descriptor"); return NGU_ERR_ARG; }
+
+int ngu_ln_fwd(const ngu_ln_desc* d, void* stream) { NGU_NONNULL(d, "ngu_ln_fwd"); return ln_fwd(*d, NGU_STREAM); }
+int ngu_ln_bwd(const ngu_ln_bwd_desc* d, void* stream) { NGU_NONNULL(d, "ngu_ln_bwd"); return ln_bwd(*d, NGU_STREAM); }
+int ngu_mona_pre_bwd(const ngu_mona_pre_bwd_desc* d, void* stream) { NGU_NONNULL(d, "ngu_mona_pre_bwd"); return mona_pre_bwd(*d, NGU_STREAM); }
+int ngu_mona_conv_fwd(const ngu_mona_conv_desc* d, void* stream) { NGU_NONNULL(d, "ngu_mona_conv_fwd"); return mona_conv_fwd(*d, NGU_STREAM); }
+int ngu_mona_conv_bwd(const ngu_mona_conv_desc* d, void* stream) { NGU_NONNULL(d, "ngu_mona_conv_bwd"); return mona_conv_bwd(*d, NGU_STREAM); }
+
+int ngu_attn_fwd(const ngu_attn_desc* d, void* stream) {
+  NGU_NONNULL(d, "ngu_attn_fwd");
+  return attn_fwd_simt(*d, NGU_STREAM);
+}
+int ngu_attn_bwd(const ngu_attn_desc* d, void* stream) {
+  NGU_NONNULL(d, "ngu_attn_bwd");
+  return attn_bwd_simt(*d, NGU_STREAM);
+}
+
+int ngu_infonce_normalize(const void* x, float* xhat, float* norm, int B, int E, int dtype, void* stream) {
+  return infonce_normalize(x, xhat, norm, B, E, dtype, NGU_STREAM);
+}
+int ngu_infonce_core(const ngu_infonce_desc* d, void* stream) { NGU_NONNULL(d, "ngu_infonce_core"); return infonce_core(*d, NGU_STREAM); }
+int ngu_infonce_normalize_bwd(const float* dxhat, const float* xhat, const float* norm, const float* gscale, void* dx, int B,
+                              int E, int dtype, void* stream) {
+  return infonce_normalize_bwd(dxhat, xhat, norm, gscale, dx, B, E, dtype, NGU_STREAM);
+}
+
+int ngu_wgrad(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int T, int Mo, int No, int dtype, int impl,
+              void* stream) {
+  (void)impl;
+  return wgrad_simt(X, ldx, Y, ldy, D, ldd, T, Mo, No, dtype, NGU_STREAM);
+}
+int ngu_colsum(const void* X, int ldx, float* out, int T, int C, int dtype, void* stream) {
+  return colsum(X, ldx, out, T, C, dtype, NGU_STREAM);
+}
+int ngu_dropout(const void* x, void* out, int64_t n, float p, uint64_t seed, int accumulate, int dtype, void* stream) {
+  return dropout(x, out, size_t(n), p, seed, accumulate, dtype, NGU_STREAM);
+}
+int ngu_patchify(const float* img, void* out, int B, int R, int P, int dtype, void* stream) {
+  return patchify(img, out, B, R, P, dtype, NGU_STREAM);
+}
+int ngu_assemble_tokens(const void* patch, const float* cls, const float* pos, void* out, int B, int np, int D, int dtype,
+                        void* stream) {
+  return assemble_tokens(patch, cls, pos, out, B, np, D, dtype, NGU_STREAM);
+}
+int ngu_embed_tokens(const int64_t* ids, const float* word, const float* pos, const float* type0, void* out, int B, int S,
+                     int D, int vocab, int dtype, void* stream) {
+  return embed_tokens(ids, word, pos, type0, out, B, S, D, vocab, dtype, NGU_STREAM);
+}
+int ngu_cast_f32(const float* in, void* out, int rows, int cols, int transpose, float scale, int dtype, void* stream) {
+  return cast_f32(in, out, rows, cols, transpose, scale, dtype, NGU_STREAM);
+}
+
 }  // extern "C"

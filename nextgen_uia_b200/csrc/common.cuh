@@ -328,3 +328,68 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int sm_count();
 
 }  // namespace ngu
+
+// ----------------------------------------------------------------------------------------
+// 16-byte vector access, generic over the activation dtype (bf16 product path / fp32 check mode)
+// ----------------------------------------------------------------------------------------
+namespace ngu {
+template <typename T> struct Vec;
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  static NGU_DEVINL void load(const bf16* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+  static NGU_DEVINL void store(bf16* p, const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  static NGU_DEVINL void load(const float* p, float (&f)[4]) {
+    const float4 u = *reinterpret_cast<const float4*>(p);
+    f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
+  }
+  static NGU_DEVINL void store(float* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+// exact (libm) variants for the fp32 check mode, fast variants for bf16
+template <typename T> NGU_DEVINL float gelu_t(float x);
+template <> NGU_DEVINL float gelu_t<bf16>(float x) { return gelu_erf(x); }
+template <> NGU_DEVINL float gelu_t<float>(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+template <typename T> NGU_DEVINL float gelu_grad_t(float x);
+template <> NGU_DEVINL float gelu_grad_t<bf16>(float x) { return gelu_erf_grad(x); }
+template <> NGU_DEVINL float gelu_grad_t<float>(float x) {
+  return 0.5f * (1.f + erff(x * 0.7071067811865476f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+}  // namespace ngu
+
+// ----------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG for dropout masks (regenerated in backward from seed + element index)
+// ----------------------------------------------------------------------------------------
+namespace ngu {
+NGU_DEVINL uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+  uint32_t c[4] = {c0, c1, 0x9E3779B9u, 0xBB67AE85u};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c[0], c[1], c[2], c[3]);
+}
+// keep-mask for element `idx` of a tensor under dropout probability p: returns 1/(1-p) or 0
+NGU_DEVINL float dropout_scale(uint64_t seed, uint64_t idx, float p) {
+  const uint4 r = philox4x32(uint32_t(idx >> 2), uint32_t(idx >> 34), uint32_t(seed), uint32_t(seed >> 32));
+  const uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+  const float u = float(w >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? 1.0f / (1.0f - p) : 0.0f;
+}
+}  // namespace ngu

@@ -12,6 +12,25 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream);
 // CUDA-core GEMM for the fp32 check mode (and a bf16 instantiation used only by tests) — gemm_simt.cu
 int gemm_simt(const GemmArgs& a, cudaStream_t stream);
 
+int ln_fwd(const ngu_ln_desc& d, cudaStream_t s);
+int ln_bwd(const ngu_ln_bwd_desc& d, cudaStream_t s);
+int mona_pre_bwd(const ngu_mona_pre_bwd_desc& d, cudaStream_t s);
+int mona_conv_fwd(const ngu_mona_conv_desc& d, cudaStream_t s);
+int mona_conv_bwd(const ngu_mona_conv_desc& d, cudaStream_t s);
+int attn_validate(const ngu_attn_desc& d, const char* what, bool bwd);
+int attn_fwd_simt(const ngu_attn_desc& d, cudaStream_t s);
+int attn_bwd_simt(const ngu_attn_desc& d, cudaStream_t s);
+int infonce_normalize(const void* x, float* xhat, float* norm, int B, int E, int dtype, cudaStream_t s);
+int infonce_core(const ngu_infonce_desc& d, cudaStream_t s);
+int infonce_normalize_bwd(const float* dxhat, const float* xhat, const float* norm, const float* gscale, void* dx, int B, int E, int dtype, cudaStream_t s);
+int patchify(const float* img, void* out, int B, int R, int P, int dtype, cudaStream_t s);
+int assemble_tokens(const void* patch, const float* cls, const float* pos, void* out, int B, int np, int D, int dtype, cudaStream_t s);
+int embed_tokens(const int64_t* ids, const float* word, const float* pos, const float* type0, void* out, int B, int S, int D, int vocab, int dtype, cudaStream_t s);
+int cast_f32(const float* in, void* out, int rows, int cols, int transpose, float scale, int dtype, cudaStream_t s);
+int wgrad_simt(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int Tn, int Mo, int No, int dtype, cudaStream_t s);
+int dropout(const void* x, void* out, size_t n, float p, uint64_t seed, int accumulate, int dtype, cudaStream_t s);
+int colsum(const void* X, int ldx, float* out, int Tn, int Cn, int dtype, cudaStream_t s);
+
 void count_launch(int n = 1);
 
 }  // namespace ngu

@@ -1,0 +1,194 @@
+// Small data-movement kernels around the block: patchify (im2col of the stride-16 patch-embed conv,
+// timm PatchEmbed / src/third_party/openai_clip/model.py:221,234), token assembly (+cls, +pos),
+// fp32 -> bf16 casts with optional transpose for the trainable adapter matrices, and the SIMT
+// weight-gradient reduction used by the fp32 check mode.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ngu {
+namespace {
+
+// images [B,3,R,R] fp32 (NCHW) -> patches [B*G*G, 3*P*P] (T), column order (c, py, px) = conv weight flattening
+template <typename T>
+__global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int R, int P) {
+  const int G = R / P, K = 3 * P * P;
+  const size_t total = size_t(B) * G * G * K;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int col = int(i % K);
+    const size_t rowi = i / K;
+    const int px = col % P, py = (col / P) % P, c = col / (P * P);
+    const int gx = int(rowi % G), gy = int((rowi / G) % G), b = int(rowi / (size_t(G) * G));
+    out[i] = from_f32<T>(img[((size_t(b) * 3 + c) * R + (gy * P + py)) * R + gx * P + px]);
+  }
+}
+
+// x0[b,0,:] = cls + pos[0];  x0[b,1+p,:] = patch[b*np+p,:] + pos[1+p]
+template <typename T>
+__global__ void assemble_kernel(const T* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
+                                T* __restrict__ out, int B, int np, int D) {
+  const size_t total = size_t(B) * (np + 1) * D;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % D);
+    const int n = int((i / D) % (np + 1));
+    const int b = int(i / (size_t(D) * (np + 1)));
+    float v = pos[size_t(n) * D + c];
+    v += (n == 0) ? cls[c] : to_f32<T>(patch[(size_t(b) * np + (n - 1)) * D + c]);
+    out[i] = from_f32<T>(v);
+  }
+}
+
+// BERT input embeddings: out[b,s,:] = word[ids[b,s]] + pos[s] + type0   (HF BertEmbeddings before its LayerNorm)
+template <typename T>
+__global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
+                             const float* __restrict__ type0, T* __restrict__ out, int B, int S, int D, int vocab) {
+  const size_t total = size_t(B) * S * D;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % D);
+    const size_t tok = i / D;
+    const int s = int(tok % S);
+    int64_t id = ids[tok];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    out[i] = from_f32<T>(word[size_t(id) * D + c] + pos[size_t(s) * D + c] + type0[c]);
+  }
+}
+
+// out (T) [cols, rows] or [rows, cols] <- in fp32 [rows, cols] * scale
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, int rows, int cols, int transpose, float scale) {
+  const size_t total = size_t(rows) * cols;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int r = int(i / cols), c = int(i % cols);
+    const float v = in[i] * scale;
+    if (transpose) out[size_t(c) * rows + r] = from_f32<T>(v);
+    else out[i] = from_f32<T>(v);
+  }
+}
+
+// D[Mo,No] += X^T Y,  X [T,Mo], Y [T,No] row-major, reduction over tokens split across blockIdx.z
+constexpr int WT = 64, WK = 16;
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(const T* __restrict__ X, int ldx, const T* __restrict__ Y, int ldy,
+                                                         float* __restrict__ D, int ldd, int Tn, int Mo, int No, int tchunk) {
+  __shared__ float sX[WK][WT + 1];
+  __shared__ float sY[WK][WT + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * WT, n0 = blockIdx.x * WT;
+  const int t0 = blockIdx.z * tchunk, t1 = min(Tn, t0 + tchunk);
+  float acc[4][4] = {};
+  for (int tb = t0; tb < t1; tb += WK) {
+    for (int i = threadIdx.x; i < WK * WT; i += 256) {
+      const int r = i / WT, c = i % WT;
+      const int t = tb + r;
+      sX[r][c] = (t < t1 && m0 + c < Mo) ? to_f32<T>(X[size_t(t) * ldx + m0 + c]) : 0.f;
+      sY[r][c] = (t < t1 && n0 + c < No) ? to_f32<T>(Y[size_t(t) * ldy + n0 + c]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < WK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sX[k][ty * 4 + i]; b[i] = sY[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < Mo && n < No) atomicAdd(D + size_t(m) * ldd + n, acc[i][j]);
+    }
+}
+
+// column sums of a [T, C] activation into fp32 (bias gradients)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ X, int ldx, float* __restrict__ out, int Tn, int Cn, int tchunk) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cn) return;
+  const int t0 = blockIdx.y * tchunk, t1 = min(Tn, t0 + tchunk);
+  float s = 0.f;
+  for (int t = t0; t < t1; ++t) s += to_f32<T>(X[size_t(t) * ldx + c]);
+  atomicAdd(out + c, s);
+}
+
+// out = (accumulate ? out : 0) + x * mask(seed, i) / (1-p)   (LoRA input dropout, src/adapters/lora.py:82-83)
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ out, size_t n, float p, uint64_t seed, int accumulate) {
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    float v = to_f32<T>(x[i]) * dropout_scale(seed, i, p);
+    if (accumulate) v += to_f32<T>(out[i]);
+    out[i] = from_f32<T>(v);
+  }
+}
+
+int grid_for(size_t total) {
+  size_t g = (total + 255) / 256;
+  const size_t cap = size_t(sm_count()) * 16;
+  return int(g > cap ? cap : (g == 0 ? 1 : g));
+}
+
+}  // namespace
+
+int patchify(const float* img, void* out, int B, int R, int P, int dtype, cudaStream_t st) {
+  if (B <= 0 || R <= 0 || P <= 0 || R % P) { set_last_error("patchify: bad shape B=%d R=%d P=%d", B, R, P); return NGU_ERR_SHAPE; }
+  const size_t total = size_t(B) * (R / P) * (R / P) * 3 * P * P;
+  if (dtype == NGU_F32) patchify_kernel<float><<<grid_for(total), 256, 0, st>>>(img, reinterpret_cast<float*>(out), B, R, P);
+  else patchify_kernel<bf16><<<grid_for(total), 256, 0, st>>>(img, reinterpret_cast<bf16*>(out), B, R, P);
+  return check_launch("patchify");
+}
+int assemble_tokens(const void* patch, const float* cls, const float* pos, void* out, int B, int np, int D, int dtype, cudaStream_t st) {
+  if (B <= 0 || np <= 0 || D <= 0) { set_last_error("assemble_tokens: empty"); return NGU_ERR_SHAPE; }
+  const size_t total = size_t(B) * (np + 1) * D;
+  if (dtype == NGU_F32) assemble_kernel<float><<<grid_for(total), 256, 0, st>>>(reinterpret_cast<const float*>(patch), cls, pos, reinterpret_cast<float*>(out), B, np, D);
+  else assemble_kernel<bf16><<<grid_for(total), 256, 0, st>>>(reinterpret_cast<const bf16*>(patch), cls, pos, reinterpret_cast<bf16*>(out), B, np, D);
+  return check_launch("assemble_tokens");
+}
+int embed_tokens(const int64_t* ids, const float* word, const float* pos, const float* type0, void* out, int B, int S, int D,
+                 int vocab, int dtype, cudaStream_t st) {
+  if (B <= 0 || S <= 0 || D <= 0 || vocab <= 0) { set_last_error("embed_tokens: empty"); return NGU_ERR_SHAPE; }
+  const size_t total = size_t(B) * S * D;
+  if (dtype == NGU_F32) embed_kernel<float><<<grid_for(total), 256, 0, st>>>(ids, word, pos, type0, reinterpret_cast<float*>(out), B, S, D, vocab);
+  else embed_kernel<bf16><<<grid_for(total), 256, 0, st>>>(ids, word, pos, type0, reinterpret_cast<bf16*>(out), B, S, D, vocab);
+  return check_launch("embed_tokens");
+}
+int cast_f32(const float* in, void* out, int rows, int cols, int transpose, float scale, int dtype, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) { set_last_error("cast: empty"); return NGU_ERR_SHAPE; }
+  const size_t total = size_t(rows) * cols;
+  if (dtype == NGU_F32) cast_kernel<float><<<grid_for(total), 256, 0, st>>>(in, reinterpret_cast<float*>(out), rows, cols, transpose, scale);
+  else cast_kernel<bf16><<<grid_for(total), 256, 0, st>>>(in, reinterpret_cast<bf16*>(out), rows, cols, transpose, scale);
+  return check_launch("cast");
+}
+int dropout(const void* x, void* out, size_t n, float p, uint64_t seed, int accumulate, int dtype, cudaStream_t st) {
+  if (n == 0 || p < 0.f || p >= 1.f) { set_last_error("dropout: bad n/p"); return NGU_ERR_ARG; }
+  if (dtype == NGU_F32) dropout_kernel<float><<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(out), n, p, seed, accumulate);
+  else dropout_kernel<bf16><<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out), n, p, seed, accumulate);
+  return check_launch("dropout");
+}
+int wgrad_simt(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int Tn, int Mo, int No, int dtype, cudaStream_t st) {
+  if (Tn <= 0 || Mo <= 0 || No <= 0) { set_last_error("wgrad: empty"); return NGU_ERR_SHAPE; }
+  int splits = (Tn + 511) / 512;
+  if (splits > 512) splits = 512;
+  int tchunk = (Tn + splits - 1) / splits;
+  tchunk = (tchunk + WK - 1) / WK * WK;
+  splits = (Tn + tchunk - 1) / tchunk;
+  dim3 grid((No + WT - 1) / WT, (Mo + WT - 1) / WT, splits);
+  if (dtype == NGU_F32) wgrad_simt_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(X), ldx, reinterpret_cast<const float*>(Y), ldy, D, ldd, Tn, Mo, No, tchunk);
+  else wgrad_simt_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(X), ldx, reinterpret_cast<const bf16*>(Y), ldy, D, ldd, Tn, Mo, No, tchunk);
+  return check_launch("wgrad_simt");
+}
+int colsum(const void* X, int ldx, float* out, int Tn, int Cn, int dtype, cudaStream_t st) {
+  if (Tn <= 0 || Cn <= 0) { set_last_error("colsum: empty"); return NGU_ERR_SHAPE; }
+  int splits = (Tn + 255) / 256;
+  if (splits > 1024) splits = 1024;
+  const int tchunk = (Tn + splits - 1) / splits;
+  dim3 grid((Cn + 127) / 128, (Tn + tchunk - 1) / tchunk);
+  if (dtype == NGU_F32) colsum_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(X), ldx, out, Tn, Cn, tchunk);
+  else colsum_kernel<bf16><<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(X), ldx, out, Tn, Cn, tchunk);
+  return check_launch("colsum");
+}
+
+}  // namespace ngu

@@ -1,0 +1,295 @@
+// Mona bottleneck stage, one CTA per image, everything between project1 and project2 in shared
+// memory (src/adapters/mona.py:85-93 BaselineMonaOp and :129-147 of BaselineMona.forward):
+//     z   = (dw3(h) + dw5(h) + dw7(h)) / 3 + h          depthwise, zero padded, per-branch bias
+//     a   = z + P z + bp                                 1x1 projector + residual
+//     g   = dropout(gelu(a))                             CLS token (if any) skips the conv: a = h
+// The three depthwise kernels are merged into ONE 7x7 stencil (exact: (pad(k3)+pad(k5)+k7)/3 + delta)
+// so the stencil reads each neighbour once; backward recomputes z/a from the saved h instead of
+// storing them, and produces dh plus all parameter gradients (fp32 atomics, one set per CTA).
+//
+// Layout: h/g/dh are [B, N, C] token-major (N = has_cls + H*W), C = 64 channels contiguous, so a
+// warp reads 32 consecutive channels of one token (coalesced, bank-conflict free in smem).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ngu {
+namespace {
+
+constexpr int C = 64;        // bottleneck channels (reference default --mona_bottleneck 64)
+constexpr int kThreads = 256;
+constexpr int kChunk = 32;   // tokens per projector chunk
+
+template <typename T> NGU_DEVINL float ldT(const T* p) { return to_f32<T>(*p); }
+
+struct ConvSmem {
+  float kc[49][C];     // merged stencil, tap-major
+  float bc[C];         // merged bias
+  float pt[C][C];      // projector weight transposed: pt[i][o] = P[o][i]
+  float bp[C];
+  float zc[kChunk][C]; // chunk of z
+  float dac[kChunk][C];// chunk of da (backward)
+};
+
+NGU_DEVINL void load_weights(ConvSmem& s, const ngu_mona_conv_weights& w) {
+  for (int i = threadIdx.x; i < 49 * C; i += kThreads) {
+    const int c = i % C, t = i / C;
+    const int ky = t / 7, kx = t % 7;
+    float v = w.k7[c * 49 + t];
+    if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) v += w.k5[c * 25 + (ky - 1) * 5 + (kx - 1)];
+    if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) v += w.k3[c * 9 + (ky - 2) * 3 + (kx - 2)];
+    v *= (1.0f / 3.0f);
+    if (t == 24) v += 1.0f;
+    s.kc[t][c] = v;
+  }
+  for (int i = threadIdx.x; i < C * C; i += kThreads) {
+    const int o = i / C, ii = i % C;
+    s.pt[ii][o] = w.P[i];
+  }
+  if (threadIdx.x < C) {
+    s.bc[threadIdx.x] = (w.b3[threadIdx.x] + w.b5[threadIdx.x] + w.b7[threadIdx.x]) * (1.0f / 3.0f);
+    s.bp[threadIdx.x] = w.bp[threadIdx.x];
+  }
+}
+
+// z for tokens [p0, p0+kChunk) of the H x W grid from the full h tile (hs: [HW][C] of T)
+template <typename T>
+NGU_DEVINL void conv_chunk(ConvSmem& s, const T* hs, int p0, int H, int W) {
+  const int c = threadIdx.x & (C - 1), grp = threadIdx.x >> 6;
+  for (int lp = grp; lp < kChunk; lp += kThreads / C) {
+    const int p = p0 + lp;
+    if (p >= H * W) { s.zc[lp][c] = 0.f; continue; }
+    const int y = p / W, x = p % W;
+    float acc = s.bc[c];
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+      const int yy = y + ky - 3;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const int xx = x + kx - 3;
+        if (xx < 0 || xx >= W) continue;
+        acc = fmaf(s.kc[ky * 7 + kx][c], to_f32<T>(hs[(yy * W + xx) * C + c]), acc);
+      }
+    }
+    s.zc[lp][c] = acc;
+  }
+}
+
+// a[lp][o] = z + bp + sum_i P[o][i] z[lp][i]
+NGU_DEVINL float proj_out(const ConvSmem& s, int lp, int o) {
+  float acc = s.zc[lp][o] + s.bp[o];
+#pragma unroll 16
+  for (int i = 0; i < C; ++i) acc = fmaf(s.pt[i][o], s.zc[lp][i], acc);
+  return acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+mona_conv_fwd_kernel(const T* __restrict__ h, T* __restrict__ g, ngu_mona_conv_weights w, int N, int H, int W,
+                     int has_cls, float drop_p, uint64_t seed) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  ConvSmem& s = *reinterpret_cast<ConvSmem*>(smem_dyn);
+  T* hs = reinterpret_cast<T*>(smem_dyn + sizeof(ConvSmem));
+  const int img = blockIdx.x;
+  const T* hb = h + size_t(img) * N * C;
+  T* gb = g + size_t(img) * N * C;
+  const int HW = H * W;
+  load_weights(s, w);
+  {
+    constexpr int V = Vec<T>::N;
+    const T* src = hb + has_cls * C;
+    for (int i = threadIdx.x * V; i < HW * C; i += kThreads * V) {
+      *reinterpret_cast<uint4*>(hs + i) = *reinterpret_cast<const uint4*>(src + i);
+    }
+  }
+  const int c = threadIdx.x & (C - 1), grp = threadIdx.x >> 6;
+  if (has_cls && grp == 0) {
+    const uint64_t idx = (uint64_t(img) * N) * C + c;
+    float v = gelu_t<T>(ldT(hb + c));
+    if (drop_p > 0.f) v *= dropout_scale(seed, idx, drop_p);
+    gb[c] = from_f32<T>(v);
+  }
+  __syncthreads();
+  for (int p0 = 0; p0 < HW; p0 += kChunk) {
+    conv_chunk<T>(s, hs, p0, H, W);
+    __syncthreads();
+    for (int lp = grp; lp < kChunk; lp += kThreads / C) {
+      const int p = p0 + lp;
+      if (p >= HW) break;
+      float v = gelu_t<T>(proj_out(s, lp, c));
+      const uint64_t tok = uint64_t(img) * N + has_cls + p;
+      if (drop_p > 0.f) v *= dropout_scale(seed, tok * C + c, drop_p);
+      gb[(has_cls + p) * C + c] = from_f32<T>(v);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+mona_conv_bwd_kernel(const T* __restrict__ h, const T* __restrict__ dg, T* __restrict__ dh, ngu_mona_conv_weights w,
+                     ngu_mona_conv_grads gr, int N, int H, int W, int has_cls, float drop_p, uint64_t seed) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  ConvSmem& s = *reinterpret_cast<ConvSmem*>(smem_dyn);
+  const int HW = H * W;
+  T* hs = reinterpret_cast<T*>(smem_dyn + sizeof(ConvSmem));
+  T* dzs = hs + size_t(HW) * C;
+  const int img = blockIdx.x;
+  const T* hb = h + size_t(img) * N * C;
+  const T* dgb = dg + size_t(img) * N * C;
+  T* dhb = dh + size_t(img) * N * C;
+  load_weights(s, w);
+  {
+    constexpr int V = Vec<T>::N;
+    const T* src = hb + has_cls * C;
+    for (int i = threadIdx.x * V; i < HW * C; i += kThreads * V)
+      *reinterpret_cast<uint4*>(hs + i) = *reinterpret_cast<const uint4*>(src + i);
+  }
+  const int c = threadIdx.x & (C - 1), grp = threadIdx.x >> 6;
+  float db1_acc = 0.f;  // column sum of dh (= d project1.bias), channel c, this thread's tokens
+  if (has_cls && grp == 0) {
+    const uint64_t idx = (uint64_t(img) * N) * C + c;
+    float v = ldT(dgb + c) * gelu_grad_t<T>(ldT(hb + c));
+    if (drop_p > 0.f) v *= dropout_scale(seed, idx, drop_p);
+    dhb[c] = from_f32<T>(v);
+    db1_acc += v;
+  }
+  __syncthreads();
+
+  // dP partials: thread owns P[o][i] for o = c, i in {grp*16 .. grp*16+15}
+  float dP[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dP[i] = 0.f;
+  float dbp_acc = 0.f;
+
+  for (int p0 = 0; p0 < HW; p0 += kChunk) {
+    conv_chunk<T>(s, hs, p0, H, W);
+    __syncthreads();
+    // da = dg * mask * gelu'(a)
+    for (int lp = grp; lp < kChunk; lp += kThreads / C) {
+      const int p = p0 + lp;
+      float v = 0.f;
+      if (p < HW) {
+        const float a = proj_out(s, lp, c);
+        v = ldT(dgb + (has_cls + p) * C + c) * gelu_grad_t<T>(a);
+        const uint64_t tok = uint64_t(img) * N + has_cls + p;
+        if (drop_p > 0.f) v *= dropout_scale(seed, tok * C + c, drop_p);
+      }
+      s.dac[lp][c] = v;
+    }
+    __syncthreads();
+    // dP[o=c][i] += sum_lp da[lp][o] * z[lp][i];  dbp[o] += sum_lp da[lp][o]
+#pragma unroll 4
+    for (int lp = 0; lp < kChunk; ++lp) {
+      const float d = s.dac[lp][c];
+      if (grp == 0) dbp_acc += d;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dP[i] = fmaf(d, s.zc[lp][grp * 16 + i], dP[i]);
+    }
+    // dz[lp][i=c] = da[lp][i] + sum_o P[o][i] da[lp][o]   -> full-size dz tile
+    for (int lp = grp; lp < kChunk; lp += kThreads / C) {
+      const int p = p0 + lp;
+      if (p >= HW) break;
+      float acc = s.dac[lp][c];
+#pragma unroll 16
+      for (int o = 0; o < C; ++o) acc = fmaf(__ldg(w.P + o * C + c), s.dac[lp][o], acc);
+      dzs[p * C + c] = from_f32<T>(acc);
+    }
+    __syncthreads();
+  }
+
+  // dh = correlate(dz, flipped stencil):  dh[p] = sum_t kc[t] * dz[p - off_t]
+  for (int p = grp; p < HW; p += kThreads / C) {
+    const int y = p / W, x = p % W;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+      const int yy = y - (ky - 3);
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const int xx = x - (kx - 3);
+        if (xx < 0 || xx >= W) continue;
+        acc = fmaf(s.kc[ky * 7 + kx][c], to_f32<T>(dzs[(yy * W + xx) * C + c]), acc);
+      }
+    }
+    dhb[(has_cls + p) * C + c] = from_f32<T>(acc);
+    db1_acc += acc;
+  }
+
+  // stencil weight grads: dkc[t][c] = sum_p dz[p][c] * h[p + off_t][c]; taps split over the 4 groups
+  float dbc_acc = 0.f;
+  if (grp == 0)
+    for (int p = 0; p < HW; ++p) dbc_acc += to_f32<T>(dzs[p * C + c]);
+  for (int t = grp; t < 49; t += kThreads / C) {
+    const int ky = t / 7, kx = t % 7;
+    float acc = 0.f;
+    const int y0 = max(0, 3 - ky), y1 = min(H, H + 3 - ky);
+    const int x0 = max(0, 3 - kx), x1 = min(W, W + 3 - kx);
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x)
+        acc = fmaf(to_f32<T>(dzs[(y * W + x) * C + c]), to_f32<T>(hs[((y + ky - 3) * W + (x + kx - 3)) * C + c]), acc);
+    acc *= (1.0f / 3.0f);
+    atomicAdd(gr.dk7 + c * 49 + t, acc);
+    if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) atomicAdd(gr.dk5 + c * 25 + (ky - 1) * 5 + (kx - 1), acc);
+    if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) atomicAdd(gr.dk3 + c * 9 + (ky - 2) * 3 + (kx - 2), acc);
+  }
+  if (grp == 0) {
+    const float b = dbc_acc * (1.0f / 3.0f);
+    atomicAdd(gr.db3 + c, b);
+    atomicAdd(gr.db5 + c, b);
+    atomicAdd(gr.db7 + c, b);
+    atomicAdd(gr.dbp + c, dbp_acc);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) atomicAdd(gr.dP + c * C + grp * 16 + i, dP[i]);
+  atomicAdd(gr.db1 + c, db1_acc);
+}
+
+template <typename T>
+int conv_smem_bytes(int HW, bool bwd) { return int(sizeof(ConvSmem)) + HW * C * int(sizeof(T)) * (bwd ? 2 : 1); }
+
+template <typename T>
+int launch_fwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
+  const int smem = conv_smem_bytes<T>(d.H * d.W, false);
+  if (smem > 227 * 1024) { set_last_error("mona_conv_fwd: %dx%d grid needs %d B smem", d.H, d.W, smem); return NGU_ERR_SHAPE; }
+  cudaError_t e = cudaFuncSetAttribute(mona_conv_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return cuda_status(e, "mona_conv_fwd attr");
+  mona_conv_fwd_kernel<T><<<d.B, kThreads, smem, st>>>(reinterpret_cast<const T*>(d.h), reinterpret_cast<T*>(d.g), d.w, d.N, d.H,
+                                                        d.W, d.has_cls, d.drop_p, d.seed);
+  return check_launch("mona_conv_fwd");
+}
+template <typename T>
+int launch_bwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
+  const int smem = conv_smem_bytes<T>(d.H * d.W, true);
+  if (smem > 227 * 1024) { set_last_error("mona_conv_bwd: %dx%d grid needs %d B smem", d.H, d.W, smem); return NGU_ERR_SHAPE; }
+  cudaError_t e = cudaFuncSetAttribute(mona_conv_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return cuda_status(e, "mona_conv_bwd attr");
+  mona_conv_bwd_kernel<T><<<d.B, kThreads, smem, st>>>(reinterpret_cast<const T*>(d.h), reinterpret_cast<const T*>(d.dg),
+                                                        reinterpret_cast<T*>(d.dh), d.w, d.gr, d.N, d.H, d.W, d.has_cls,
+                                                        d.drop_p, d.seed);
+  return check_launch("mona_conv_bwd");
+}
+
+int validate(const ngu_mona_conv_desc& d, const char* what) {
+  if (d.C != C) { set_last_error("%s: bottleneck %d not instantiated (only %d)", what, d.C, C); return NGU_ERR_SHAPE; }
+  if (d.B <= 0 || d.H <= 0 || d.W <= 0 || d.N != d.H * d.W + (d.has_cls ? 1 : 0)) {
+    set_last_error("%s: bad shape B=%d N=%d H=%d W=%d has_cls=%d", what, d.B, d.N, d.H, d.W, d.has_cls);
+    return NGU_ERR_SHAPE;
+  }
+  if (d.drop_p < 0.f || d.drop_p >= 1.f) { set_last_error("%s: dropout p=%f out of range", what, d.drop_p); return NGU_ERR_ARG; }
+  return NGU_OK;
+}
+
+}  // namespace
+
+int mona_conv_fwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
+  if (int rc = validate(d, "mona_conv_fwd")) return rc;
+  return d.dtype == NGU_F32 ? launch_fwd<float>(d, st) : launch_fwd<bf16>(d, st);
+}
+int mona_conv_bwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
+  if (int rc = validate(d, "mona_conv_bwd")) return rc;
+  return d.dtype == NGU_F32 ? launch_bwd<float>(d, st) : launch_bwd<bf16>(d, st);
+}
+
+}  // namespace ngu

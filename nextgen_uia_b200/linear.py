@@ -1,0 +1,92 @@
+"""Projection helper shared by the ViT block, the BERT tower and the standalone LoRA modules.
+
+A projection is y = x W^T + b (+ s * drop(x) A^T B^T for LoRA, src/adapters/lora.py:78-90) with a
+FROZEN base weight: backward only ever needs dx = dy W (dgrad), never dW, so the host keeps a
+[N,K] and a [K,N] low-precision copy of every frozen weight (made once) and both directions are
+"NT" tcgen05 GEMMs.  The LoRA branch is evaluated in its low-rank form and accumulated into the same
+TMEM tile as extra K blocks (A2/B2 operand pair of ngu_gemm) — the reference's dense B@A is never formed.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+
+
+def frozen_copies(weight, dtype):
+    """(W [N,K], W^T [K,N]) in `dtype` for a frozen fp32 parameter, cached on the parameter."""
+    if weight.requires_grad:
+        raise NotImplementedError(
+            "ngu B200 path: base projection weights must be frozen (Mona / LoRA fine-tuning, "
+            "src/models/biomedclip/finetune.py:165-197); full fine-tuning is outside this hot path")
+    key = (dtype, weight.device, weight._version, weight.data_ptr())
+    cache = getattr(weight, "_ngu_cache", None)
+    if cache is None or cache[0] != key:
+        w32 = weight.detach().float().contiguous()
+        cache = (key, ops.cast(w32, dtype), ops.cast(w32, dtype, transpose=True))
+        weight._ngu_cache = cache
+    return cache[1], cache[2]
+
+
+class Proj:
+    """Per-call view of one projection's operands."""
+
+    __slots__ = ("W", "WT", "bias", "A", "B", "scaling", "p", "r", "rp")
+
+    def __init__(self, linear, dtype):
+        self.W, self.WT = frozen_copies(linear.weight, dtype)
+        self.bias = linear.bias
+        self.A = self.B = None
+        self.scaling, self.p, self.r, self.rp = 0.0, 0.0, 0, 0
+        r = getattr(linear, "r", 0)
+        if r and hasattr(linear, "w_lora_A"):
+            self.A, self.B = linear.w_lora_A, linear.w_lora_B
+            self.scaling = float(linear.scaling)
+            self.r = r
+            self.rp = (r + 7) // 8 * 8 if dtype == torch.bfloat16 else r
+            drop = getattr(linear, "dropout", None)
+            self.p = float(drop.p) if (drop is not None and linear.training) else 0.0
+
+
+def _lora_operands(pj, dtype):
+    A, B = pj.A.detach(), pj.B.detach()
+    if pj.rp != pj.r:  # rank not a multiple of 8: zero-pad the tiny fp32 factors (16-byte TMA rows)
+        A = F.pad(A, (0, 0, 0, pj.rp - pj.r))
+        B = F.pad(B, (0, pj.rp - pj.r))
+    return A.contiguous(), B.contiguous()
+
+
+def proj_fwd(x2, pj, *, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save_pre=False, seed=0):
+    """Returns (out, saved) where out is y or (y, pre) and saved feeds proj_bwd."""
+    bias = pj.bias.detach() if pj.bias is not None else None
+    if pj.A is None:
+        return ops.gemm(x2, pj.W, bias=bias, act=act, aux=aux, aux_mode=aux_mode, save_pre=save_pre), None
+    dt = x2.dtype
+    A32, B32 = _lora_operands(pj, dt)
+    xd = ops.dropout(x2, pj.p, seed) if pj.p > 0 else x2
+    t = ops.gemm(xd, ops.cast(A32, dt), alpha=pj.scaling)                       # [M, rp] = s * drop(x) A^T
+    out = ops.gemm(x2, pj.W, bias=bias, act=act, aux=aux, aux_mode=aux_mode, save_pre=save_pre,
+                   A2=t, B2=ops.cast(B32, dt))
+    return out, (xd, t, seed)
+
+
+def proj_bwd(dy2, pj, saved, *, need_dx=True, need_bias=False):
+    """dy2 [M,N] -> (dx [M,K] or None, dbias, dA, dB); grads are fp32 in the parameter shapes."""
+    dbias = ops.colsum(dy2) if (need_bias and pj.bias is not None) else None
+    if pj.A is None:
+        return (ops.gemm(dy2, pj.WT) if need_dx else None), dbias, None, None
+    dt = dy2.dtype
+    xd, t, seed = saved
+    A32, B32 = _lora_operands(pj, dt)
+    dts = ops.gemm(dy2, ops.cast(B32, dt, transpose=True), alpha=pj.scaling)    # [M, rp] = s * dy B
+    dB = ops.wgrad(dy2, t)[:, :pj.r].contiguous()                               # [N, r]
+    dA = ops.wgrad(xd, dts)[:, :pj.r].t().contiguous()                          # [r, K]
+    dx = None
+    if need_dx:
+        At = ops.cast(A32, dt, transpose=True)                                  # [K, rp]
+        if pj.p > 0:
+            dx = ops.gemm(dy2, pj.WT)
+            ops.dropout(ops.gemm(dts, At), pj.p, seed, out=dx, accumulate=True)
+        else:
+            dx = ops.gemm(dy2, pj.WT, A2=dts, B2=At)
+    return dx, dbias, dA, dB

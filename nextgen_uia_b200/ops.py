@@ -1,0 +1,329 @@
+"""Tensor-level wrappers over the C ABI (include/ngu_b200.h).
+
+PyTorch is used here only for device memory and streams: every function takes CUDA tensors,
+allocates outputs with torch.empty and enqueues the sm_100a kernels of libngu_b200.so on the
+current stream.  dtype selects the path: torch.bfloat16 -> tcgen05 product path, torch.float32 ->
+fp32 check mode (CUDA cores).  Nothing here falls back to torch math.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+_byref = ctypes.byref
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return L.NGU_BF16
+    if t.dtype == torch.float32:
+        return L.NGU_F32
+    raise L.NguError(f"unsupported activation dtype {t.dtype} (bf16 or fp32)")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.NguError("ngu ops need CUDA tensors: there is no CPU fallback in the product path")
+
+
+def _f32(t):
+    assert t.dtype == torch.float32 and t.is_contiguous(), "parameters are passed as contiguous fp32"
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+def gemm(A, B, *, bias=None, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save_pre=False,
+         A2=None, B2=None, alpha=1.0, out=None, block_n=0, force_simt=False):
+    """C[M,N] = epi(alpha * (A[M,K] @ B[N,K]^T + A2 @ B2^T)); returns C or (C, Pre)."""
+    _need_cuda(A, B)
+    assert A.dim() == 2 and B.dim() == 2 and A.shape[1] == B.shape[1] and A.dtype == B.dtype
+    assert A.stride(1) == 1 and B.stride(1) == 1
+    M, K = A.shape
+    N = B.shape[0]
+    C = out if out is not None else torch.empty(M, N, device=A.device, dtype=A.dtype)
+    assert C.shape == (M, N) and C.stride(1) == 1 and C.dtype == A.dtype
+    Pre = torch.empty(M, N, device=A.device, dtype=A.dtype) if save_pre else None
+    d = L.GemmDesc()
+    d.A, d.lda, d.B, d.ldb, d.C, d.ldc = A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), C.data_ptr(), C.stride(0)
+    if A2 is not None:
+        assert A2.shape[0] == M and B2.shape[0] == N and A2.shape[1] == B2.shape[1]
+        assert A2.stride(1) == 1 and B2.stride(1) == 1 and A2.dtype == A.dtype and B2.dtype == A.dtype
+        d.A2, d.lda2, d.B2, d.ldb2, d.K2 = A2.data_ptr(), A2.stride(0), B2.data_ptr(), B2.stride(0), A2.shape[1]
+    if bias is not None:
+        d.bias = _f32(bias).data_ptr()
+    if aux is not None:
+        assert aux.shape == (M, N) and aux.stride(1) == 1 and aux.dtype == A.dtype
+        d.aux, d.ldaux = aux.data_ptr(), aux.stride(0)
+    if save_pre:
+        d.Pre, d.ldpre = Pre.data_ptr(), Pre.stride(0)
+    d.M, d.N, d.K = M, N, K
+    d.act, d.aux_mode, d.save_pre = act, aux_mode, int(save_pre)
+    d.alpha = alpha
+    d.dtype = (100 + L.NGU_BF16) if (force_simt and A.dtype == torch.bfloat16) else _dt(A)
+    d.block_n = block_n
+    L.check(L.lib().ngu_gemm(_byref(d), _stream()), "ngu_gemm")
+    return (C, Pre) if save_pre else C
+
+
+def ln_fwd(x, w, b, eps, *, gamma=None, gammax=None, rows=None, ldx=None, out=None, ldy=None, save_stats=True):
+    """LayerNorm over the last dim of x (viewed as [M, D]); optional Mona pre-scale.  Returns (y, mean, rstd)."""
+    _need_cuda(x)
+    D = x.shape[-1]
+    if rows is None:
+        assert x.is_contiguous()
+        M, ldx_ = x.numel() // D, D
+    else:
+        M, ldx_ = rows, ldx
+    y = out if out is not None else torch.empty((M, D) if rows is not None else x.shape, device=x.device, dtype=x.dtype)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32) if save_stats else None
+    d = L.LnDesc()
+    d.x, d.ldx, d.y, d.ldy = x.data_ptr(), ldx_, y.data_ptr(), (ldy if ldy is not None else D)
+    d.w, d.b = _f32(w).data_ptr(), _f32(b).data_ptr()
+    d.gamma, d.gammax = _p(gamma), _p(gammax)
+    d.mean, d.rstd = _p(mean), _p(rstd)
+    d.M, d.D, d.eps, d.dtype = M, D, eps, _dt(x)
+    L.check(L.lib().ngu_ln_fwd(_byref(d), _stream()), "ngu_ln_fwd")
+    return y, mean, rstd
+
+
+def ln_bwd(g, x, mean, rstd, w, *, dres=None, rows=None, ldg=None, ldx=None, out=None, lddx=None):
+    """dx = LNbwd(g) (+ dres) for a frozen-affine LayerNorm."""
+    _need_cuda(g, x)
+    D = x.shape[-1]
+    M = rows if rows is not None else x.numel() // D
+    dx = out if out is not None else torch.empty((M, D) if rows is not None else x.shape, device=x.device, dtype=x.dtype)
+    d = L.LnBwdDesc()
+    d.g, d.ldg = g.data_ptr(), (ldg if ldg is not None else D)
+    d.x, d.ldx = x.data_ptr(), (ldx if ldx is not None else D)
+    if dres is not None:
+        assert dres.is_contiguous()
+        d.dres, d.ldr = dres.data_ptr(), D
+    d.dx, d.lddx = dx.data_ptr(), (lddx if lddx is not None else D)
+    d.mean, d.rstd, d.w = mean.data_ptr(), rstd.data_ptr(), _f32(w).data_ptr()
+    d.M, d.D, d.dtype = M, D, _dt(x)
+    L.check(L.lib().ngu_ln_bwd(_byref(d), _stream()), "ngu_ln_bwd")
+    return dx
+
+
+def mona_pre_bwd(du, dy, x, mean, rstd, w, b, gamma, gammax, dw, db, dgamma, dgammax, dycol):
+    _need_cuda(du, dy, x)
+    D = x.shape[-1]
+    M = x.numel() // D
+    dx = torch.empty_like(x)
+    d = L.MonaPreBwdDesc()
+    d.du, d.dy, d.x = du.data_ptr(), dy.data_ptr(), x.data_ptr()
+    d.mean, d.rstd = mean.data_ptr(), rstd.data_ptr()
+    d.w, d.b, d.gamma, d.gammax = (_f32(t).data_ptr() for t in (w, b, gamma, gammax))
+    d.dx = dx.data_ptr()
+    d.dw, d.db, d.dgamma, d.dgammax, d.dycol = (_f32(t).data_ptr() for t in (dw, db, dgamma, dgammax, dycol))
+    d.M, d.D, d.dtype = M, D, _dt(x)
+    L.check(L.lib().ngu_mona_pre_bwd(_byref(d), _stream()), "ngu_mona_pre_bwd")
+    return dx
+
+
+def _conv_desc(h, weights, hw, has_cls, drop_p, seed):
+    B, N, C = h.shape
+    d = L.MonaConvDesc()
+    k3, b3, k5, b5, k7, b7, P, bp = weights
+    d.w.k3, d.w.b3, d.w.k5, d.w.b5, d.w.k7, d.w.b7, d.w.P, d.w.bp = (_f32(t).data_ptr() for t in (k3, b3, k5, b5, k7, b7, P, bp))
+    d.B, d.N, d.H, d.W, d.C, d.has_cls = B, N, hw[0], hw[1], C, int(has_cls)
+    d.drop_p, d.seed, d.dtype = float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _dt(h)
+    return d
+
+
+def mona_conv_fwd(h, weights, hw, has_cls, drop_p=0.0, seed=0):
+    """h [B,N,C] -> g = dropout(gelu(conv-stage(h))); weights = (k3,b3,k5,b5,k7,b7,P,bp) fp32."""
+    _need_cuda(h)
+    assert h.is_contiguous()
+    g = torch.empty_like(h)
+    d = _conv_desc(h, weights, hw, has_cls, drop_p, seed)
+    d.h, d.g = h.data_ptr(), g.data_ptr()
+    L.check(L.lib().ngu_mona_conv_fwd(_byref(d), _stream()), "ngu_mona_conv_fwd")
+    return g
+
+
+def mona_conv_bwd(h, dg, weights, grads, hw, has_cls, drop_p=0.0, seed=0):
+    """Returns dh; accumulates into grads = (dk3,db3,dk5,db5,dk7,db7,dP,dbp,db1) fp32."""
+    _need_cuda(h, dg)
+    assert h.is_contiguous() and dg.is_contiguous()
+    dh = torch.empty_like(h)
+    d = _conv_desc(h, weights, hw, has_cls, drop_p, seed)
+    d.h, d.dg, d.dh = h.data_ptr(), dg.data_ptr(), dh.data_ptr()
+    (d.gr.dk3, d.gr.db3, d.gr.dk5, d.gr.db5, d.gr.dk7, d.gr.db7, d.gr.dP, d.gr.dbp, d.gr.db1) = (_f32(t).data_ptr() for t in grads)
+    L.check(L.lib().ngu_mona_conv_bwd(_byref(d), _stream()), "ngu_mona_conv_bwd")
+    return dh
+
+
+def _attn_desc(q, k, v, o, B, H, N, S, dh, strides, scale, causal, impl):
+    d = L.AttnDesc()
+    (d.q_bs, d.q_ts), (d.k_bs, d.k_ts), (d.v_bs, d.v_ts), (d.o_bs, d.o_ts) = strides
+    d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    d.B, d.H, d.N, d.S, d.dh = B, H, N, S, dh
+    d.scale, d.causal, d.dtype, d.impl = scale, int(causal), _dt(q), impl
+    return d
+
+
+def attn_fwd_packed(qkv, B, N, H, dh, *, causal=False, impl=0):
+    """timm layout: qkv [B*N, 3*H*dh] (= [B,N,3,H,dh]); returns (o [B*N, H*dh], lse [B,H,N])."""
+    _need_cuda(qkv)
+    D = H * dh
+    o = torch.empty(B * N, D, device=qkv.device, dtype=qkv.dtype)
+    lse = torch.empty(B, H, N, device=qkv.device, dtype=torch.float32)
+    st = ((N * 3 * D, 3 * D),) * 3 + ((N * D, D),)
+    d = _attn_desc(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B, H, N, N, dh, st, dh ** -0.5, causal, impl)
+    d.lse = lse.data_ptr()
+    L.check(L.lib().ngu_attn_fwd(_byref(d), _stream()), "ngu_attn_fwd")
+    return o, lse
+
+
+def attn_bwd_packed(qkv, o, lse, do, B, N, H, dh, *, causal=False, impl=0):
+    """Returns dqkv [B*N, 3*H*dh]."""
+    _need_cuda(qkv, o, do)
+    D = H * dh
+    assert do.is_contiguous() and o.is_contiguous()
+    dqkv = torch.empty_like(qkv)
+    st = ((N * 3 * D, 3 * D),) * 3 + ((N * D, D),)
+    d = _attn_desc(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B, H, N, N, dh, st, dh ** -0.5, causal, impl)
+    d.lse, d.d_o = lse.data_ptr(), do.data_ptr()
+    d.dq, d.dk, d.dv = dqkv.data_ptr(), dqkv[:, D:].data_ptr(), dqkv[:, 2 * D:].data_ptr()
+    L.check(L.lib().ngu_attn_bwd(_byref(d), _stream()), "ngu_attn_bwd")
+    return dqkv
+
+
+def attn_fwd_strided(q, k, v, B, H, N, S, dh, strides, *, causal=False, impl=0):
+    """General layout (see include/ngu_b200.h): strides = ((q_bs,q_ts),(k_bs,k_ts),(v_bs,v_ts),(o_bs,o_ts)); o is
+    allocated as [B*N... ] by the caller's convention: returns (o flat [B*N*H*dh], lse)."""
+    _need_cuda(q, k, v)
+    o = torch.empty(B * N * H * dh, device=q.device, dtype=q.dtype)
+    lse = torch.empty(B, H, N, device=q.device, dtype=torch.float32)
+    d = _attn_desc(q, k, v, o, B, H, N, S, dh, strides, dh ** -0.5, causal, impl)
+    d.lse = lse.data_ptr()
+    L.check(L.lib().ngu_attn_fwd(_byref(d), _stream()), "ngu_attn_fwd")
+    return o, lse
+
+
+def attn_bwd_strided(q, k, v, o, lse, do, B, H, N, S, dh, strides, *, causal=False, impl=0):
+    _need_cuda(q, k, v, o, do)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    d = _attn_desc(q, k, v, o, B, H, N, S, dh, strides, dh ** -0.5, causal, impl)
+    d.lse, d.d_o = lse.data_ptr(), do.data_ptr()
+    d.dq, d.dk, d.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    L.check(L.lib().ngu_attn_bwd(_byref(d), _stream()), "ngu_attn_bwd")
+    return dq, dk, dv
+
+
+def wgrad(X, Y, out=None, impl=0):
+    """D[Mo,No] (+)= X[T,Mo]^T @ Y[T,No] in fp32."""
+    _need_cuda(X, Y)
+    assert X.shape[0] == Y.shape[0] and X.stride(1) == 1 and Y.stride(1) == 1 and X.dtype == Y.dtype
+    T, Mo = X.shape
+    No = Y.shape[1]
+    D = out if out is not None else torch.zeros(Mo, No, device=X.device, dtype=torch.float32)
+    assert D.dtype == torch.float32 and D.stride(1) == 1
+    L.check(L.lib().ngu_wgrad(X.data_ptr(), X.stride(0), Y.data_ptr(), Y.stride(0), D.data_ptr(), D.stride(0), T, Mo, No,
+                              _dt(X), impl, _stream()), "ngu_wgrad")
+    return D
+
+
+def colsum(X, out=None):
+    _need_cuda(X)
+    assert X.dim() == 2 and X.stride(1) == 1
+    T, C = X.shape
+    o = out if out is not None else torch.zeros(C, device=X.device, dtype=torch.float32)
+    L.check(L.lib().ngu_colsum(X.data_ptr(), X.stride(0), o.data_ptr(), T, C, _dt(X), _stream()), "ngu_colsum")
+    return o
+
+
+def dropout(x, p, seed, out=None, accumulate=False):
+    _need_cuda(x)
+    assert x.is_contiguous()
+    o = out if out is not None else torch.empty_like(x)
+    L.check(L.lib().ngu_dropout(x.data_ptr(), o.data_ptr(), x.numel(), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(accumulate),
+                                _dt(x), _stream()), "ngu_dropout")
+    return o
+
+
+def patchify(img, P, dtype):
+    _need_cuda(img)
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4 and img.shape[1] == 3
+    B, _, R, R2 = img.shape
+    assert R == R2
+    G = R // P
+    out = torch.empty(B * G * G, 3 * P * P, device=img.device, dtype=dtype)
+    L.check(L.lib().ngu_patchify(img.data_ptr(), out.data_ptr(), B, R, P, _dt(out), _stream()), "ngu_patchify")
+    return out
+
+
+def assemble_tokens(patch, cls, pos, B):
+    _need_cuda(patch)
+    np_, D = patch.shape[0] // B, patch.shape[1]
+    out = torch.empty(B, np_ + 1, D, device=patch.device, dtype=patch.dtype)
+    L.check(L.lib().ngu_assemble_tokens(patch.data_ptr(), _f32(cls).data_ptr(), _f32(pos).data_ptr(), out.data_ptr(), B, np_, D,
+                                        _dt(patch), _stream()), "ngu_assemble_tokens")
+    return out
+
+
+def embed_tokens(ids, word, pos, type0, dtype):
+    _need_cuda(ids)
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    B, S = ids.shape
+    V, D = word.shape
+    out = torch.empty(B * S, D, device=ids.device, dtype=dtype)
+    L.check(L.lib().ngu_embed_tokens(ids.data_ptr(), _f32(word).data_ptr(), _f32(pos).data_ptr(), _f32(type0).data_ptr(),
+                                     out.data_ptr(), B, S, D, V, _dt(out), _stream()), "ngu_embed_tokens")
+    return out
+
+
+def cast(w, dtype, transpose=False, scale=1.0):
+    """fp32 [rows, cols] parameter -> dtype copy (optionally transposed, scaled)."""
+    _need_cuda(w)
+    w = _f32(w.detach())
+    rows, cols = w.shape
+    out = torch.empty((cols, rows) if transpose else (rows, cols), device=w.device, dtype=dtype)
+    L.check(L.lib().ngu_cast_f32(w.data_ptr(), out.data_ptr(), rows, cols, int(transpose), float(scale), _dt(out), _stream()),
+            "ngu_cast_f32")
+    return out
+
+
+def infonce_normalize(x, xhat_out, norm_out):
+    _need_cuda(x)
+    assert x.is_contiguous() and xhat_out.dtype == torch.float32
+    B, E = x.shape
+    L.check(L.lib().ngu_infonce_normalize(x.data_ptr(), xhat_out.data_ptr(), norm_out.data_ptr(), B, E, _dt(x), _stream()),
+            "ngu_infonce_normalize")
+
+
+def infonce_core(ihat, that, r0, Bl, temperature, want_grad=True):
+    """ihat/that: fp32 [Bg,E] gathered normalised features. Returns (loss[1], dihat[Bl,E], dthat[Bl,E])."""
+    _need_cuda(ihat, that)
+    Bg, E = ihat.shape
+    dev = ihat.device
+    loss = torch.empty(1, device=dev, dtype=torch.float32)
+    ws = torch.empty(2 * Bg * Bg + 2 * Bg, device=dev, dtype=torch.float32)
+    di = torch.empty(Bl, E, device=dev, dtype=torch.float32) if want_grad else None
+    dt_ = torch.empty(Bl, E, device=dev, dtype=torch.float32) if want_grad else None
+    d = L.InfoNceDesc()
+    d.ihat, d.that, d.dihat, d.dthat = ihat.data_ptr(), that.data_ptr(), _p(di), _p(dt_)
+    d.loss, d.ws = loss.data_ptr(), ws.data_ptr()
+    d.Bg, d.Bl, d.r0, d.E, d.temperature = Bg, Bl, r0, E, float(temperature)
+    L.check(L.lib().ngu_infonce_core(_byref(d), _stream()), "ngu_infonce_core")
+    return loss, di, dt_
+
+
+def infonce_normalize_bwd(dxhat, xhat, norm, gscale, dtype):
+    B, E = dxhat.shape
+    dx = torch.empty(B, E, device=dxhat.device, dtype=dtype)
+    L.check(L.lib().ngu_infonce_normalize_bwd(dxhat.data_ptr(), xhat.data_ptr(), norm.data_ptr(), _p(gscale), dx.data_ptr(), B, E,
+                                              _dt(dx), _stream()), "ngu_infonce_normalize_bwd")
+    return dx

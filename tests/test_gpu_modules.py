@@ -1,0 +1,190 @@
+"""GPU parity of the drop-in modules (Mona, LoRA, block, full model) against golden vectors made from
+the reference's own modules and against the CPU oracle."""
+import pytest
+import torch
+
+from conftest import relerr, TOL, GTOL
+
+pytestmark = pytest.mark.gpu
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("name", ["mona_cls", "mona_nocls"])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_mona_golden(golden, name, dtype):
+    """BatchFirstMonaWrapper(BaselineMona) forward + all grads vs the reference module's outputs."""
+    from src.adapters import BaselineMona, BatchFirstMonaWrapper
+    g = golden(name)
+    D = g["x"].shape[-1]
+    m = BatchFirstMonaWrapper(BaselineMona(D, 64))
+    m.load_state_dict(g["state"], strict=True)
+    m = m.to(dev()).eval()
+    x = g["x"].to(dev(), dtype).requires_grad_(True)
+    y = m(x, g["hw"] if g["has_cls"] else None)
+    (y * g["gy"].to(dev(), dtype)).sum().backward()
+    assert y.shape == g["y"].shape and y.dtype == dtype
+    assert relerr(y, g["y"]) < TOL[dtype]
+    assert relerr(x.grad, g["dx"]) < GTOL[dtype]
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        assert relerr(p.grad, g["grads"][k]) < GTOL[dtype], k
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_mona_seq_first_768(dtype):
+    """BaselineMona called the OpenAI-CLIP way ([N,B,D], reference mona.py:115-151) at D=768 vs the oracle."""
+    from src.adapters import BaselineMona
+    from oracle import functional as OF
+    torch.manual_seed(0)
+    m = BaselineMona(768, 64)
+    with torch.no_grad():
+        m.gamma.copy_(torch.randn(768) * 0.3)
+    sd = {f"m.{k}": v.detach().double() for k, v in m.state_dict().items()}
+    m = m.to(dev()).eval()
+    x = torch.randn(197, 3, 768).to(dtype)
+    y = m(x.to(dev()), (14, 14))
+    ref = OF.mona(x.double().permute(1, 0, 2), sd, "m.", (14, 14), True).permute(1, 0, 2)
+    assert y.shape == x.shape and relerr(y, ref) < TOL[dtype]
+
+
+def test_mona_dropout_statistics():
+    """train mode: keep-rate ~ 0.9 with 1/(1-p) scaling, same mask in backward (reference mona.py:109,147)."""
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(0)
+    B, N, C = 4, 197, 64
+    h = torch.randn(B, N, C, device=dev())
+    w = [torch.zeros(64, 1, 3, 3), torch.zeros(64), torch.zeros(64, 1, 5, 5), torch.zeros(64), torch.zeros(64, 1, 7, 7), torch.zeros(64),
+         torch.zeros(64, 64, 1, 1), torch.zeros(64)]
+    w = [t.to(dev()) for t in w]
+    g0 = ops.mona_conv_fwd(h, w, (14, 14), True, 0.0, 0)
+    g1 = ops.mona_conv_fwd(h, w, (14, 14), True, 0.1, 1234)
+    keep = (g1 != 0) | (g0 == 0)
+    rate = keep.float().mean().item()
+    assert abs(rate - 0.9) < 0.01
+    assert torch.allclose(g1[keep], g0[keep] / 0.9, rtol=1e-5, atol=1e-6)
+    grads = [torch.zeros_like(t) for t in w] + [torch.zeros(64, device=dev())]
+    dh = ops.mona_conv_bwd(h, torch.ones_like(h), w, grads, (14, 14), True, 0.1, 1234)
+    assert bool(((dh == 0) | keep).all()) and bool(((dh != 0) == (keep & (dh != 0))).all())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_lora_linear_golden(golden, dtype):
+    from src.adapters import LinearLoRA
+    g = golden("lora_linear")
+    lin = torch.nn.Linear(256, 384)
+    m = LinearLoRA(lin, r=g["r"], lora_alpha=g["alpha"], dropout_rate=0.1)
+    m.load_state_dict(g["state"], strict=True)
+    m = m.to(dev()).eval()
+    x = g["x"].to(dev(), dtype).requires_grad_(True)
+    y = m(x)
+    (y * g["gy"].to(dev(), dtype)).sum().backward()
+    assert relerr(y, g["y"]) < TOL[dtype]
+    assert relerr(x.grad, g["dx"]) < GTOL[dtype]
+    for n in ("w_lora_A", "w_lora_B", "bias"):
+        assert relerr(getattr(m, n).grad, g["grads"][n]) < GTOL[dtype], n
+    assert m.weight.grad is None
+
+
+def _tiny_model(method, depth=2, seed=1):
+    from nextgen_uia_b200.biomedclip import BiomedCLIP, init_synthetic_
+    from src.adapters import inject_mona_variant_to_open_clip, inject_lora_to_biomedclip
+    torch.manual_seed(seed)
+    model = BiomedCLIP(vision=dict(depth=depth), text=dict(layers=depth, vocab=1000, max_pos=128))
+    init_synthetic_(model, seed=seed, std=0.02)
+    for p in model.parameters():
+        p.requires_grad = False
+    if method == "mona":
+        inject_mona_variant_to_open_clip(model, variant="baseline", bottleneck_dim=64)
+        key = "mona"
+    else:
+        inject_lora_to_biomedclip(model, lora_r=8, lora_alpha=32, lora_dropout=0.1)
+        key = "lora"
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if n.endswith("w_lora_B"):
+                    p.copy_(torch.randn(p.shape) * 0.02)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("gamma"):
+                p.copy_(torch.randn(p.shape) * 0.2)
+    for n, p in model.named_parameters():
+        if key in n.lower():
+            p.requires_grad = True
+    return model
+
+
+@pytest.mark.parametrize("method", ["mona", "lora"])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_model_loss_and_grads_vs_oracle(method, dtype):
+    """Config-1-shaped micro-step (encode_image, encode_text, InfoNCE, backward) on a 2-layer tower:
+    features, loss and every adapter gradient vs the CPU oracle on identical weights/inputs."""
+    from oracle import functional as OF
+    from src.losses import InfoNCELoss
+    model = _tiny_model(method)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    trainable = [n for n, p in model.named_parameters() if p.requires_grad]
+    torch.manual_seed(1)
+    B = 4
+    images = torch.rand(B, 3, 224, 224)
+    ids = torch.randint(5, 1000, (B, 77)); ids[:, 0] = 2; ids[:, -1] = 3
+    cfg = dict(patch=16, depth=2, heads=12, text_layers=2, text_heads=12, lora=(8, 32) if method == "lora" else None)
+    lo, fio, fto, _, go = OF.loss_and_grads(sd, images, ids, cfg, trainable)
+    model = model.to(dev()).eval().set_compute_dtype(dtype)
+    fi = model.encode_image(images.to(dev()))
+    ft = model.encode_text(ids.to(dev()))
+    loss = InfoNCELoss(0.07)(fi, ft)
+    assert relerr(fi, fio) < TOL[dtype] and relerr(ft, fto) < TOL[dtype]
+    assert abs(float(loss.detach()) - float(lo)) / abs(float(lo)) < TOL[dtype]
+    if dtype == torch.float32:
+        loss.backward()                      # the full chain, every adapter gradient at 1e-3
+    else:
+        # With random synthetic weights all images map to nearly the same feature, so d(InfoNCE)/d(feature) is a
+        # difference of near-equal vectors: bf16 feature rounding (4e-3) is amplified ~50x in that cotangent for ANY
+        # bf16 implementation.  InfoNCE's own bf16 gradients are pinned by test_infonce_golden; here the tower
+        # backward is checked with a well-conditioned fixed cotangent G on the image features.
+        G = torch.randn(fi.shape, generator=torch.Generator().manual_seed(3))
+        (fi * G.to(dev(), dtype)).sum().backward()
+        p64 = {k: v.double().clone().requires_grad_(k in trainable) for k, v in sd.items()}
+        fo = OF.encode_image(p64, images.double(), cfg)
+        go = dict(zip(trainable, torch.autograd.grad((fo * G.double()).sum(), [p64[k] for k in trainable])))
+    worst, num, den = ("", 0.0), 0.0, 0.0
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None, n
+            e = relerr(p.grad, go[n])
+            d = (p.grad.detach().double().cpu() - go[n].double())
+            num += float((d * d).sum()); den += float((go[n].double() ** 2).sum())
+            if e > worst[1]:
+                worst = (n, e)
+    if dtype == torch.float32:
+        # fp32 check mode: every adapter gradient tensor individually
+        assert worst[1] < 1e-3, worst
+    else:
+        # bf16: per-tensor max-error is dominated by cancellation noise in near-zero-sum bias gradients at this
+        # tiny batch; the contract is on the aggregate adapter gradient (relative L2) + per-op tests above
+        assert (num / den) ** 0.5 < 3e-2, ((num / den) ** 0.5, worst)
+
+
+def test_zero_shot_argmax_matches_oracle():
+    """identical argmax zero-shot predictions (src/models/biomedclip/zero_shot.py:176-228 recipe)."""
+    from oracle import functional as OF
+    model = _tiny_model("mona")
+    sd = {k: v.detach().double() for k, v in model.state_dict().items()}
+    torch.manual_seed(2)
+    B = 8
+    images = torch.rand(B, 3, 224, 224)
+    prompts = [torch.randint(5, 1000, (10, 77)) for _ in range(2)]
+    for p in prompts:
+        p[:, 0] = 2; p[:, -1] = 3
+    cfg = dict(patch=16, depth=2, heads=12, text_layers=2, text_heads=12)
+    ref = OF.zero_shot_predict(OF.encode_image(sd, images.double(), cfg), [OF.encode_text(sd, p, cfg) for p in prompts])
+    model = model.to(dev()).eval().set_compute_dtype(torch.bfloat16)
+    with torch.no_grad():
+        fi = model.encode_image(images.to(dev())).float().cpu()
+        tf = [model.encode_text(p.to(dev())).float().cpu() for p in prompts]
+    got = OF.zero_shot_predict(fi, tf)
+    assert torch.equal(got, ref)

@@ -1,0 +1,148 @@
+"""GPU parity of the individual kernels (through the C ABI) against the CPU oracle / golden vectors."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import relerr, TOL, GTOL
+
+pytestmark = pytest.mark.gpu
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K", [(300, 200, 264), (1000, 768, 768), (515, 3072, 768), (128, 64, 64), (77, 512, 640)])
+def test_gemm_plain(dtype, M, N, K):
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(0)
+    A = (torch.randn(M, K) * 0.5).to(dev(), dtype)
+    B = (torch.randn(N, K) * 0.05).to(dev(), dtype)
+    bias = torch.randn(N, device=dev())
+    C = ops.gemm(A, B, bias=bias)
+    R = A.double().cpu() @ B.double().cpu().t() + bias.double().cpu()
+    assert relerr(C, R) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_epilogues(dtype):
+    from nextgen_uia_b200 import ops, _lib as L
+    torch.manual_seed(1)
+    M, N, K, r = 640, 768, 256, 8
+    A = (torch.randn(M, K) * 0.5).to(dev(), dtype)
+    B = (torch.randn(N, K) * 0.1).to(dev(), dtype)
+    bias = torch.randn(N, device=dev())
+    aux = torch.randn(M, N).to(dev(), dtype)
+    A2 = torch.randn(M, r).to(dev(), dtype)
+    B2 = (torch.randn(N, r) * 0.1).to(dev(), dtype)
+    base = (A.double() @ B.double().t() + bias.double()).cpu()
+    # GELU + saved pre-activation
+    C, Pre = ops.gemm(A, B, bias=bias, act=L.ACT_GELU, save_pre=True)
+    assert relerr(Pre, base) < TOL[dtype] and relerr(C, F.gelu(base)) < TOL[dtype]
+    # QuickGELU
+    C = ops.gemm(A, B, bias=bias, act=L.ACT_QUICKGELU)
+    assert relerr(C, base * torch.sigmoid(1.702 * base)) < TOL[dtype]
+    # residual
+    C = ops.gemm(A, B, bias=bias, aux=aux, aux_mode=L.AUX_RESIDUAL)
+    assert relerr(C, base + aux.double().cpu()) < TOL[dtype]
+    # backward through GELU: (acc) * gelu'(aux)
+    a = aux.double().cpu().requires_grad_(True)
+    (dg,) = torch.autograd.grad(F.gelu(a).sum(), a)
+    C = ops.gemm(A, B, act=L.ACT_GELU, aux=aux, aux_mode=L.AUX_DACT)
+    assert relerr(C, (base - bias.double().cpu()) * dg) < TOL[dtype]
+    # low-rank pair (LoRA) + alpha
+    C = ops.gemm(A, B, bias=bias, A2=A2, B2=B2, alpha=0.5)
+    ref = 0.5 * (A.double() @ B.double().t() + A2.double() @ B2.double().t()).cpu() + bias.double().cpu()
+    assert relerr(C, ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("D", [768, 1024])
+def test_layernorm(dtype, D):
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(2)
+    M = 333
+    x = torch.randn(M, D) * 2 + 0.3
+    w, b = 1 + 0.1 * torch.randn(D), 0.1 * torch.randn(D)
+    g = torch.randn(M, D)
+    dres = torch.randn(M, D)
+    xd = x.to(dev(), dtype)
+    y, mean, rstd = ops.ln_fwd(xd, w.to(dev()), b.to(dev()), 1e-6)
+    xr = xd.double().cpu().requires_grad_(True)
+    yr = F.layer_norm(xr, (D,), w.double(), b.double(), 1e-6)
+    assert relerr(y, yr) < TOL[dtype]
+    gd = g.to(dev(), dtype)
+    (dxr,) = torch.autograd.grad((yr * gd.double().cpu()).sum(), xr)
+    dx = ops.ln_bwd(gd, xd, mean, rstd, w.to(dev()), dres=dres.to(dev(), dtype))
+    assert relerr(dx, dxr + dres.to(dtype).double()) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_layernorm_strided_rows(dtype):
+    """final norm on the CLS rows of [B,N,D] (rows = B, stride N*D)."""
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(3)
+    B, N, D = 5, 7, 768
+    x = torch.randn(B, N, D).to(dev(), dtype)
+    w, b = torch.randn(D).to(dev()), torch.randn(D).to(dev())
+    y, mean, rstd = ops.ln_fwd(x, w, b, 1e-6, rows=B, ldx=N * D)
+    ref = F.layer_norm(x[:, 0].double().cpu(), (D,), w.double().cpu(), b.double().cpu(), 1e-6)
+    assert relerr(y, ref) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,N,H,causal", [(2, 197, 12, False), (3, 77, 12, False), (2, 50, 4, True)])
+def test_attention(dtype, B, N, H, causal):
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(4)
+    dh = 64
+    D = H * dh
+    qkv = torch.randn(B * N, 3 * D).to(dev(), dtype)
+    do = torch.randn(B * N, D).to(dev(), dtype)
+    o, lse = ops.attn_fwd_packed(qkv, B, N, H, dh, causal=causal)
+    dqkv = ops.attn_bwd_packed(qkv, o, lse, do, B, N, H, dh, causal=causal)
+    t = qkv.double().cpu().requires_grad_(True)
+    q, k, v = t.view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(B * N, D)
+    (dref,) = torch.autograd.grad((ref * do.double().cpu()).sum(), t)
+    assert relerr(o, ref) < TOL[dtype]
+    assert relerr(dqkv, dref) < GTOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_wgrad_colsum(dtype):
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(5)
+    T, Mo, No = 3000, 768, 64
+    X = torch.randn(T, Mo).to(dev(), dtype)
+    Y = torch.randn(T, No).to(dev(), dtype)
+    D = ops.wgrad(X, Y)
+    assert relerr(D, X.double().cpu().t() @ Y.double().cpu()) < TOL[dtype]
+    s = ops.colsum(X)
+    assert relerr(s, X.double().cpu().sum(0)) < TOL[dtype]
+
+
+@pytest.mark.parametrize("name", ["infonce_b8", "infonce_b37"])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_infonce_golden(golden, name, dtype):
+    """loss and feature grads vs the reference InfoNCELoss outputs stored in tests/golden."""
+    from src.losses import InfoNCELoss
+    g = golden(name)
+    I = g["I"].to(dev(), dtype).requires_grad_(True)
+    T = g["T"].to(dev(), dtype).requires_grad_(True)
+    loss = InfoNCELoss(temperature=g["temperature"])(I, T)
+    loss.backward()
+    # inputs were rounded to `dtype`; recompute the oracle on the rounded inputs for a like-for-like check
+    from oracle import functional as OF
+    Io, To = I.detach().double().cpu().requires_grad_(True), T.detach().double().cpu().requires_grad_(True)
+    lo, _ = OF.info_nce(Io, To, g["temperature"])
+    gI, gT = torch.autograd.grad(lo, [Io, To])
+    assert abs(float(loss) - float(lo)) / abs(float(lo)) < 1e-4
+    assert relerr(I.grad, gI) < TOL[dtype] and relerr(T.grad, gT) < TOL[dtype]
+    if dtype == torch.float32:
+        assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-4
+        assert relerr(I.grad, g["dI"]) < 1e-4 and relerr(T.grad, g["dT"]) < 1e-4

@@ -1,0 +1,156 @@
+"""One-process-per-GPU data-parallel fine-tuning step (NCCL over NVLink 5 / NVSwitch).
+
+The reference trains on a single GPU (`--device cuda:0`, src/models/biomedclip/finetune.py:101) with no
+torch.distributed call anywhere, so the data-parallel layer is new:
+  * the global batch is partitioned by rank; every rank holds a full replica of the frozen towers and of
+    the adapters;
+  * InfoNCE all-gathers the L2-normalised image/text features once per micro-step (losses.py) and forms
+    the global loss, so feature gradients need no second collective;
+  * adapter / LoRA gradients are all-reduced with SUM (the loss is already a mean over the global
+    batch) — in per-layer buckets launched from autograd hooks on a side stream so the collective of
+    layer i overlaps the backward kernels of layer i-1;
+  * gradient clipping uses the post-all-reduce global norm; accumulation stays local to a rank
+    (finetune.py:287,296-303 semantics).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+
+def setup_mona(model, variant="baseline", bottleneck=64, num_layers=None):
+    """finetune.py:165-177 `_setup_mona_finetuning`: freeze all, inject, thaw names containing 'mona'."""
+    from .adapters.mona import inject_mona_variant_to_open_clip
+    for p in model.parameters():
+        p.requires_grad = False
+    inject_mona_variant_to_open_clip(model, variant=variant, bottleneck_dim=bottleneck, num_layers=num_layers)
+    for n, p in model.named_parameters():
+        if "mona" in n.lower():
+            p.requires_grad = True
+    return model
+
+
+def setup_lora(model, r=16, alpha=32, dropout=0.1, num_layers=None):
+    """finetune.py:180-197 `_setup_lora_finetuning` (the wrapped projections' biases stay trainable, as in the reference)."""
+    from .adapters.lora import inject_lora_to_biomedclip
+    for p in model.parameters():
+        p.requires_grad = False
+    inject_lora_to_biomedclip(model, lora_r=r, lora_alpha=alpha, lora_dropout=dropout, num_layers=num_layers)
+    for n, p in model.named_parameters():
+        if "lora" in n.lower():
+            p.requires_grad = True
+    return model
+
+
+class GradBuckets:
+    """Flat fp32 gradient buckets (one per group of parameters) with async SUM all-reduce.
+
+    Parameters' .grad tensors are views into the flat bucket, so the collective runs on one contiguous
+    buffer per bucket and the optimiser sees the reduced values without a copy."""
+
+    def __init__(self, params, bucket_of, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.buckets = {}
+        for p in params:
+            self.buckets.setdefault(bucket_of(p), []).append(p)
+        self.flat = {}
+        self.pending = {}
+        self.works = []
+        self.comm_stream = None
+        for key, ps in self.buckets.items():
+            n = sum(p.numel() for p in ps)
+            flat = torch.zeros(n, device=ps[0].device, dtype=torch.float32)
+            off = 0
+            for p in ps:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self.flat[key] = flat
+        if self.world > 1:
+            if params and params[0].is_cuda:
+                self.comm_stream = torch.cuda.Stream()
+            for key, ps in self.buckets.items():
+                for p in ps:
+                    p.register_post_accumulate_grad_hook(self._make_hook(key, len(ps)))
+
+    def _make_hook(self, key, count):
+        def hook(_p):
+            c = self.pending.get(key, 0) + 1
+            if c == count:
+                self.pending[key] = 0
+                self._launch(key)
+            else:
+                self.pending[key] = c
+        return hook
+
+    def _launch(self, key):
+        if not self.enabled:
+            return
+        if self.comm_stream is None:  # CPU tensors (gloo): no stream juggling
+            self.works.append(dist.all_reduce(self.flat[key], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            self.works.append(dist.all_reduce(self.flat[key], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    enabled = True
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def zero(self):
+        for f in self.flat.values():
+            f.zero_()
+
+
+class Trainer:
+    """The training micro-step of finetune.py:272-303 on the B200 path, data-parallel when torch.distributed is up."""
+
+    def __init__(self, model, temperature=0.07, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.01, grad_clip=1.0,
+                 accumulation_steps=1, total_updates=1000, lr_min=1e-8):
+        from .losses import InfoNCELoss
+        self.model = model
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.criterion = InfoNCELoss(temperature, gather_distributed=self.distributed)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        names = {id(p): n for n, p in model.named_parameters()}
+
+        def bucket_of(p):  # one bucket per transformer layer
+            parts = names[id(p)].split(".")
+            for i, s in enumerate(parts):
+                if s in ("blocks", "resblocks", "layer") and i + 1 < len(parts) and parts[i + 1].isdigit():
+                    return int(parts[i + 1])
+            return -1
+
+        self.buckets = GradBuckets(self.params, bucket_of)
+        self.optimizer = torch.optim.AdamW(self.params, lr=lr, betas=betas, weight_decay=weight_decay, fused=True)
+        self.scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizer, T_max=total_updates, eta_min=lr_min)
+        self.grad_clip = grad_clip
+        self.accum = accumulation_steps
+        self.micro = 0
+
+    def micro_step(self, images, ids):
+        """One micro-batch: encode, loss, backward (+ optimizer update at accumulation boundaries).
+        Returns the (device) loss tensor; nothing here synchronises with the host."""
+        m = self.model
+        last = (self.micro + 1) % self.accum == 0
+        self.buckets.enabled = last  # all-reduce only on the micro-step that completes an update
+        fi = m.encode_image(images)
+        ft = m.encode_text(ids)
+        loss = self.criterion(fi, ft)
+        (loss / self.accum).backward()
+        self.micro += 1
+        if last:
+            self.buckets.wait()
+            if self.grad_clip and self.grad_clip > 0:
+                torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip, foreach=True)
+            self.optimizer.step()
+            self.scheduler.step()
+            self.buckets.zero()
+        return loss.detach()

@@ -1,0 +1,77 @@
+"""CPU: the oracle against the golden vectors produced from the reference's own modules
+(oracle/make_golden.py), plus identities from SURVEY.md §8c."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import relerr
+from oracle import functional as OF
+
+
+@pytest.mark.parametrize("name", ["mona_cls", "mona_nocls"])
+def test_oracle_mona_matches_reference_golden(golden, name):
+    g = golden(name)
+    p = {k: v.double().requires_grad_(True) for k, v in g["state"].items()}
+    x = g["x"].double().requires_grad_(True)
+    y = OF.mona(x, p, "clip_mona.", g["hw"], g["has_cls"])
+    assert relerr(y, g["y"]) < 1e-6
+    keys = list(g["grads"].keys())
+    grads = torch.autograd.grad((y * g["gy"].double()).sum(), [x] + [p[k] for k in keys])
+    assert relerr(grads[0], g["dx"]) < 1e-5
+    for k, gr in zip(keys, grads[1:]):
+        assert relerr(gr, g["grads"][k]) < 1e-5, k
+
+
+def test_oracle_lora_matches_reference_golden(golden):
+    g = golden("lora_linear")
+    p = {f"l.{k}": v.double() for k, v in g["state"].items()}
+    y = OF.lora_linear(g["x"].double(), p, "l.", g["r"], g["alpha"])
+    assert relerr(y, g["y"]) < 1e-6
+    assert abs(g["alpha"] / math.sqrt(g["r"]) - 11.3137085) < 1e-6  # s = 32/sqrt(8)
+
+
+@pytest.mark.parametrize("name", ["infonce_b8", "infonce_b37"])
+def test_oracle_infonce_matches_reference_golden(golden, name):
+    g = golden(name)
+    I, T = g["I"].double().requires_grad_(True), g["T"].double().requires_grad_(True)
+    loss, _ = OF.info_nce(I, T, g["temperature"])
+    gI, gT = torch.autograd.grad(loss, [I, T])
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    assert relerr(gI, g["dI"]) < 1e-5 and relerr(gT, g["dT"]) < 1e-5
+
+
+def test_merged_stencil_identity():
+    """(dw3+dw5+dw7)/3 + x == one 7x7 depthwise with K=(pad(k3)+pad(k5)+k7)/3+delta — the kernel's stencil."""
+    torch.manual_seed(0)
+    C = 8
+    x = torch.randn(2, C, 14, 14, dtype=torch.float64)
+    k3, k5, k7 = (torch.randn(C, 1, k, k, dtype=torch.float64) for k in (3, 5, 7))
+    b3, b5, b7 = (torch.randn(C, dtype=torch.float64) for _ in range(3))
+    ref = (F.conv2d(x, k3, b3, padding=1, groups=C) + F.conv2d(x, k5, b5, padding=2, groups=C) + F.conv2d(x, k7, b7, padding=3, groups=C)) / 3 + x
+    K = (F.pad(k3, (2, 2, 2, 2)) + F.pad(k5, (1, 1, 1, 1)) + k7) / 3
+    K[:, 0, 3, 3] += 1
+    got = F.conv2d(x, K, (b3 + b5 + b7) / 3, padding=3, groups=C)
+    assert relerr(got, ref) < 1e-12
+
+
+def test_lora_is_identity_at_init_and_mona_is_not():
+    from src.adapters import LinearLoRA, BaselineMona
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(32, 48)
+    ll = LinearLoRA(lin, r=8, lora_alpha=32, dropout_rate=0.1)
+    assert torch.count_nonzero(ll.w_lora_B) == 0 and not ll.weight.requires_grad and ll.bias.requires_grad
+    assert torch.equal(ll.weight, lin.weight)
+    m = BaselineMona(64, 16)
+    assert float(m.gamma[0]) == pytest.approx(1e-6) and float(m.gammax[0]) == 1.0
+    assert len(list(m.parameters())) == 16
+
+
+def test_oracle_global_batch_equals_concat():
+    """DP semantics: loss on the concatenated global features == what every rank computes."""
+    torch.manual_seed(0)
+    I, T = torch.randn(8, 16, dtype=torch.float64), torch.randn(8, 16, dtype=torch.float64)
+    full, _ = OF.info_nce(I, T)
+    halves = [OF.info_nce(I[:4], T[:4])[0], OF.info_nce(I[4:], T[4:])[0]]
+    assert abs(float(full) - float(sum(halves) / 2)) > 1e-3  # local-only losses differ: global negatives matter

@@ -20,6 +20,9 @@ int mona_conv_bwd(const ngu_mona_conv_desc& d, cudaStream_t s);
 int attn_validate(const ngu_attn_desc& d, const char* what, bool bwd);
 int attn_fwd_simt(const ngu_attn_desc& d, cudaStream_t s);
 int attn_bwd_simt(const ngu_attn_desc& d, cudaStream_t s);
+bool attn_tc_supported(const ngu_attn_desc& d, bool bwd);
+int attn_fwd_tc(const ngu_attn_desc& d, cudaStream_t s);
+int attn_bwd_tc(const ngu_attn_desc& d, cudaStream_t s);
 int infonce_normalize(const void* x, float* xhat, float* norm, int B, int E, int dtype, cudaStream_t s);
 int infonce_core(const ngu_infonce_desc& d, cudaStream_t s);
 int infonce_normalize_bwd(const float* dxhat, const float* xhat, const float* norm, const float* gscale, void* dx, int B, int E, int dtype, cudaStream_t s);

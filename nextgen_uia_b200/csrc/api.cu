@@ -70,7 +70,7 @@ int ngu_infonce_normalize_bwd(const float* dxhat, const float* xhat, const float
 
 int ngu_wgrad(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int T, int Mo, int No, int dtype, int impl,
               void* stream) {
-  (void)impl;
+  if (impl == 0 && T > 0 && wgrad_tc_supported(ldx, ldy, ldd, Mo, No, dtype, X, Y, D)) return wgrad_tc(X, ldx, Y, ldy, D, ldd, T, Mo, NGU_STREAM);
   return wgrad_simt(X, ldx, Y, ldy, D, ldd, T, Mo, No, dtype, NGU_STREAM);
 }
 int ngu_colsum(const void* X, int ldx, float* out, int T, int C, int dtype, void* stream) {

@@ -32,6 +32,8 @@ int embed_tokens(const int64_t* ids, const float* word, const float* pos, const 
 int cast_f32(const float* in, void* out, int rows, int cols, int transpose, float scale, int dtype, cudaStream_t s);
 int wgrad_simt(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int Tn, int Mo, int No, int dtype, cudaStream_t s);
 int dropout(const void* x, void* out, size_t n, float p, uint64_t seed, int accumulate, int dtype, cudaStream_t s);
+bool wgrad_tc_supported(int ldx, int ldy, int ldd, int Mo, int No, int dtype, const void* X, const void* Y, const float* D);
+int wgrad_tc(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int T, int Mo, cudaStream_t s);
 int colsum(const void* X, int ldx, float* out, int Tn, int Cn, int dtype, cudaStream_t s);
 
 void count_launch(int n = 1);

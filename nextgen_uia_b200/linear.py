@@ -43,17 +43,24 @@ class Proj:
             self.A, self.B = linear.w_lora_A, linear.w_lora_B
             self.scaling = float(linear.scaling)
             self.r = r
-            self.rp = (r + 7) // 8 * 8 if dtype == torch.bfloat16 else r
+            # bf16: rank zero-padded to 64 so the factors' gradients run on the tcgen05 wgrad kernel (N tile = 64);
+            # the base GEMM only consumes the first ceil16(r) columns as its extra K block
+            self.rp = 64 if (dtype == torch.bfloat16 and r <= 64) else r
             drop = getattr(linear, "dropout", None)
             self.p = float(drop.p) if (drop is not None and linear.training) else 0.0
 
 
 def _lora_operands(pj, dtype):
     A, B = pj.A.detach(), pj.B.detach()
-    if pj.rp != pj.r:  # rank not a multiple of 8: zero-pad the tiny fp32 factors (16-byte TMA rows)
+    if pj.rp != pj.r:  # zero-pad the tiny fp32 factors to the padded rank
         A = F.pad(A, (0, 0, 0, pj.rp - pj.r))
         B = F.pad(B, (0, pj.rp - pj.r))
     return A.contiguous(), B.contiguous()
+
+
+def _k2(pj):
+    """columns of the low-rank factors the base GEMM reads as its extra K block (multiple of 16 for UMMA_K)."""
+    return min(pj.rp, (pj.r + 15) // 16 * 16) if pj.rp != pj.r else pj.r
 
 
 def proj_fwd(x2, pj, *, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save_pre=False, seed=0):
@@ -65,8 +72,9 @@ def proj_fwd(x2, pj, *, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save_pre=
     A32, B32 = _lora_operands(pj, dt)
     xd = ops.dropout(x2, pj.p, seed) if pj.p > 0 else x2
     t = ops.gemm(xd, ops.cast(A32, dt), alpha=pj.scaling)                       # [M, rp] = s * drop(x) A^T
+    k2 = _k2(pj)
     out = ops.gemm(x2, pj.W, bias=bias, act=act, aux=aux, aux_mode=aux_mode, save_pre=save_pre,
-                   A2=t, B2=ops.cast(B32, dt))
+                   A2=t[:, :k2], B2=ops.cast(B32, dt)[:, :k2])
     return out, (xd, t, seed)
 
 
@@ -88,5 +96,6 @@ def proj_bwd(dy2, pj, saved, *, need_dx=True, need_bias=False):
             dx = ops.gemm(dy2, pj.WT)
             ops.dropout(ops.gemm(dts, At), pj.p, seed, out=dx, accumulate=True)
         else:
-            dx = ops.gemm(dy2, pj.WT, A2=dts, B2=At)
+            k2 = _k2(pj)
+            dx = ops.gemm(dy2, pj.WT, A2=dts[:, :k2], B2=At[:, :k2])
     return dx, dbias, dA, dB

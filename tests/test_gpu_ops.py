@@ -121,7 +121,16 @@ def test_wgrad_colsum(dtype):
     X = torch.randn(T, Mo).to(dev(), dtype)
     Y = torch.randn(T, No).to(dev(), dtype)
     D = ops.wgrad(X, Y)
-    assert relerr(D, X.double().cpu().t() @ Y.double().cpu()) < TOL[dtype]
+    ref = X.double().cpu().t() @ Y.double().cpu()
+    assert relerr(D, ref) < TOL[dtype]
+    D1 = ops.wgrad(X, Y, impl=1)                       # CUDA-core path
+    assert relerr(D1, ref) < TOL[dtype]
+    D2 = ops.wgrad(X, Y, out=D.clone())                # accumulates
+    assert relerr(D2, 2 * ref) < TOL[dtype]
+    if dtype == torch.bfloat16:                        # strided views (LoRA-padded factors), Mo = 2304, ragged T
+        Xb = torch.randn(1111, 2304).to(dev(), dtype)
+        Yb = torch.zeros(1111, 64, device=dev(), dtype=dtype); Yb[:, :8] = torch.randn(1111, 8).to(dev(), dtype)
+        assert relerr(ops.wgrad(Xb, Yb), Xb.double().cpu().t() @ Yb.double().cpu()) < TOL[dtype]
     s = ops.colsum(X)
     assert relerr(s, X.double().cpu().sum(0)) < TOL[dtype]
 

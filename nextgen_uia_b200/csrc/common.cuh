@@ -310,6 +310,13 @@ NGU_DEVINL float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// 128-bit shared-memory load the compiler will neither hoist nor keep live across loop iterations
+NGU_DEVINL float4 lds128_volatile(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
 // dtype-generic scalar load/store used by the SIMT (fp32 check mode) kernels
 template <typename T> NGU_DEVINL float to_f32(T v);
 template <> NGU_DEVINL float to_f32<float>(float v) { return v; }
@@ -341,6 +348,10 @@ template <> struct Vec<bf16> {
     const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
   }
+  static NGU_DEVINL void unpack(const uint4& u, float (&f)[8]) {
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
   static NGU_DEVINL void store(bf16* p, const float (&f)[8]) {
     uint4 u;
     u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
@@ -353,6 +364,9 @@ template <> struct Vec<float> {
   static NGU_DEVINL void load(const float* p, float (&f)[4]) {
     const float4 u = *reinterpret_cast<const float4*>(p);
     f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
+  }
+  static NGU_DEVINL void unpack(const uint4& u, float (&f)[4]) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
   }
   static NGU_DEVINL void store(float* p, const float (&f)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);

@@ -8,17 +8,22 @@
 namespace ngu {
 namespace {
 
-// images [B,3,R,R] fp32 (NCHW) -> patches [B*G*G, 3*P*P] (T), column order (c, py, px) = conv weight flattening
+// images [B,3,R,R] fp32 (NCHW) -> patches [B*G*G, 3*P*P] (T), column order (c, py, px) = conv weight flattening.
+// Thread per 4 consecutive pixels of one image row: one 16-byte load, one contiguous store (P % 4 == 0).
 template <typename T>
 __global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int R, int P) {
   const int G = R / P, K = 3 * P * P;
-  const size_t total = size_t(B) * G * G * K;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int col = int(i % K);
-    const size_t rowi = i / K;
-    const int px = col % P, py = (col / P) % P, c = col / (P * P);
-    const int gx = int(rowi % G), gy = int((rowi / G) % G), b = int(rowi / (size_t(G) * G));
-    out[i] = from_f32<T>(img[((size_t(b) * 3 + c) * R + (gy * P + py)) * R + gx * P + px]);
+  const size_t total4 = size_t(B) * 3 * R * R / 4;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total4; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t e = i * 4;
+    const int xx = int(e % R);
+    const int yy = int((e / R) % R);
+    const int c = int((e / (size_t(R) * R)) % 3);
+    const int b = int(e / (size_t(3) * R * R));
+    const float4 v = *reinterpret_cast<const float4*>(img + e);
+    const int gx = xx / P, px = xx % P, gy = yy / P, py = yy % P;
+    T* dst = out + (size_t(b) * G * G + size_t(gy) * G + gx) * K + c * P * P + py * P + px;
+    dst[0] = from_f32<T>(v.x); dst[1] = from_f32<T>(v.y); dst[2] = from_f32<T>(v.z); dst[3] = from_f32<T>(v.w);
   }
 }
 
@@ -135,7 +140,8 @@ int grid_for(size_t total) {
 
 int patchify(const float* img, void* out, int B, int R, int P, int dtype, cudaStream_t st) {
   if (B <= 0 || R <= 0 || P <= 0 || R % P) { set_last_error("patchify: bad shape B=%d R=%d P=%d", B, R, P); return NGU_ERR_SHAPE; }
-  const size_t total = size_t(B) * (R / P) * (R / P) * 3 * P * P;
+  if (P % 4) { set_last_error("patchify: patch size must be a multiple of 4"); return NGU_ERR_SHAPE; }
+  const size_t total = size_t(B) * (R / P) * (R / P) * 3 * P * P / 4;
   if (dtype == NGU_F32) patchify_kernel<float><<<grid_for(total), 256, 0, st>>>(img, reinterpret_cast<float*>(out), B, R, P);
   else patchify_kernel<bf16><<<grid_for(total), 256, 0, st>>>(img, reinterpret_cast<bf16*>(out), B, R, P);
   return check_launch("patchify");

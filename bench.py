@@ -229,25 +229,23 @@ def main():
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event time of every launch in one step
     roof = None
+    recs = []
+    orig = ops.gemm
+
+    def timed_gemm(A, Bm, **kw):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = orig(A, Bm, **kw)
+        b.record()
+        k2 = kw["A2"].shape[1] if kw.get("A2") is not None else 0
+        recs.append((a, b, 2.0 * A.shape[0] * Bm.shape[0] * (A.shape[1] + k2)))
+        return out
+
+    ops.gemm = timed_gemm
+    step_resident()          # every rank runs it (the step contains collectives); rank 0 reports
+    torch.cuda.synchronize()
+    ops.gemm = orig
     if rank == 0:
-        recs = []
-        orig = ops.gemm
-
-        def timed_gemm(A, Bm, **kw):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            out = orig(A, Bm, **kw)
-            b.record()
-            k2 = kw["A2"].shape[1] if kw.get("A2") is not None else 0
-            recs.append((a, b, 2.0 * A.shape[0] * Bm.shape[0] * (A.shape[1] + k2)))
-            return out
-
-        import nextgen_uia_b200.linear as lin_mod, nextgen_uia_b200.vit as vit_mod, nextgen_uia_b200.biomedclip as bc_mod
-        import nextgen_uia_b200.adapters.mona as mona_mod
-        ops.gemm = timed_gemm
-        step_resident()
-        torch.cuda.synchronize()
-        ops.gemm = orig
         t_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
         fl = sum(f for _, _, f in recs)
         peaks = {}

@@ -1,0 +1,55 @@
+"""torchrun --nproc-per-node 2 tools/dp_check.py : data-parallel parity.
+Every rank computes the global InfoNCE loss over the all-gathered features; SUM-all-reduced adapter grads must equal the
+single-process oracle gradients on the concatenated global batch."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from nextgen_uia_b200.biomedclip import BiomedCLIP, init_synthetic_
+from nextgen_uia_b200 import dp
+from oracle import functional as OF
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+dtype = torch.float32 if (len(sys.argv) > 1 and sys.argv[1] == "fp32") else torch.bfloat16
+torch.manual_seed(1)
+model = BiomedCLIP(vision=dict(depth=2), text=dict(layers=2, vocab=1000, max_pos=128))
+init_synthetic_(model, seed=1)
+dp.setup_mona(model, "baseline", 64)
+with torch.no_grad():
+    for n, p in model.named_parameters():
+        if n.endswith("gamma"):
+            p.copy_(torch.randn(p.shape, generator=torch.Generator().manual_seed(5)) * 0.2)
+sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+trainable = [n for n, p in model.named_parameters() if p.requires_grad]
+Bl = 4
+g = torch.Generator().manual_seed(2)
+# well separated images so the contrastive gradient is well conditioned
+images = torch.rand(Bl * world, 3, 224, 224, generator=g) * torch.linspace(0.2, 1.0, Bl * world).view(-1, 1, 1, 1)
+ids = torch.randint(5, 1000, (Bl * world, 77), generator=g); ids[:, 0] = 2; ids[:, -1] = 3
+cfg = dict(patch=16, depth=2, heads=12, text_layers=2, text_heads=12)
+model = model.to(dev).eval().set_compute_dtype(dtype)
+tr = dp.Trainer(model, grad_clip=0.0, lr=0.0)
+sl = slice(rank * Bl, (rank + 1) * Bl)
+m = tr.model
+tr.buckets.enabled = True
+fi = m.encode_image(images[sl].to(dev)); ft = m.encode_text(ids[sl].to(dev))
+loss = tr.criterion(fi, ft)
+loss.backward()
+tr.buckets.wait()
+torch.cuda.synchronize()
+if rank == 0:
+    lo, _, _, _, go = OF.loss_and_grads(sd, images, ids, cfg, trainable)
+    num = den = 0.0
+    worst = ("", 0.0)
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            d = p.grad.double().cpu() - go[n]
+            num += float((d * d).sum()); den += float((go[n] ** 2).sum())
+            e = float(d.abs().max() / go[n].abs().max().clamp_min(1e-30))
+            if e > worst[1]: worst = (n, e)
+    print(f"[{dtype}] world={world} global loss {float(loss):.6f} vs oracle {float(lo):.6f} rel {abs(float(loss)-float(lo))/float(lo):.2e}; "
+          f"grad L2 relerr {(num/den)**0.5:.3e}; worst tensor {worst}")
+dist.barrier()
+dist.destroy_process_group()

@@ -47,7 +47,7 @@ extern "C" {
 /* role of the auxiliary [M,N] operand in a GEMM epilogue */
 #define NGU_AUX_NONE 0
 #define NGU_AUX_RESIDUAL 1 /* C = act(acc + bias) + aux            (x + attn(..), x + mlp(..)) */
-#define NGU_AUX_DACT 2     /* C = (acc + bias) * act'(aux)          (backward through fc1's activation) */
+#define NGU_AUX_DACT 2     /* C = (acc + bias) * aux,  aux = act'(pre) saved by the forward (backward through fc1's activation) */
 
 int ngu_version(void);
 const char* ngu_last_error(void);
@@ -73,7 +73,7 @@ typedef struct ngu_gemm_desc {
   const void* B2; int ldb2;  /* [N,K2] or NULL */
   const float* bias;         /* [N] fp32 or NULL */
   const void* aux; int ldaux;/* [M,N] or NULL (see NGU_AUX_*) */
-  void* Pre;      int ldpre; /* [M,N] pre-activation output when save_pre != 0 */
+  void* Pre;      int ldpre; /* [M,N] when save_pre != 0: act'(acc + bias) (the derivative backward needs); acc + bias if act == NONE */
   int M, N, K, K2;
   int act, aux_mode, save_pre;
   float alpha;

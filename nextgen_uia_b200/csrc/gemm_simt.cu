@@ -59,23 +59,24 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs a) {
       if (gn >= a.N) continue;
       float x = acc[i][j] * a.alpha;
       if (a.bias) x += a.bias[gn];
-      if (a.save_pre) Pre[size_t(gm) * a.ldpre + gn] = from_f32<T>(x);
       const float ax = (a.aux_mode != NGU_AUX_NONE) ? to_f32<T>(aux[size_t(gm) * a.ldaux + gn]) : 0.f;
+      float dact = x;  // what save_pre stores: act'(pre) when there is an activation, else the pre-activation itself
       if (a.aux_mode == NGU_AUX_DACT) {
-        if (a.act == NGU_ACT_GELU) {
-          // exact derivative in check mode
-          const float cdf = 0.5f * (1.f + erff(ax * 0.7071067811865476f));
-          const float pdf = 0.3989422804014327f * expf(-0.5f * ax * ax);
-          x *= cdf + ax * pdf;
-        } else if (a.act == NGU_ACT_QUICKGELU) {
-          const float s = 1.f / (1.f + expf(-1.702f * ax));
-          x *= s * (1.f + 1.702f * ax * (1.f - s));
-        }
+        x *= ax;  // aux = act'(pre) saved by the forward
       } else {
-        if (a.act == NGU_ACT_GELU) x = 0.5f * x * (1.f + erff(x * 0.7071067811865476f));
-        else if (a.act == NGU_ACT_QUICKGELU) x = x / (1.f + expf(-1.702f * x));
+        if (a.act == NGU_ACT_GELU) {
+          const float cdf = 0.5f * (1.f + erff(x * 0.7071067811865476f));
+          const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+          dact = cdf + x * pdf;
+          x = x * cdf;
+        } else if (a.act == NGU_ACT_QUICKGELU) {
+          const float sg = 1.f / (1.f + expf(-1.702f * x));
+          dact = sg * (1.f + 1.702f * x * (1.f - sg));
+          x = x * sg;
+        }
         if (a.aux_mode == NGU_AUX_RESIDUAL) x += ax;
       }
+      if (a.save_pre) Pre[size_t(gm) * a.ldpre + gn] = from_f32<T>(dact);
       C[size_t(gm) * a.ldc + gn] = from_f32<T>(x);
     }
   }

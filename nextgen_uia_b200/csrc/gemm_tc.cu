@@ -25,7 +25,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kNumEpiWarps = 4;
+constexpr int kNumEpiWarps = 8;
 constexpr int kGemmThreads = 32 * (2 + kNumEpiWarps);
 constexpr int kSlabBytes = 32 * 128;  // 32 rows x 64 bf16
 
@@ -34,8 +34,8 @@ struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytes = kNumEpiWarps * 2 * kSlabBytes;
-  static constexpr int kBarBytes = 2048;  // mbarriers + tmem ptr (first 1 KB) and per-warp bias staging (second 1 KB)
+  static constexpr int kEpiBytes = kNumEpiWarps * kSlabBytes;  // one 32x64 slab per epilogue warp
+  static constexpr int kBarBytes = 1024;  // mbarriers + tmem ptr
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/;
   static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes - kBarBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -44,7 +44,9 @@ struct GemmCfg {
 };
 
 struct GemmKernelParams {
-  CUtensorMap tmA, tmB, tmA2, tmB2, tmC, tmPre;
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmC;
+  void* pre;   // [M, ldpre] pre-activation output (save_pre)
+  int ldpre;
   const float* bias;  // [N] fp32 or nullptr
   const bf16* aux;    // [M, ldaux] residual / saved pre-activation, or nullptr
   int ldaux;
@@ -59,17 +61,19 @@ struct GemmKernelParams {
 // (bf16x2 words), bias_s = smem address of this warp's 64 staged bias floats.  Compile-time
 // ACT/AUX so the hot loop stays small (the runtime switch happens once per chunk, warp-uniform).
 template <int ACT, int AUX>
-NGU_DEVINL void epi_chunk(const uint32_t (&v)[64], const uint4 (&ax)[8], uint32_t bias_s, float alpha,
+NGU_DEVINL void epi_chunk(const uint32_t (&v)[64], const uint4 (&ax)[8], float2 bias2, float alpha, bool save,
                           uint32_t (&outp)[32], uint32_t (&prep)[32]) {
+  // bias2 = this lane's (bias[2*lane], bias[2*lane+1]) of the chunk; element j of the row needs lane j/2's value
 #pragma unroll
   for (int j4 = 0; j4 < 16; ++j4) {
     float b[4];
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]) : "r"(bias_s + j4 * 16));
-    float x[4];
+    b[0] = __shfl_sync(0xffffffffu, bias2.x, 2 * j4);
+    b[1] = __shfl_sync(0xffffffffu, bias2.y, 2 * j4);
+    b[2] = __shfl_sync(0xffffffffu, bias2.x, 2 * j4 + 1);
+    b[3] = __shfl_sync(0xffffffffu, bias2.y, 2 * j4 + 1);
+    float x[4], d[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = fmaf(__uint_as_float(v[4 * j4 + i]), alpha, b[i]);
-    prep[2 * j4] = pack_bf16x2(x[0], x[1]);
-    prep[2 * j4 + 1] = pack_bf16x2(x[2], x[3]);
+    for (int i = 0; i < 4; ++i) { x[i] = fmaf(__uint_as_float(v[4 * j4 + i]), alpha, b[i]); d[i] = x[i]; }
     const uint32_t* axw = reinterpret_cast<const uint32_t*>(ax);
     const float2 a01 = unpack_bf16x2(axw[2 * j4]);
     const float2 a23 = unpack_bf16x2(axw[2 * j4 + 1]);
@@ -77,14 +81,18 @@ NGU_DEVINL void epi_chunk(const uint32_t (&v)[64], const uint4 (&ax)[8], uint32_
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (AUX == NGU_AUX_DACT) {
-        if (ACT == NGU_ACT_GELU) x[i] *= gelu_erf_grad(a[i]);
-        else if (ACT == NGU_ACT_QUICKGELU) x[i] *= quick_gelu_grad(a[i]);
+        x[i] *= a[i];  // aux holds act'(pre) saved by the forward epilogue
       } else {
-        if (ACT == NGU_ACT_GELU) x[i] = gelu_erf(x[i]);
-        else if (ACT == NGU_ACT_QUICKGELU) x[i] = quick_gelu(x[i]);
+        if (ACT == NGU_ACT_GELU) {
+          if (save) gelu_and_grad(x[i], x[i], d[i]); else x[i] = gelu_erf(x[i]);
+        } else if (ACT == NGU_ACT_QUICKGELU) {
+          if (save) quick_gelu_and_grad(x[i], x[i], d[i]); else x[i] = quick_gelu(x[i]);
+        }
         if (AUX == NGU_AUX_RESIDUAL) x[i] += a[i];
       }
     }
+    prep[2 * j4] = pack_bf16x2(d[0], d[1]);
+    prep[2 * j4 + 1] = pack_bf16x2(d[2], d[3]);
     outp[2 * j4] = pack_bf16x2(x[0], x[1]);
     outp[2 * j4 + 1] = pack_bf16x2(x[2], x[3]);
   }
@@ -106,7 +114,6 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
   auto tfull_bar = [&](int a) { return sBar + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return sBar + 8u * (2 * Cfg::kStages + 2 + a); };
   const uint32_t sTmemPtr = sBar + 8u * (2 * Cfg::kStages + 4);
-  const uint32_t sBias = sBar + 1024u;  // 4 warps x 64 fp32
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,7 +135,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kNumEpiWarps);
+      mbar_init(tempty_bar(a), (BLOCK_N / 64 >= 2) ? kNumEpiWarps : 4);
     }
     fence_mbar_init();
   }
@@ -202,122 +209,132 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     }
   } else {
     // ================================ epilogue ================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int e = warp - 2;  // slab owner index
-    const uint32_t slab0 = sEpi + (e * 2 + 0) * kSlabBytes;
-    const uint32_t slab1 = sEpi + (e * 2 + 1) * kSlabBytes;
-    int acc = 0;
-    uint32_t acc_ph = 0;
-    uint32_t g = 0;  // running chunk counter -> slab parity
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / n_tiles) * BLOCK_M;
-      const int n0 = (t % n_tiles) * BLOCK_N;
+    // 8 warps: warp w owns TMEM lane quarter (w & 3) and one half of the tile's 64-column chunks, so two warps
+    // share each SM sub-partition and overlap each other's TMEM / global-load / MUFU latencies.
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    constexpr int kChunks = BLOCK_N / 64;
+    constexpr int kPerWarp = kChunks >= 2 ? kChunks / 2 : 1;
+    const int c_begin = (kChunks >= 2 ? (ew >> 2) : 0) * kPerWarp;
+    const bool active = (kChunks >= 2) || (ew < 4);
+    const uint32_t slab = sEpi + ew * kSlabBytes;
+    const bool use_aux = p.aux_mode != NGU_AUX_NONE;
+    const bf16* pre_out = reinterpret_cast<const bf16*>(p.pre);
+
+    auto load_aux = [&](int t, int c, uint4 (&dst)[8]) {
+      const int m0 = (t / n_tiles) * BLOCK_M, nc = (t % n_tiles) * BLOCK_N + c * 64;
       const int row = m0 + q * 32 + lane;
-      mbar_wait(tfull_bar(acc), acc_ph);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
-      constexpr int kChunks = BLOCK_N / 64;
+      const bool ok = use_aux && t < num_tiles && nc < p.N && row < p.M;
+      const uint4* ap = reinterpret_cast<const uint4*>(p.aux + size_t(ok ? row : 0) * p.ldaux + (ok ? nc : 0));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = (ok && nc + j * 8 < p.N) ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
+    };
+
+    if (active) {
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      uint4 axn[8];
+      load_aux(blockIdx.x, c_begin, axn);
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BLOCK_M;
+        const int n0 = (t % n_tiles) * BLOCK_N;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
 #pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
-        const int nc = n0 + c * 64;
-        const bool live = nc < p.N;  // warp-uniform
-        uint32_t v[64];
-        {
-          uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-          uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-          tmem_ld32(t_addr + c * 64, lo);
-          tmem_ld32(t_addr + c * 64 + 32, hi);
-        }
-        // bias chunk: lane l fetches 2 floats, staged in this warp's 256 B of smem, read back broadcast
-        const uint32_t bias_s = sBias + uint32_t(e) * 256u;
-        if (live) {
-          const int n = nc + 2 * lane;
-          float2 bv = make_float2(0.f, 0.f);
-          if (p.bias != nullptr) {
-            bv.x = (n < p.N) ? __ldg(p.bias + n) : 0.f;
-            bv.y = (n + 1 < p.N) ? __ldg(p.bias + n + 1) : 0.f;
+        for (int ci = 0; ci < kPerWarp; ++ci) {
+          const int c = c_begin + ci;
+          const int nc = n0 + c * 64;
+          const bool live = nc < p.N;  // warp-uniform
+          uint32_t v[64];
+          {
+            uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+            uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+            tmem_ld32(t_addr + c * 64, lo);
+            tmem_ld32(t_addr + c * 64 + 32, hi);
           }
+          float2 bias2 = make_float2(0.f, 0.f);
+          if (p.bias != nullptr && live) {
+            const int n = nc + 2 * lane;
+            bias2.x = (n < p.N) ? __ldg(p.bias + n) : 0.f;
+            bias2.y = (n + 1 < p.N) ? __ldg(p.bias + n + 1) : 0.f;
+          }
+          // aux chunk was prefetched one work item ago; start fetching the next one now
+          uint4 ax[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ax[j] = axn[j];
+          if (use_aux) {
+            if (ci + 1 < kPerWarp) load_aux(t, c + 1, axn);
+            else load_aux(t + gridDim.x, c_begin, axn);
+          }
+          tmem_ld_wait();
+          if (ci == kPerWarp - 1) {
+            // all TMEM reads of this accumulator by this warp are done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          if (!live) continue;
+
+          uint32_t outp[32];
+          uint32_t prep[32];
+          {
+            const bool sv = p.save_pre != 0;
+            const int mode = (p.aux_mode == NGU_AUX_DACT) ? 100 : p.act * 3 + p.aux_mode;  // warp-uniform
+            switch (mode) {
+              case 100: epi_chunk<NGU_ACT_NONE, NGU_AUX_DACT>(v, ax, bias2, p.alpha, false, outp, prep); break;
+              case NGU_ACT_NONE * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_NONE, NGU_AUX_RESIDUAL>(v, ax, bias2, p.alpha, sv, outp, prep); break;
+              case NGU_ACT_GELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_GELU, NGU_AUX_NONE>(v, ax, bias2, p.alpha, sv, outp, prep); break;
+              case NGU_ACT_GELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_GELU, NGU_AUX_RESIDUAL>(v, ax, bias2, p.alpha, sv, outp, prep); break;
+              case NGU_ACT_QUICKGELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_NONE>(v, ax, bias2, p.alpha, sv, outp, prep); break;
+              case NGU_ACT_QUICKGELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_RESIDUAL>(v, ax, bias2, p.alpha, sv, outp, prep); break;
+              default: epi_chunk<NGU_ACT_NONE, NGU_AUX_NONE>(v, ax, bias2, p.alpha, sv, outp, prep); break;
+            }
+          }
+          if (lane == 0) tma_store_wait_read<0>();   // previous TMA store has finished reading this warp's slab
           __syncwarp();
-          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_s + lane * 8), "f"(bv.x), "f"(bv.y) : "memory");
-          __syncwarp();
-        }
-        // aux row chunk straight from global (each thread owns one row: 8 x 16 B)
-        uint4 ax[8];
-        const bool has_aux = (p.aux_mode != NGU_AUX_NONE) && live && row < p.M;
-        if (has_aux) {
-          const uint4* ap = reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.ldaux + nc);
+          const uint32_t rbase = slab + lane * 128;
+          if (p.save_pre) {
+            // activation derivative (saved for backward): transpose through the slab, then coalesced 512-byte row groups
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t a = rbase + (uint32_t(j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(prep[4 * j]), "r"(prep[4 * j + 1]),
+                           "r"(prep[4 * j + 2]), "r"(prep[4 * j + 3]) : "memory");
+            }
+            __syncwarp();
+            const int piece = lane & 7, rsub = lane >> 3;
+            bf16* pbase = const_cast<bf16*>(pre_out) + size_t(m0 + q * 32) * p.ldpre + nc + piece * 8;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + rsub;
+              uint4 val;
+              const uint32_t a = slab + r * 128 + (uint32_t(piece ^ (r & 7)) << 4);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(a));
+              if (m0 + q * 32 + r < p.M && nc + piece * 8 < p.N) *reinterpret_cast<uint4*>(pbase + size_t(r) * p.ldpre) = val;
+            }
+            __syncwarp();
+          }
+          // registers -> swizzled slab -> TMA store (per-warp 32 x 64 box)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (nc + j * 8 < p.N) ax[j] = __ldg(ap + j);
-            else ax[j] = make_uint4(0, 0, 0, 0);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ax[j] = make_uint4(0, 0, 0, 0);
-        }
-        tmem_ld_wait();
-        if (c == kChunks - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
-        if (!live) continue;
-
-        uint32_t outp[32];
-        uint32_t prep[32];
-        {
-          const int mode = p.act * 3 + p.aux_mode;  // warp-uniform
-          switch (mode) {
-            case NGU_ACT_NONE * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_NONE, NGU_AUX_NONE>(v, ax, bias_s, p.alpha, outp, prep); break;
-            case NGU_ACT_NONE * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_NONE, NGU_AUX_RESIDUAL>(v, ax, bias_s, p.alpha, outp, prep); break;
-            case NGU_ACT_GELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_GELU, NGU_AUX_NONE>(v, ax, bias_s, p.alpha, outp, prep); break;
-            case NGU_ACT_GELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_GELU, NGU_AUX_RESIDUAL>(v, ax, bias_s, p.alpha, outp, prep); break;
-            case NGU_ACT_GELU * 3 + NGU_AUX_DACT: epi_chunk<NGU_ACT_GELU, NGU_AUX_DACT>(v, ax, bias_s, p.alpha, outp, prep); break;
-            case NGU_ACT_QUICKGELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_NONE>(v, ax, bias_s, p.alpha, outp, prep); break;
-            case NGU_ACT_QUICKGELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_RESIDUAL>(v, ax, bias_s, p.alpha, outp, prep); break;
-            case NGU_ACT_QUICKGELU * 3 + NGU_AUX_DACT: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_DACT>(v, ax, bias_s, p.alpha, outp, prep); break;
-            default: epi_chunk<NGU_ACT_NONE, NGU_AUX_NONE>(v, ax, bias_s, p.alpha, outp, prep); break;
-          }
-        }
-
-        // registers -> swizzled slab -> TMA store (per-warp 32 x 64 box)
-        const uint32_t slab = (p.save_pre || (g & 1u) == 0) ? slab0 : slab1;
-        if (lane == 0) {
-          if (p.save_pre) tma_store_wait_read<0>();
-          else tma_store_wait_read<1>();
-        }
-        __syncwarp();
-        const uint32_t rbase = slab + lane * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t a = rbase + (uint32_t(j ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(outp[4 * j]),
-                       "r"(outp[4 * j + 1]), "r"(outp[4 * j + 2]), "r"(outp[4 * j + 3])
-                       : "memory");
-        }
-        if (p.save_pre) {
-          const uint32_t rb1 = slab1 + lane * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t a = rb1 + (uint32_t(j ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(prep[4 * j]),
-                         "r"(prep[4 * j + 1]), "r"(prep[4 * j + 2]), "r"(prep[4 * j + 3])
+            const uint32_t a = rbase + (uint32_t(j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(outp[4 * j]),
+                         "r"(outp[4 * j + 1]), "r"(outp[4 * j + 2]), "r"(outp[4 * j + 3])
                          : "memory");
           }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmC, slab, nc, m0 + q * 32);
+            tma_store_commit();
+          }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&p.tmC, slab, nc, m0 + q * 32);
-          if (p.save_pre) tma_store_2d(&p.tmPre, slab1, nc, m0 + q * 32);
-          tma_store_commit();
-        }
-        ++g;
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
-      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      if (lane == 0) tma_store_wait<0>();
     }
-    if (lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -344,11 +361,8 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     p.tmB2 = p.tmB;
   }
   if ((rc = make_tmap_2d_bf16(&p.tmC, a.C, a.M, a.N, a.ldc, 32, 64, true))) return rc;
-  if (a.save_pre) {
-    if ((rc = make_tmap_2d_bf16(&p.tmPre, a.Pre, a.M, a.N, a.ldpre, 32, 64, true))) return rc;
-  } else {
-    p.tmPre = p.tmC;
-  }
+  p.pre = a.Pre;
+  p.ldpre = a.ldpre;
   p.bias = a.bias;
   p.aux = reinterpret_cast<const bf16*>(a.aux);
   p.ldaux = a.ldaux;
@@ -381,6 +395,10 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   }
   if (a.aux_mode != NGU_AUX_NONE && (a.aux == nullptr || (a.ldaux % 8) || (a.N % 8))) {
     set_last_error("gemm_tc: aux operand needs a pointer, ldaux %% 8 == 0 and N %% 8 == 0");
+    return NGU_ERR_ALIGN;
+  }
+  if (a.save_pre && (a.Pre == nullptr || (a.ldpre % 8) || (a.N % 8))) {
+    set_last_error("gemm_tc: save_pre needs a Pre pointer, ldpre %% 8 == 0 and N %% 8 == 0");
     return NGU_ERR_ALIGN;
   }
   int bn = a.block_n;

@@ -44,7 +44,8 @@ def _f32(t):
 # ------------------------------------------------------------------------------------------------
 def gemm(A, B, *, bias=None, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save_pre=False,
          A2=None, B2=None, alpha=1.0, out=None, block_n=0, force_simt=False):
-    """C[M,N] = epi(alpha * (A[M,K] @ B[N,K]^T + A2 @ B2^T)); returns C or (C, Pre)."""
+    """C[M,N] = epi(alpha * (A[M,K] @ B[N,K]^T + A2 @ B2^T)); returns C, or (C, D) with save_pre where
+    D = act'(pre-activation) (the factor AUX_DACT multiplies by in backward; the pre-activation itself if act is NONE)."""
     _need_cuda(A, B)
     assert A.dim() == 2 and B.dim() == 2 and A.shape[1] == B.shape[1] and A.dtype == B.dtype
     assert A.stride(1) == 1 and B.stride(1) == 1

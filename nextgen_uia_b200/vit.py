@@ -50,10 +50,10 @@ class BlockFunction(torch.autograd.Function):
         ao, lse = ops.attn_fwd_packed(qkv, B, N, H, dh)
         x1, sv_p = proj_fwd(ao, pp, aux=x2, aux_mode=L.AUX_RESIDUAL, seed=sp)
         xn2, m2, r2 = ops.ln_fwd(x1, blk.norm2.weight.detach(), blk.norm2.bias.detach(), blk.norm2.eps)
-        (hact, hpre), _ = proj_fwd(xn2, p1, act=act, save_pre=True)
+        (hact, hder), _ = proj_fwd(xn2, p1, act=act, save_pre=True)   # hder = act'(pre), what backward multiplies by
         y, _ = proj_fwd(hact, p2, aux=x1, aux_mode=L.AUX_RESIDUAL)
 
-        ctx.save_for_backward(x2, m1, r1, qkv, ao, lse, x1, m2, r2, hpre)
+        ctx.save_for_backward(x2, m1, r1, qkv, ao, lse, x1, m2, r2, hder)
         ctx.lora_saved = (sv_q, sv_p)
         ctx.projs = (pq, pp, p1, p2)
         ctx.blk = blk
@@ -62,7 +62,7 @@ class BlockFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x2, m1, r1, qkv, ao, lse, x1, m2, r2, hpre = ctx.saved_tensors
+        x2, m1, r1, qkv, ao, lse, x1, m2, r2, hder = ctx.saved_tensors
         pq, pp, p1, p2 = ctx.projs
         sv_q, sv_p = ctx.lora_saved
         blk = ctx.blk
@@ -70,7 +70,7 @@ class BlockFunction(torch.autograd.Function):
         need = ctx.needs_input_grad
         dy2 = dy.contiguous().view(B * N, D)
         # MLP:  y = x1 + fc2(act(fc1(LN2 x1)))
-        dhpre = ops.gemm(dy2, p2.WT, act=act, aux=hpre, aux_mode=L.AUX_DACT)          # (dy W2) * act'(pre)
+        dhpre = ops.gemm(dy2, p2.WT, aux=hder, aux_mode=L.AUX_DACT)                   # (dy W2) * act'(pre)
         dxn2 = ops.gemm(dhpre, p1.WT)
         dx1 = ops.ln_bwd(dxn2, x1, m2, r2, blk.norm2.weight.detach(), dres=dy2)      # dy + LN2bwd
         # attention:  x1 = x + proj(attn(qkv(LN1 x)))

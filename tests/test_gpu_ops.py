@@ -40,20 +40,27 @@ def test_gemm_epilogues(dtype):
     A2 = torch.randn(M, r).to(dev(), dtype)
     B2 = (torch.randn(N, r) * 0.1).to(dev(), dtype)
     base = (A.double() @ B.double().t() + bias.double()).cpu()
-    # GELU + saved pre-activation
-    C, Pre = ops.gemm(A, B, bias=bias, act=L.ACT_GELU, save_pre=True)
-    assert relerr(Pre, base) < TOL[dtype] and relerr(C, F.gelu(base)) < TOL[dtype]
-    # QuickGELU
-    C = ops.gemm(A, B, bias=bias, act=L.ACT_QUICKGELU)
-    assert relerr(C, base * torch.sigmoid(1.702 * base)) < TOL[dtype]
+    # GELU + saved derivative gelu'(pre) (what the backward epilogue multiplies by)
+    C, Der = ops.gemm(A, B, bias=bias, act=L.ACT_GELU, save_pre=True)
+    bb = base.clone().requires_grad_(True)
+    (dg_ref,) = torch.autograd.grad(F.gelu(bb).sum(), bb)
+    assert relerr(Der, dg_ref) < TOL[dtype] and relerr(C, F.gelu(base)) < TOL[dtype]
+    # no activation: save_pre stores the pre-activation itself
+    C0, P0 = ops.gemm(A, B, bias=bias, save_pre=True)
+    assert relerr(P0, base) < TOL[dtype] and relerr(C0, base) < TOL[dtype]
+    # QuickGELU (+ derivative)
+    C, Der = ops.gemm(A, B, bias=bias, act=L.ACT_QUICKGELU, save_pre=True)
+    bb = base.clone().requires_grad_(True)
+    (dq_ref,) = torch.autograd.grad((bb * torch.sigmoid(1.702 * bb)).sum(), bb)
+    assert relerr(C, base * torch.sigmoid(1.702 * base)) < TOL[dtype] and relerr(Der, dq_ref) < TOL[dtype]
+    C = ops.gemm(A, B, bias=bias, act=L.ACT_GELU)
+    assert relerr(C, F.gelu(base)) < TOL[dtype]
     # residual
     C = ops.gemm(A, B, bias=bias, aux=aux, aux_mode=L.AUX_RESIDUAL)
     assert relerr(C, base + aux.double().cpu()) < TOL[dtype]
-    # backward through GELU: (acc) * gelu'(aux)
-    a = aux.double().cpu().requires_grad_(True)
-    (dg,) = torch.autograd.grad(F.gelu(a).sum(), a)
-    C = ops.gemm(A, B, act=L.ACT_GELU, aux=aux, aux_mode=L.AUX_DACT)
-    assert relerr(C, (base - bias.double().cpu()) * dg) < TOL[dtype]
+    # backward through the activation: (acc) * aux with aux = saved derivative
+    C = ops.gemm(A, B, aux=aux, aux_mode=L.AUX_DACT)
+    assert relerr(C, (base - bias.double().cpu()) * aux.double().cpu()) < TOL[dtype]
     # low-rank pair (LoRA) + alpha
     C = ops.gemm(A, B, bias=bias, A2=A2, B2=B2, alpha=0.5)
     ref = 0.5 * (A.double() @ B.double().t() + A2.double() @ B2.double().t()).cpu() + bias.double().cpu()

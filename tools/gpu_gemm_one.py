@@ -16,6 +16,10 @@ d.A, d.lda, d.B, d.ldb, d.C, d.ldc = A.data_ptr(), K, B.data_ptr(), K, C.data_pt
 d.bias = bias.data_ptr()
 d.M, d.N, d.K = M, N, K
 d.act = act
+save = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+if save:
+    Pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    d.Pre, d.ldpre, d.save_pre = Pre.data_ptr(), N, 1
 d.alpha = 1.0
 for _ in range(3):
     L.check(lib.ngu_gemm(ctypes.byref(d), torch.cuda.current_stream().cuda_stream))

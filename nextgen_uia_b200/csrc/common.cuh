@@ -433,11 +433,15 @@ NGU_DEVINL uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) 
   }
   return make_uint4(c[0], c[1], c[2], c[3]);
 }
-// keep-mask for element `idx` of a tensor under dropout probability p: returns 1/(1-p) or 0
+// keep-mask for element `idx` of a tensor under dropout probability p: returns 1/(1-p) or 0.
+// Counter-based (stateless, regenerated in backward from seed + element index): splitmix64 finaliser of
+// (seed, idx) — ~12 integer instructions per element instead of a 10-round Philox.
 NGU_DEVINL float dropout_scale(uint64_t seed, uint64_t idx, float p) {
-  const uint4 r = philox4x32(uint32_t(idx >> 2), uint32_t(idx >> 34), uint32_t(seed), uint32_t(seed >> 32));
-  const uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
-  const float u = float(w >> 8) * (1.0f / 16777216.0f);
+  uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = float(uint32_t(z >> 40)) * (1.0f / 16777216.0f);
   return u >= p ? 1.0f / (1.0f - p) : 0.0f;
 }
 }  // namespace ngu

@@ -246,11 +246,332 @@ mona_conv_bwd_kernel(const T* __restrict__ h, const T* __restrict__ dg, T* __res
   atomicAdd(gr.db1 + c, db1_acc);
 }
 
+// =====================================================================================================
+// Register-blocked full-tile kernels (grids up to 16x16 tokens, e.g. ViT-B/16 @ 224 -> 14x14).
+// Same math as the generic kernels above; differences are purely about shared-memory traffic:
+//   * stencil taps (49) and one projector row/column (64) live in REGISTERS of the thread that owns the channel,
+//   * the stencil is evaluated on 8-wide output strips with a 14-wide sliding window (13/49 loads per FMA),
+//   * the 1x1 projector reads the token's 64 inputs as 128-bit shared-memory broadcasts.
+// Intermediates z / da / dz stay in smem in the activation dtype (two CTAs per SM in bf16).
+// =====================================================================================================
+constexpr int kStrip = 8;
+
+struct FastSmem {
+  float kc[49][C];
+  float bc[C];
+  float pt[C][C];  // pt[i][o] = P[o][i]
+  float bp[C];
+};
+
+template <typename T>
+NGU_DEVINL void fast_load_common(FastSmem& s, T* hs, const T* hb, const ngu_mona_conv_weights& w, int HW, int has_cls) {
+  for (int i = threadIdx.x; i < 49 * C; i += kThreads) {
+    const int c = i % C, t = i / C;
+    const int ky = t / 7, kx = t % 7;
+    float v = w.k7[c * 49 + t];
+    if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) v += w.k5[c * 25 + (ky - 1) * 5 + (kx - 1)];
+    if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) v += w.k3[c * 9 + (ky - 2) * 3 + (kx - 2)];
+    v *= (1.0f / 3.0f);
+    if (t == 24) v += 1.0f;
+    s.kc[t][c] = v;
+  }
+  for (int i = threadIdx.x; i < C * C; i += kThreads) s.pt[i % C][i / C] = w.P[i];
+  if (threadIdx.x < C) {
+    s.bc[threadIdx.x] = (w.b3[threadIdx.x] + w.b5[threadIdx.x] + w.b7[threadIdx.x]) * (1.0f / 3.0f);
+    s.bp[threadIdx.x] = w.bp[threadIdx.x];
+  }
+  constexpr int V = Vec<T>::N;
+  const T* src = hb + has_cls * C;
+  for (int i = threadIdx.x * V; i < HW * C; i += kThreads * V) *reinterpret_cast<uint4*>(hs + i) = *reinterpret_cast<const uint4*>(src + i);
+}
+
+// out[y][x0 + j] = bias + sum_{ky,kx} k[ky*7 + (FLIP ? 6-kx : kx)] * in[y + (FLIP ? 3-ky : ky-3)][x0 + j + kx - 3]   (channel c)
+template <typename T, bool FLIP>
+NGU_DEVINL void stencil_strip(const T* in, const float (&k)[49], float bias, int y, int x0, int H, int W, int c, float (&acc)[kStrip]) {
+#pragma unroll
+  for (int j = 0; j < kStrip; ++j) acc[j] = bias;
+#pragma unroll
+  for (int ky = 0; ky < 7; ++ky) {
+    const int yy = FLIP ? y + 3 - ky : y + ky - 3;
+    if (yy < 0 || yy >= H) continue;
+    float win[kStrip + 6];
+#pragma unroll
+    for (int i = 0; i < kStrip + 6; ++i) {
+      const int xx = x0 + i - 3;
+      win[i] = (xx >= 0 && xx < W) ? to_f32<T>(in[(yy * W + xx) * C + c]) : 0.f;
+    }
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const float kv = k[ky * 7 + (FLIP ? 6 - kx : kx)];
+#pragma unroll
+      for (int j = 0; j < kStrip; ++j) acc[j] = fmaf(kv, win[j + kx], acc[j]);
+    }
+  }
+}
+
+// a = z[p][o] + bp[o] + sum_i pt[i][o] z[p][i], z row read as 128-bit broadcasts
+template <typename T>
+NGU_DEVINL float proj_token(const T* zrow, const float (&pcol)[C], float bp, int o) {
+  float acc[4] = {to_f32<T>(zrow[o]) + bp, 0.f, 0.f, 0.f};  // 4 independent FMA chains
+  constexpr int V = Vec<T>::N;
+#pragma unroll
+  for (int i0 = 0; i0 < C; i0 += V) {
+    float zv[V];
+    Vec<T>::load(zrow + i0, zv);
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i & 3] = fmaf(pcol[i0 + i], zv[i], acc[i & 3]);
+  }
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+mona_conv_fwd_fast_kernel(const T* __restrict__ h, T* __restrict__ g, ngu_mona_conv_weights w, int N, int H, int W,
+                          int has_cls, float drop_p, uint64_t seed) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  FastSmem& s = *reinterpret_cast<FastSmem*>(smem_dyn);
+  const int HW = H * W;
+  T* hs = reinterpret_cast<T*>(smem_dyn + sizeof(FastSmem));
+  T* zs = hs + HW * C;
+  const int img = blockIdx.x;
+  const T* hb = h + size_t(img) * N * C;
+  T* gb = g + size_t(img) * N * C;
+  fast_load_common<T>(s, hs, hb, w, HW, has_cls);
+  const int c = threadIdx.x & (C - 1), grp = threadIdx.x >> 6;
+  if (has_cls && grp == 0) {
+    float v = gelu_t<T>(to_f32<T>(hb[c]));
+    if (drop_p > 0.f) v *= dropout_scale(seed, (uint64_t(img) * N) * C + c, drop_p);
+    gb[c] = from_f32<T>(v);
+  }
+  __syncthreads();
+  {
+    float k[49];
+#pragma unroll
+    for (int t = 0; t < 49; ++t) k[t] = s.kc[t][c];
+    const float bias = s.bc[c];
+    const int spr = (W + kStrip - 1) / kStrip;
+    for (int st = grp; st < H * spr; st += kThreads / C) {
+      const int y = st / spr, x0 = (st % spr) * kStrip;
+      float acc[kStrip];
+      stencil_strip<T, false>(hs, k, bias, y, x0, H, W, c, acc);
+#pragma unroll
+      for (int j = 0; j < kStrip; ++j)
+        if (x0 + j < W) zs[(y * W + x0 + j) * C + c] = from_f32<T>(acc[j]);
+    }
+  }
+  __syncthreads();
+  {
+    float pcol[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) pcol[i] = s.pt[i][c];
+    const float bp = s.bp[c];
+    for (int p = grp; p < HW; p += kThreads / C) {
+      float v = gelu_t<T>(proj_token<T>(zs + p * C, pcol, bp, c));
+      const uint64_t tok = uint64_t(img) * N + has_cls + p;
+      if (drop_p > 0.f) v *= dropout_scale(seed, tok * C + c, drop_p);
+      gb[(has_cls + p) * C + c] = from_f32<T>(v);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+mona_conv_bwd_fast_kernel(const T* __restrict__ h, const T* __restrict__ dg, T* __restrict__ dh, ngu_mona_conv_weights w,
+                          ngu_mona_conv_grads gr, int N, int H, int W, int has_cls, float drop_p, uint64_t seed) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  FastSmem& s = *reinterpret_cast<FastSmem*>(smem_dyn);
+  const int HW = H * W;
+  T* hs = reinterpret_cast<T*>(smem_dyn + sizeof(FastSmem));
+  T* zs = hs + HW * C;    // z, later dz
+  T* das = zs + HW * C;   // da
+  const int img = blockIdx.x;
+  const T* hb = h + size_t(img) * N * C;
+  const T* dgb = dg + size_t(img) * N * C;
+  T* dhb = dh + size_t(img) * N * C;
+  fast_load_common<T>(s, hs, hb, w, HW, has_cls);
+  const int c = threadIdx.x & (C - 1), grp = threadIdx.x >> 6;
+  float db1_acc = 0.f;
+  if (has_cls && grp == 0) {
+    float v = to_f32<T>(dgb[c]) * gelu_grad_t<T>(to_f32<T>(hb[c]));
+    if (drop_p > 0.f) v *= dropout_scale(seed, (uint64_t(img) * N) * C + c, drop_p);
+    dhb[c] = from_f32<T>(v);
+    db1_acc += v;
+  }
+  __syncthreads();
+  const int spr = (W + kStrip - 1) / kStrip;
+  // ---- phase 1: z = stencil(h)
+  {
+    float k[49];
+#pragma unroll
+    for (int t = 0; t < 49; ++t) k[t] = s.kc[t][c];
+    const float bias = s.bc[c];
+    for (int st = grp; st < H * spr; st += kThreads / C) {
+      const int y = st / spr, x0 = (st % spr) * kStrip;
+      float acc[kStrip];
+      stencil_strip<T, false>(hs, k, bias, y, x0, H, W, c, acc);
+#pragma unroll
+      for (int j = 0; j < kStrip; ++j)
+        if (x0 + j < W) zs[(y * W + x0 + j) * C + c] = from_f32<T>(acc[j]);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: da = dg * mask * gelu'(z + P z + bp)
+  {
+    float pcol[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) pcol[i] = s.pt[i][c];
+    const float bp = s.bp[c];
+    for (int p = grp; p < HW; p += kThreads / C) {
+      const float a = proj_token<T>(zs + p * C, pcol, bp, c);
+      float v = to_f32<T>(dgb[(has_cls + p) * C + c]) * gelu_grad_t<T>(a);
+      const uint64_t tok = uint64_t(img) * N + has_cls + p;
+      if (drop_p > 0.f) v *= dropout_scale(seed, tok * C + c, drop_p);
+      das[p * C + c] = from_f32<T>(v);
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: dP[o = c][i in 16*grp..+15] = sum_p da[p][o] z[p][i];  dbp[o] = sum_p da[p][o]
+  {
+    float dP[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dP[i] = 0.f;
+    float dbp_acc = 0.f;
+    constexpr int V = Vec<T>::N;
+    for (int p = 0; p < HW; ++p) {
+      const float d = to_f32<T>(das[p * C + c]);
+      dbp_acc += d;
+#pragma unroll
+      for (int i0 = 0; i0 < 16; i0 += V) {
+        float zv[V];
+        Vec<T>::load(zs + p * C + grp * 16 + i0, zv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) dP[i0 + i] = fmaf(d, zv[i], dP[i0 + i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) atomicAdd(gr.dP + c * C + grp * 16 + i, dP[i]);
+    if (grp == 0) atomicAdd(gr.dbp + c, dbp_acc);
+  }
+  __syncthreads();
+  // ---- phase 4: dz[p][i = c] = da[p][i] + sum_o P[o][i] da[p][o]   (overwrites z)
+  {
+    float prow[C];
+#pragma unroll
+    for (int o = 0; o < C; ++o) prow[o] = s.pt[c][o];
+    constexpr int V = Vec<T>::N;
+    for (int p = grp; p < HW; p += kThreads / C) {
+      float acc[4] = {to_f32<T>(das[p * C + c]), 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int o0 = 0; o0 < C; o0 += V) {
+        float dv[V];
+        Vec<T>::load(das + p * C + o0, dv);
+#pragma unroll
+        for (int o = 0; o < V; ++o) acc[o & 3] = fmaf(prow[o0 + o], dv[o], acc[o & 3]);
+      }
+      zs[p * C + c] = from_f32<T>((acc[0] + acc[1]) + (acc[2] + acc[3]));
+    }
+  }
+  __syncthreads();
+  // ---- phase 5: dh = transposed stencil of dz;  phase 6: stencil weight grads dk[t] = sum_p dz[p] h[p + off_t]
+  float dbc_acc = 0.f;
+  float dk[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) dk[t] = 0.f;
+  {
+    float k[49];
+#pragma unroll
+    for (int t = 0; t < 49; ++t) k[t] = s.kc[t][c];
+    for (int st = grp; st < H * spr; st += kThreads / C) {
+      const int y = st / spr, x0 = (st % spr) * kStrip;
+      float acc[kStrip];
+      stencil_strip<T, true>(zs, k, 0.f, y, x0, H, W, c, acc);
+#pragma unroll
+      for (int j = 0; j < kStrip; ++j)
+        if (x0 + j < W) { dhb[(has_cls + y * W + x0 + j) * C + c] = from_f32<T>(acc[j]); db1_acc += acc[j]; }
+    }
+  }
+  for (int st = grp; st < H * spr; st += kThreads / C) {
+    const int y = st / spr, x0 = (st % spr) * kStrip;
+    float dzv[kStrip];
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j) {
+      dzv[j] = (x0 + j < W) ? to_f32<T>(zs[(y * W + x0 + j) * C + c]) : 0.f;
+      dbc_acc += dzv[j];
+    }
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+      const int yy = y + ky - 3;
+      if (yy < 0 || yy >= H) continue;
+      float win[kStrip + 6];
+#pragma unroll
+      for (int i = 0; i < kStrip + 6; ++i) {
+        const int xx = x0 + i - 3;
+        win[i] = (xx >= 0 && xx < W) ? to_f32<T>(hs[(yy * W + xx) * C + c]) : 0.f;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        float a = dk[ky * 7 + kx];
+#pragma unroll
+        for (int j = 0; j < kStrip; ++j) a = fmaf(dzv[j], win[j + kx], a);
+        dk[ky * 7 + kx] = a;
+      }
+    }
+  }
+  __syncthreads();
+  // cross-group reduction of dk through smem (reuses the z / da tiles), then one atomic per (tap, channel)
+  float* red = reinterpret_cast<float*>(zs);  // needs 4*49*64 floats = 50,176 B <= 2 tiles when HW*C*sizeof(T)*2 >= that
+  const bool red_ok = size_t(HW) * C * sizeof(T) * 2 >= size_t(4) * 49 * C * sizeof(float);
+  if (red_ok) {
+#pragma unroll
+    for (int t = 0; t < 49; ++t) red[(grp * 49 + t) * C + c] = dk[t];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 49 * C; i += kThreads) {
+      const int t = i / C, cc = i % C;
+      const float v = (red[(0 * 49 + t) * C + cc] + red[(1 * 49 + t) * C + cc] + red[(2 * 49 + t) * C + cc] + red[(3 * 49 + t) * C + cc]) * (1.0f / 3.0f);
+      const int ky = t / 7, kx = t % 7;
+      atomicAdd(gr.dk7 + cc * 49 + t, v);
+      if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) atomicAdd(gr.dk5 + cc * 25 + (ky - 1) * 5 + (kx - 1), v);
+      if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) atomicAdd(gr.dk3 + cc * 9 + (ky - 2) * 3 + (kx - 2), v);
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 49; ++t) {
+      const float v = dk[t] * (1.0f / 3.0f);
+      const int ky = t / 7, kx = t % 7;
+      atomicAdd(gr.dk7 + c * 49 + t, v);
+      if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) atomicAdd(gr.dk5 + c * 25 + (ky - 1) * 5 + (kx - 1), v);
+      if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) atomicAdd(gr.dk3 + c * 9 + (ky - 2) * 3 + (kx - 2), v);
+    }
+  }
+  {
+    const float bsum = dbc_acc * (1.0f / 3.0f);
+    atomicAdd(gr.db3 + c, bsum);
+    atomicAdd(gr.db5 + c, bsum);
+    atomicAdd(gr.db7 + c, bsum);
+    atomicAdd(gr.db1 + c, db1_acc);
+  }
+}
+
+template <typename T>
+bool fast_ok(const ngu_mona_conv_desc& d, bool bwd) {
+  const int HW = d.H * d.W;
+  const size_t smem = sizeof(FastSmem) + size_t(HW) * C * sizeof(T) * (bwd ? 3 : 2);
+  return d.W <= 16 && d.H <= 16 && smem <= 227 * 1024;
+}
+
 template <typename T>
 int conv_smem_bytes(int HW, bool bwd) { return int(sizeof(ConvSmem)) + HW * C * int(sizeof(T)) * (bwd ? 2 : 1); }
 
 template <typename T>
 int launch_fwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
+  if (fast_ok<T>(d, false)) {
+    const int smf = int(sizeof(FastSmem)) + d.H * d.W * C * int(sizeof(T)) * 2;
+    cudaError_t e = cudaFuncSetAttribute(mona_conv_fwd_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
+    if (e != cudaSuccess) return cuda_status(e, "mona_conv_fwd attr");
+    mona_conv_fwd_fast_kernel<T><<<d.B, kThreads, smf, st>>>(reinterpret_cast<const T*>(d.h), reinterpret_cast<T*>(d.g), d.w, d.N, d.H,
+                                                              d.W, d.has_cls, d.drop_p, d.seed);
+    return check_launch("mona_conv_fwd");
+  }
   const int smem = conv_smem_bytes<T>(d.H * d.W, false);
   if (smem > 227 * 1024) { set_last_error("mona_conv_fwd: %dx%d grid needs %d B smem", d.H, d.W, smem); return NGU_ERR_SHAPE; }
   cudaError_t e = cudaFuncSetAttribute(mona_conv_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -261,6 +582,15 @@ int launch_fwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
 }
 template <typename T>
 int launch_bwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
+  if (fast_ok<T>(d, true)) {
+    const int smf = int(sizeof(FastSmem)) + d.H * d.W * C * int(sizeof(T)) * 3;
+    cudaError_t e = cudaFuncSetAttribute(mona_conv_bwd_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
+    if (e != cudaSuccess) return cuda_status(e, "mona_conv_bwd attr");
+    mona_conv_bwd_fast_kernel<T><<<d.B, kThreads, smf, st>>>(reinterpret_cast<const T*>(d.h), reinterpret_cast<const T*>(d.dg),
+                                                              reinterpret_cast<T*>(d.dh), d.w, d.gr, d.N, d.H, d.W, d.has_cls,
+                                                              d.drop_p, d.seed);
+    return check_launch("mona_conv_bwd");
+  }
   const int smem = conv_smem_bytes<T>(d.H * d.W, true);
   if (smem > 227 * 1024) { set_last_error("mona_conv_bwd: %dx%d grid needs %d B smem", d.H, d.W, smem); return NGU_ERR_SHAPE; }
   cudaError_t e = cudaFuncSetAttribute(mona_conv_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

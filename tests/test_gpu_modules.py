@@ -51,6 +51,34 @@ def test_mona_seq_first_768(dtype):
     assert y.shape == x.shape and relerr(y, ref) < TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype,grid", [(torch.float32, 18), (torch.bfloat16, 24), (torch.bfloat16, 22), (torch.float32, 16)])
+def test_mona_large_grids_vs_oracle(dtype, grid):
+    """grids above 16x16 (ViT-L/14@336 -> 24x24, ViT-B/16@352 -> 22x22) take the generic chunked conv-stage kernels."""
+    from src.adapters import BaselineMona, BatchFirstMonaWrapper
+    from oracle import functional as OF
+    torch.manual_seed(0)
+    D = 256
+    m = BatchFirstMonaWrapper(BaselineMona(D, 64))
+    with torch.no_grad():
+        m.clip_mona.gamma.copy_(torch.randn(D) * 0.3)
+    sd = {k: v.detach().double() for k, v in m.state_dict().items()}
+    m = m.to(dev()).eval()
+    N = grid * grid + 1
+    x = torch.randn(2, N, D).to(dtype)
+    gy = torch.randn(2, N, D).to(dtype)
+    xg = x.to(dev()).requires_grad_(True)
+    y = m(xg, (grid, grid))
+    (y * gy.to(dev())).sum().backward()
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.double().requires_grad_(True)
+    yo = OF.mona(xo, p, "clip_mona.", (grid, grid), True)
+    names = [n for n, _ in m.named_parameters()]
+    go = torch.autograd.grad((yo * gy.double()).sum(), [xo] + [p[n] for n in names])
+    assert relerr(y, yo) < TOL[dtype] and relerr(xg.grad, go[0]) < GTOL[dtype]
+    for (n, prm), gref in zip(m.named_parameters(), go[1:]):
+        assert relerr(prm.grad, gref) < GTOL[dtype], n
+
+
 def test_mona_dropout_statistics():
     """train mode: keep-rate ~ 0.9 with 1/(1-p) scaling, same mask in backward (reference mona.py:109,147)."""
     from nextgen_uia_b200 import ops

@@ -99,16 +99,13 @@ NGU_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin on an mbarrier phase.  A watchdog traps after ~4 s so a protocol bug surfaces as a
-// CUDA error on the host instead of wedging the GPU.
+// Spin on an mbarrier phase (try_wait suspends in hardware between probes).  A spin-count watchdog traps
+// instead of wedging the GPU if a barrier protocol bug ever leaves a phase incomplete.
 NGU_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0 && (clock64() - t0) > 8000000000ll) {
-      printf("ngu: mbarrier watchdog block %d thread %d bar %u parity %u\n", blockIdx.x,
-             threadIdx.x, bar, parity);
+    if (++spins > (1u << 28)) {
+      printf("ngu: mbarrier watchdog block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
   }
@@ -132,6 +129,25 @@ NGU_DEVINL void tma_load_2d(uint32_t smem_dst, const CUtensorMap* m, uint32_t ba
       " [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
+}
+// multicast variant: the box lands at the same smem offset of every CTA in cta_mask and completes tx bytes on the
+// mbarrier at the same offset in each of them
+NGU_DEVINL void tma_load_2d_mcast(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t cta_mask,
+                                  uint64_t hint = kEvictNormal) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5, %6;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask), "l"(hint)
+      : "memory");
+}
+NGU_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+NGU_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 NGU_DEVINL void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -193,6 +209,13 @@ NGU_DEVINL void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint3
 // mbarrier arrive when all previously issued tcgen05 ops of this thread have completed.
 NGU_DEVINL void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+
+// same, arriving on the mbarrier at this smem offset in every CTA of cta_mask
+NGU_DEVINL void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
                : "memory");
 }
 
@@ -301,22 +324,28 @@ NGU_DEVINL float gelu_erf_grad(float x) {
   const float cdf = x >= 0.f ? 1.0f - tail : tail;
   return fmaf(x, pdf, cdf);
 }
-// gelu(x) and gelu'(x) together from ONE MUFU: pdf = phi(x); Phi(-|x|) = pdf * m(|x|) (degree-6 Mills-ratio fit,
-// |Phi err| <= 4e-4, |gelu err| <= 8e-5: below bf16 resolution).  Used by the GEMM epilogue that emits both the
-// activation and its derivative so the backward epilogue is a plain multiply.
+// gelu(x) and gelu'(x) together from ONE MUFU: Phi(x) = 0.5 + 0.5 tanh(x (a0 + a1 x^2 + a2 x^4)) with (a0,a1,a2)
+// fitted to the exact erf CDF (|Phi err| <= 2e-5 + tanh.approx error, |gelu err| <= 5e-5, |gelu' err| <= 1.3e-4:
+// below bf16 resolution).  The GEMM epilogue emits the activation and its derivative so the backward epilogue
+// is a plain multiply.
+NGU_DEVINL float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kGa0 = 7.97704294e-01f, kGa1 = 3.68194288e-02f, kGa2 = -3.20606757e-04f;
+NGU_DEVINL float gelu_fast(float x) {
+  const float x2 = x * x;
+  const float t = tanh_approx(x * fmaf(fmaf(kGa2, x2, kGa1), x2, kGa0));
+  return x * fmaf(0.5f, t, 0.5f);
+}
 NGU_DEVINL void gelu_and_grad(float x, float& y, float& dy) {
-  const float a = fminf(fabsf(x), 6.5f);
-  const float pdf = 0.3989422804014327f * ex2_approx(-0.7213475204444817f * a * a);
-  float m = fmaf(4.388972011e-04f, a, -7.882993668e-03f);
-  m = fmaf(m, a, 5.726995692e-02f);
-  m = fmaf(m, a, -2.265181839e-01f);
-  m = fmaf(m, a, 5.643693805e-01f);
-  m = fmaf(m, a, -9.844003916e-01f);
-  m = fmaf(m, a, 1.252348423e+00f);
-  const float tail = pdf * m;
-  const float cdf = x >= 0.f ? 1.0f - tail : tail;
+  const float x2 = x * x;
+  const float t = tanh_approx(x * fmaf(fmaf(kGa2, x2, kGa1), x2, kGa0));
+  const float cdf = fmaf(0.5f, t, 0.5f);
+  const float du = fmaf(fmaf(5.0f * kGa2, x2, 3.0f * kGa1), x2, kGa0);
   y = x * cdf;
-  dy = fmaf(x, pdf, cdf);
+  dy = fmaf(0.5f * x * fmaf(-t, t, 1.0f), du, cdf);
 }
 NGU_DEVINL float rcp_approx(float x) {
   float y;

@@ -45,6 +45,7 @@ struct GemmCfg {
 
 struct GemmKernelParams {
   CUtensorMap tmA, tmB, tmA2, tmB2, tmC;
+  CUtensorMap tmBh, tmB2h;  // B with a half-height box (cluster multicast: each CTA fetches BLOCK_N/2 rows)
   void* pre;   // [M, ldpre] pre-activation output (save_pre)
   int ldpre;
   const float* bias;  // [N] fp32 or nullptr
@@ -84,7 +85,7 @@ NGU_DEVINL void epi_chunk(const uint32_t (&v)[64], const uint4 (&ax)[8], float2 
         x[i] *= a[i];  // aux holds act'(pre) saved by the forward epilogue
       } else {
         if (ACT == NGU_ACT_GELU) {
-          if (save) gelu_and_grad(x[i], x[i], d[i]); else x[i] = gelu_erf(x[i]);
+          if (save) gelu_and_grad(x[i], x[i], d[i]); else x[i] = gelu_fast(x[i]);
         } else if (ACT == NGU_ACT_QUICKGELU) {
           if (save) quick_gelu_and_grad(x[i], x[i], d[i]); else x[i] = quick_gelu(x[i]);
         }
@@ -98,7 +99,7 @@ NGU_DEVINL void epi_chunk(const uint32_t (&v)[64], const uint4 (&ax)[8], float2 
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int kCluster>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -118,9 +119,18 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  // Tiles are handed out per CLUSTER: the kCluster CTAs of a cluster take vertically adjacent 128-row tiles of the
+  // same N tile, so the B (weight) tile is common and is fetched once from L2 with TMA multicast (each CTA loads
+  // 1/kCluster of it into every CTA's smem).  "Virtual" tile index vt = (pair index) * kCluster + rank.
+  const int rank = (kCluster > 1) ? int(cluster_ctarank()) : 0;
+  const int m_tiles_real = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int m_tiles = (m_tiles_real + kCluster - 1) / kCluster * kCluster;  // padded so every CTA of a cluster has a tile
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = m_tiles * n_tiles;
+  const int tile_first = (int(blockIdx.x) / kCluster) * kCluster;          // same for all CTAs of the cluster
+  const int tile_stride = int(gridDim.x);
+  auto tile_m0 = [&](int t) { return (((t / kCluster) / n_tiles) * kCluster + rank) * BLOCK_M; };
+  auto tile_n0 = [&](int t) { return ((t / kCluster) % n_tiles) * BLOCK_N; };
   const int kb1 = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb2 = (p.K2 + BLOCK_K - 1) / BLOCK_K;
   const int num_kb = kb1 + kb2;
@@ -131,7 +141,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     tma_prefetch_desc(&p.tmC);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), kCluster);  // released by the MMA warps of every CTA that reads this slot's B tile
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -145,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // peers' mbarriers must be initialised before any multicast signals them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmemPtr));
@@ -154,58 +165,69 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / n_tiles) * BLOCK_M;
-        const int n0 = (t % n_tiles) * BLOCK_N;
+      constexpr int kBRows = BLOCK_N / kCluster;            // rows of the B tile this CTA fetches (and multicasts)
+      constexpr uint16_t kMask = uint16_t((1u << kCluster) - 1u);
+      for (int t = tile_first; t < num_tiles; t += tile_stride) {
+        const int m0 = tile_m0(t);
+        const int n0 = tile_n0(t);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_arrive_expect_tx(full_bar(s), Cfg::kStageBytes);
-          if (kb < kb1) {
-            tma_load_2d(sA0 + s * Cfg::kABytes, &p.tmA, full_bar(s), kb * BLOCK_K, m0, kEvictNormal);
-            tma_load_2d(sB0 + s * Cfg::kBBytes, &p.tmB, full_bar(s), kb * BLOCK_K, n0, kEvictLast);
-          } else {
-            tma_load_2d(sA0 + s * Cfg::kABytes, &p.tmA2, full_bar(s), (kb - kb1) * BLOCK_K, m0, kEvictNormal);
-            tma_load_2d(sB0 + s * Cfg::kBBytes, &p.tmB2, full_bar(s), (kb - kb1) * BLOCK_K, n0, kEvictLast);
-          }
+          const bool main_k = kb < kb1;
+          const int kc = (main_k ? kb : kb - kb1) * BLOCK_K;
+          const CUtensorMap* ta = main_k ? &p.tmA : &p.tmA2;
+          const CUtensorMap* tb = main_k ? (kCluster > 1 ? &p.tmBh : &p.tmB) : (kCluster > 1 ? &p.tmB2h : &p.tmB2);
+          tma_load_2d(sA0 + s * Cfg::kABytes, ta, full_bar(s), kc, m0, kEvictNormal);
+          if (kCluster > 1)
+            tma_load_2d_mcast(sB0 + s * Cfg::kBBytes + rank * kBRows * BLOCK_K * 2, tb, full_bar(s), kc, n0 + rank * kBRows, kMask, kEvictLast);
+          else
+            tma_load_2d(sB0 + s * Cfg::kBBytes, tb, full_bar(s), kc, n0, kEvictLast);
           if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
-      int s = 0;
-      uint32_t ph = 0;
-      int acc = 0;
-      uint32_t acc_ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+    // The whole warp walks the loop (so every value is warp-uniform and lives in uniform registers); one elected
+    // lane issues the tcgen05.mma / commit instructions.  Descriptors differ only in their 14-bit address field:
+    // desc = base + (byte offset >> 4).
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+    const uint64_t a_base = make_smem_desc_sw128(sA0, 16, 1024);
+    const uint64_t b_base = make_smem_desc_sw128(sB0, 16, 1024);
+    int s = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int t = tile_first; t < num_tiles; t += tile_stride) {
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          // number of valid 16-wide K slices in this block (zero-filled tails are skipped)
-          int kext = (kb < kb1) ? (p.K - kb * BLOCK_K) : (p.K2 - (kb - kb1) * BLOCK_K);
-          kext = kext > BLOCK_K ? BLOCK_K : kext;
-          const int nk = (kext + UMMA_K - 1) / UMMA_K;
-          const uint32_t a_addr = sA0 + s * Cfg::kABytes;
-          const uint32_t b_addr = sB0 + s * Cfg::kBBytes;
+        // number of valid 16-wide K slices in this block (zero-filled tails are skipped)
+        int kext = (kb < kb1) ? (p.K - kb * BLOCK_K) : (p.K2 - (kb - kb1) * BLOCK_K);
+        kext = kext > BLOCK_K ? BLOCK_K : kext;
+        const uint64_t ad = a_base + uint64_t((s * Cfg::kABytes) >> 4);
+        const uint64_t bd = b_base + uint64_t((s * Cfg::kBBytes) >> 4);
+        if (elect_one()) {
+          if (kext == BLOCK_K) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            if (k < nk) {
-              const uint64_t adesc = make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
-              const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-              umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_ss(d_tmem, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          } else {
+            const int nk = (kext + UMMA_K - 1) / UMMA_K;
+            for (int k = 0; k < nk; ++k)
+              umma_ss(d_tmem, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(s));  // frees the smem slot once these MMAs have read it
+          // frees the smem slot once these MMAs have read it (in every CTA whose producer writes into it)
+          if (kCluster > 1) umma_commit_mcast(empty_bar(s), uint16_t((1u << kCluster) - 1u)); else umma_commit(empty_bar(s));
           if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
-          if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
         }
-        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+        __syncwarp();
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
       }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
     }
   } else {
     // ================================ epilogue ================================
@@ -222,7 +244,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     const bf16* pre_out = reinterpret_cast<const bf16*>(p.pre);
 
     auto load_aux = [&](int t, int c, uint4 (&dst)[8]) {
-      const int m0 = (t / n_tiles) * BLOCK_M, nc = (t % n_tiles) * BLOCK_N + c * 64;
+      const int m0 = tile_m0(t), nc = tile_n0(t) + c * 64;
       const int row = m0 + q * 32 + lane;
       const bool ok = use_aux && t < num_tiles && nc < p.N && row < p.M;
       const uint4* ap = reinterpret_cast<const uint4*>(p.aux + size_t(ok ? row : 0) * p.ldaux + (ok ? nc : 0));
@@ -234,10 +256,10 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
       int acc = 0;
       uint32_t acc_ph = 0;
       uint4 axn[8];
-      load_aux(blockIdx.x, c_begin, axn);
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / n_tiles) * BLOCK_M;
-        const int n0 = (t % n_tiles) * BLOCK_N;
+      load_aux(tile_first, c_begin, axn);
+      for (int t = tile_first; t < num_tiles; t += tile_stride) {
+        const int m0 = tile_m0(t);
+        const int n0 = tile_n0(t);
         const int row = m0 + q * 32 + lane;
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
@@ -266,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
           for (int j = 0; j < 8; ++j) ax[j] = axn[j];
           if (use_aux) {
             if (ci + 1 < kPerWarp) load_aux(t, c + 1, axn);
-            else load_aux(t + gridDim.x, c_begin, axn);
+            else load_aux(t + tile_stride, c_begin, axn);
           }
           tmem_ld_wait();
           if (ci == kPerWarp - 1) {
@@ -339,13 +361,14 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int kCluster>
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   GemmKernelParams p;
@@ -353,12 +376,15 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   int rc;
   if ((rc = make_tmap_2d_bf16(&p.tmA, a.A, a.M, a.K, a.lda, BLOCK_M, BLOCK_K, true))) return rc;
   if ((rc = make_tmap_2d_bf16(&p.tmB, a.B, a.N, a.K, a.ldb, BLOCK_N, BLOCK_K, true))) return rc;
+  if ((rc = make_tmap_2d_bf16(&p.tmBh, a.B, a.N, a.K, a.ldb, BLOCK_N / 2, BLOCK_K, true))) return rc;
   if (a.K2 > 0) {
     if ((rc = make_tmap_2d_bf16(&p.tmA2, a.A2, a.M, a.K2, a.lda2, BLOCK_M, BLOCK_K, true))) return rc;
     if ((rc = make_tmap_2d_bf16(&p.tmB2, a.B2, a.N, a.K2, a.ldb2, BLOCK_N, BLOCK_K, true))) return rc;
+    if ((rc = make_tmap_2d_bf16(&p.tmB2h, a.B2, a.N, a.K2, a.ldb2, BLOCK_N / 2, BLOCK_K, true))) return rc;
   } else {
     p.tmA2 = p.tmA;
     p.tmB2 = p.tmB;
+    p.tmB2h = p.tmBh;
   }
   if ((rc = make_tmap_2d_bf16(&p.tmC, a.C, a.M, a.N, a.ldc, 32, 64, true))) return rc;
   p.pre = a.Pre;
@@ -372,17 +398,32 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
 
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_status(e, "gemm_tc smem attribute");
     attr_done = true;
   }
-  const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+  const int m_tiles = ((a.M + BLOCK_M - 1) / BLOCK_M + kCluster - 1) / kCluster * kCluster;
   const int n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
   int grid = m_tiles * n_tiles;
-  const int sms = sm_count();
+  const int sms = sm_count() / kCluster * kCluster;
   if (grid > sms) grid = sms;
-  gemm_tc_kernel<BLOCK_N><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
-  return check_launch("gemm_tc");
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kCluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kCluster>, p);
+  count_launch(1);
+  if (e != cudaSuccess) return cuda_status(e, "gemm_tc launch");
+  return cuda_status(cudaGetLastError(), "gemm_tc");
 }
 
 }  // namespace
@@ -403,10 +444,14 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   }
   int bn = a.block_n;
   if (bn == 0) bn = (a.N > 128) ? 256 : (a.N > 64 ? 128 : 64);
+  // block_n + 1000 forces the single-CTA (no multicast) variant: tests / tuning
+  const bool no_cluster = a.block_n >= 1000;
+  if (no_cluster) bn = a.block_n - 1000 ? a.block_n - 1000 : ((a.N > 128) ? 256 : (a.N > 64 ? 128 : 64));
+  const bool cluster = !no_cluster && a.M > BLOCK_M;
   switch (bn) {
-    case 256: return launch_gemm_tc<256>(a, stream);
-    case 128: return launch_gemm_tc<128>(a, stream);
-    case 64: return launch_gemm_tc<64>(a, stream);
+    case 256: return cluster ? launch_gemm_tc<256, 2>(a, stream) : launch_gemm_tc<256, 1>(a, stream);
+    case 128: return cluster ? launch_gemm_tc<128, 2>(a, stream) : launch_gemm_tc<128, 1>(a, stream);
+    case 64: return cluster ? launch_gemm_tc<64, 2>(a, stream) : launch_gemm_tc<64, 1>(a, stream);
     default: set_last_error("gemm_tc: unsupported block_n %d", bn); return NGU_ERR_ARG;
   }
 }

@@ -140,6 +140,11 @@ NGU_DEVINL void tma_load_2d_mcast(uint32_t smem_dst, const CUtensorMap* m, uint3
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask), "l"(hint)
       : "memory");
 }
+// pull a tile into L2 ahead of the TMA load that will consume it (no smem, no barrier)
+NGU_DEVINL void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
 NGU_DEVINL uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

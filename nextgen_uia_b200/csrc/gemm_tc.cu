@@ -15,6 +15,7 @@
 //     as extra K blocks: this is how LoRA's s*(x A^T) B^T rides on the base projection.
 //   * epilogue: + bias, erf-GELU / QuickGELU (optionally also storing the pre-activation for
 //     backward), + residual, or * act'(pre) for the backward through the activation.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -56,6 +57,7 @@ struct GemmKernelParams {
   int aux_mode;  // NGU_AUX_*
   int save_pre;  // also store (acc + bias) through tmPre
   float alpha;   // scale on the accumulator before bias
+  int prefetch;  // L2 prefetch distance for A in k-blocks (0 = off)
 };
 
 // Epilogue math for one 64-column chunk of one row: v = raw fp32 accumulators, ax = aux row chunk
@@ -178,6 +180,12 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
           const CUtensorMap* ta = main_k ? &p.tmA : &p.tmA2;
           const CUtensorMap* tb = main_k ? (kCluster > 1 ? &p.tmBh : &p.tmB) : (kCluster > 1 ? &p.tmB2h : &p.tmB2);
           tma_load_2d(sA0 + s * Cfg::kABytes, ta, full_bar(s), kc, m0, kEvictNormal);
+          // A streams from HBM: warm L2 for the block kPrefetch steps ahead (next tile's rows once this tile's K is done)
+          if (main_k && p.prefetch > 0) {
+            int pk = kb + p.prefetch, pt = t;
+            if (pk >= kb1) { pk -= kb1; pt += tile_stride; }
+            if (pt < num_tiles && pk < kb1) tma_prefetch_l2_2d(&p.tmA, pk * BLOCK_K, tile_m0(pt));
+          }
           if (kCluster > 1)
             tma_load_2d_mcast(sB0 + s * Cfg::kBBytes + rank * kBRows * BLOCK_K * 2, tb, full_bar(s), kc, n0 + rank * kBRows, kMask, kEvictLast);
           else
@@ -395,6 +403,11 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   p.M = a.M; p.N = a.N; p.K = a.K; p.K2 = a.K2;
   p.act = a.act; p.aux_mode = a.aux_mode; p.save_pre = a.save_pre;
   p.alpha = a.alpha;
+  {
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("NGU_GEMM_PREFETCH"); pf = e ? atoi(e) : 0;  // measured on B200: L2 prefetch of A costs more TMA issue than it saves (off) }
+    p.prefetch = pf;
+  }
 
   static bool attr_done = false;
   if (!attr_done) {

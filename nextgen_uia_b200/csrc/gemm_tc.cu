@@ -405,7 +405,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   p.alpha = a.alpha;
   {
     static int pf = -1;
-    if (pf < 0) { const char* e = getenv("NGU_GEMM_PREFETCH"); pf = e ? atoi(e) : 0;  // measured on B200: L2 prefetch of A costs more TMA issue than it saves (off) }
+    if (pf < 0) { const char* e = getenv("NGU_GEMM_PREFETCH"); pf = e ? atoi(e) : 0; }  // default off: on B200 the extra TMA issue costs more than the L2 warm-up saves
     p.prefetch = pf;
   }
 

@@ -57,38 +57,39 @@ NGU_DEVINL void st_row_bf16(bf16* dst, const float (&v)[64]) {
 // =====================================================================================================
 // forward
 // =====================================================================================================
-constexpr int kFwdThreads = 32 * 9;  // 8 softmax warps (2 query tiles x 4 lane quarters) + 1 control warp
-constexpr int kFwdSmem = 6 * kTileBytes + 1024 + 1024;
+constexpr int kFwdThreads = 32 * 5;  // 4 softmax warps (one query row per thread) + 1 control warp
+constexpr int kFwdSmem = 5 * kTileBytes + 1024 + 1024;  // Q tile + K (2 tiles) + V (2 tiles)
 
-__global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
+// One CTA per (batch, head, 128-row query tile); 256 TMEM columns and ~82 KB smem so two CTAs share an SM and
+// overlap each other's load / MMA / softmax phases.
+__global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = base + 2 * kTileBytes, sV = base + 4 * kTileBytes;
-  const uint32_t sBar = base + 6 * kTileBytes;
-  const uint32_t bar_kv = sBar, bar_q0 = sBar + 8;            // bar_q[t] = bar_q0 + 8t
-  const uint32_t bar_s0 = sBar + 24, bar_p0 = sBar + 40, bar_o0 = sBar + 56;
-  const uint32_t sTmem = sBar + 72;
+  const uint32_t sQ = base, sK = base + kTileBytes, sV = base + 3 * kTileBytes;
+  const uint32_t sBar = base + 5 * kTileBytes;
+  const uint32_t bar_kv = sBar, bar_q = sBar + 8, bar_s = sBar + 16, bar_p = sBar + 24, bar_o = sBar + 32;
+  const uint32_t sTmem = sBar + 40;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int N = p.N, D = p.H * DH;
   const int ntiles = (N + TILE - 1) / TILE;      // 1 or 2
+  const int t = blockIdx.x % ntiles;             // query tile of this CTA
+  const int bh = blockIdx.x / ntiles;
+  const int b = bh / p.H, h = bh % p.H;
   const int npad = (N + 15) & ~15;               // MMA N extent over the kv axis
   const int row0 = b * N;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmQKV);
     mbar_init(bar_kv, 1);
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(bar_q0 + 8 * t, 1);
-      mbar_init(bar_s0 + 8 * t, 1);
-      mbar_init(bar_p0 + 8 * t, 128);
-      mbar_init(bar_o0 + 8 * t, 1);
-    }
+    mbar_init(bar_q, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
     fence_mbar_init();
   }
-  if (warp == 8) {
-    tmem_alloc(sTmem, 512);
+  if (warp == 4) {
+    tmem_alloc(sTmem, 256);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -97,113 +98,103 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_tc_kernel(const __gri
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(sTmem));
 
-  if (warp == 8) {
+  if (warp == 4) {
     if (lane == 0) {
-      // ---- loads: K, V (all kv rows) then the query tiles
+      mbar_arrive_expect_tx(bar_q, kTileBytes);
+      tma_load_2d(sQ, &p.tmQKV, bar_q, h * DH, row0 + t * TILE);
       mbar_arrive_expect_tx(bar_kv, 2 * ntiles * kTileBytes);
-      for (int t = 0; t < ntiles; ++t) {
-        tma_load_2d(sK + t * kTileBytes, &p.tmQKV, bar_kv, D + h * DH, row0 + t * TILE);
-        tma_load_2d(sV + t * kTileBytes, &p.tmQKV, bar_kv, 2 * D + h * DH, row0 + t * TILE);
+      for (int u = 0; u < ntiles; ++u) {
+        tma_load_2d(sK + u * kTileBytes, &p.tmQKV, bar_kv, D + h * DH, row0 + u * TILE);
+        tma_load_2d(sV + u * kTileBytes, &p.tmQKV, bar_kv, 2 * D + h * DH, row0 + u * TILE);
       }
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_arrive_expect_tx(bar_q0 + 8 * t, kTileBytes);
-        tma_load_2d(sQ + t * kTileBytes, &p.tmQKV, bar_q0 + 8 * t, h * DH, row0 + t * TILE);
-      }
-      // ---- S_t = Q_t K^T
+      // ---- S = Q K^T
       const uint32_t idesc_s = make_idesc_bf16(TILE, npad);
+      mbar_wait(bar_q, 0);
       mbar_wait(bar_kv, 0);
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(bar_q0 + 8 * t, 0);
-        tc_fence_after();
+      tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_ss(tmem + t * 256, desc_kmajor(sQ + t * kTileBytes + k * 32), desc_kmajor(sK + k * 32), idesc_s, k != 0);
-        umma_commit(bar_s0 + 8 * t);
-      }
-      // ---- O_t = P_t V   (A = P in TMEM at columns [t*256, t*256 + npad/2), D = O at t*256 + 128)
+      for (int k = 0; k < DH / 16; ++k) umma_ss(tmem, desc_kmajor(sQ + k * 32), desc_kmajor(sK + k * 32), idesc_s, k != 0);
+      umma_commit(bar_s);
+      // ---- O = P V   (A = P in TMEM at columns [0, npad/2), D = O at column 128)
       constexpr uint32_t idesc_o = make_idesc_bf16(TILE, DH, 0, 1);
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(bar_p0 + 8 * t, 0);
-        tc_fence_after();
-        for (int j = 0; j < npad / 16; ++j)
-          umma_ts(tmem + t * 256 + 128, tmem + t * 256 + j * 8, desc_mnmajor(sV + j * 2048, 0), idesc_o, j != 0);
-        umma_commit(bar_o0 + 8 * t);
-      }
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      for (int j = 0; j < npad / 16; ++j) umma_ts(tmem + 128, tmem + j * 8, desc_mnmajor(sV + j * 2048, 0), idesc_o, j != 0);
+      umma_commit(bar_o);
     }
   } else {
-    const int t = warp >> 2, q = warp & 3;
-    if (t < ntiles) {
-      const int r = t * TILE + q * 32 + lane;  // query row within the sequence
-      const uint32_t trow = tmem + (uint32_t(q * 32) << 16) + t * 256;
-      const float c = p.scale * kLog2e;
-      mbar_wait(bar_s0 + 8 * t, 0);
-      tc_fence_after();
-      const int nchunks = (npad + 31) / 32;
-      float mx = -INFINITY;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(trow + ch * 32, v);
-        tmem_ld_wait();
+    const int q = warp;
+    const int r = t * TILE + q * 32 + lane;  // query row within the sequence
+    const uint32_t trow = tmem + (uint32_t(q * 32) << 16);
+    const float c = p.scale * kLog2e;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    const int nchunks = (npad + 31) / 32;
+    float mx = -INFINITY;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(trow + ch * 32, v);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (ch * 32 + i < N) mx = fmaxf(mx, __uint_as_float(v[i]));
-      }
-      float sum = 0.f;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(trow + ch * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      for (int i = 0; i < 32; ++i)
+        if (ch * 32 + i < N) mx = fmaxf(mx, __uint_as_float(v[i]));
+    }
+    float sum = 0.f;
+    const float mc = mx * c;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(trow + ch * 32, v);
+      tmem_ld_wait();
+      uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c0 = ch * 32 + 2 * i;
-          float p0 = ex2_approx((__uint_as_float(v[2 * i]) - mx) * c);
-          float p1 = ex2_approx((__uint_as_float(v[2 * i + 1]) - mx) * c);
-          p0 = (c0 < N) ? p0 : 0.f;
-          p1 = (c0 + 1 < N) ? p1 : 0.f;
-          // the PV MMA sees bf16 probabilities: accumulate the same rounded values into the row sum
-          const uint32_t w = pack_bf16x2(p0, p1);
-          const float2 rr = unpack_bf16x2(w);
-          sum += rr.x + rr.y;
-          pk[i] = w;
-        }
-        tmem_st16(trow + ch * 16, pk);
+      for (int i = 0; i < 16; ++i) {
+        const int c0 = ch * 32 + 2 * i;
+        float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, -mc));
+        float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
+        p0 = (c0 < N) ? p0 : 0.f;
+        p1 = (c0 + 1 < N) ? p1 : 0.f;
+        // the PV MMA sees bf16 probabilities: accumulate the same rounded values into the row sum
+        const uint32_t w = pack_bf16x2(p0, p1);
+        const float2 rr = unpack_bf16x2(w);
+        sum += rr.x + rr.y;
+        pk[i] = w;
       }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(bar_p0 + 8 * t);
-      mbar_wait(bar_o0 + 8 * t, 0);
-      tc_fence_after();
-      uint32_t ov[64];
-      {
-        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&ov[0]);
-        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&ov[32]);
-        tmem_ld32(trow + 128, lo);
-        tmem_ld32(trow + 160, hi);
-        tmem_ld_wait();
-      }
-      if (r < N) {
-        const float inv = 1.f / sum;
-        float of[64];
+      tmem_st16(trow + ch * 16, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    uint32_t ov[64];
+    {
+      uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&ov[0]);
+      uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&ov[32]);
+      tmem_ld32(trow + 128, lo);
+      tmem_ld32(trow + 160, hi);
+      tmem_ld_wait();
+    }
+    if (r < N) {
+      const float inv = 1.f / sum;
+      float of[64];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) of[i] = __uint_as_float(ov[i]) * inv;
-        st_row_bf16(p.o + size_t(row0 + r) * D + h * DH, of);
-        if (p.lse) p.lse[(size_t(b) * p.H + h) * N + r] = mx * p.scale + logf(sum);
-      }
+      for (int i = 0; i < 64; ++i) of[i] = __uint_as_float(ov[i]) * inv;
+      st_row_bf16(p.o + size_t(row0 + r) * D + h * DH, of);
+      if (p.lse) p.lse[(size_t(b) * p.H + h) * N + r] = mx * p.scale + logf(sum);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, 256);
   }
 }
 
 // =====================================================================================================
 // backward
 // =====================================================================================================
-constexpr int kBwdThreads = 32 * 5;  // 4 compute warps (one kv row per thread) + 1 control warp
+constexpr int kBwdThreads = 32 * 9;  // 8 compute warps (kv row = lane quarter, query columns split in halves) + 1 control warp
 constexpr int kBwdSmem = 10 * kTileBytes + 2048 + 1024 + 1024;
 
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
@@ -232,11 +223,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     tma_prefetch_desc(&p.tmDO);
     mbar_init(bar_load, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, 256);
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc(sTmem, 512);
     tmem_relinquish();
   }
@@ -246,7 +237,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(sTmem));
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_load, 4 * ntiles * kTileBytes);
       for (int t = 0; t < ntiles; ++t) {
@@ -285,59 +276,75 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       }
     }
   } else {
-    const int t = threadIdx.x;  // 0..127: kv row within the tile (= TMEM lane)
-    // ---- prologue: lse (log2 domain) and delta = rowsum(dO * O) for every query row
-    for (int r = t; r < ntiles * TILE; r += 128) {
-      float l2 = 0.f, dl = 0.f;
-      if (r < N) {
-        l2 = p.lse[(size_t(b) * p.H + h) * N + r] * kLog2e;
-        const uint4* po = reinterpret_cast<const uint4*>(p.o_in + size_t(row0 + r) * D + h * DH);
-        const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + size_t(row0 + r) * D + h * DH);
+    const int qd = warp & 3, hf = warp >> 2;     // TMEM lane quarter, query-column half
+    const int t = qd * 32 + lane;                // kv row within the tile (= TMEM lane)
+    // ---- prologue: lse (log2 domain) and delta = rowsum(dO * O) for every query row (one row per thread)
+    {
+      const int r = threadIdx.x;
+      if (r < ntiles * TILE) {
+        float l2 = 0.f, dl = 0.f;
+        if (r < N) {
+          l2 = p.lse[(size_t(b) * p.H + h) * N + r] * kLog2e;
+          const uint4* po = reinterpret_cast<const uint4*>(p.o_in + size_t(row0 + r) * D + h * DH);
+          const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + size_t(row0 + r) * D + h * DH);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint4 a = __ldg(po + j), g = __ldg(pd + j);
-          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+          for (int j = 0; j < 8; ++j) {
+            const uint4 a = __ldg(po + j), g = __ldg(pd + j);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(gw[e]);
-            dl = fmaf(x.x, y.x, dl);
-            dl = fmaf(x.y, y.y, dl);
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(gw[e]);
+              dl = fmaf(x.x, y.x, dl);
+              dl = fmaf(x.y, y.y, dl);
+            }
           }
         }
+        lse2[r] = l2;
+        delta[r] = dl;
       }
-      lse2[r] = l2;
-      delta[r] = dl;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const uint32_t trow = tmem + (uint32_t(qd * 32) << 16);
     const float c = p.scale * kLog2e;
     uint32_t ph = 0, acc_ph = 0;
     for (int j = 0; j < ntiles; ++j) {
       const int kv = j * TILE + t;
       const bool kv_ok = kv < N;
+      const bool warp_live = j * TILE + qd * 32 < N;   // any valid kv row in this warp (warp-uniform)
       for (int i = 0; i < ntiles; ++i) {
         mbar_wait(bar_s, ph);
         tc_fence_after();
-        for (int ch = 0; ch < 4; ++ch) {  // 32 query columns per chunk
-          uint32_t sv[32], dv[32];
-          tmem_ld32(trow + cST + ch * 32, sv);
-          tmem_ld32(trow + cDPT + ch * 32, dv);
-          tmem_ld_wait();
+        for (int cc = 0; cc < 2; ++cc) {  // this warp's two 32-column chunks of the 128 query columns
+          const int ch = hf * 2 + cc;
+          const bool chunk_live = warp_live && (i * TILE + ch * 32 < N);
           uint32_t pp[16], ds[16];
+          if (chunk_live) {
+            uint32_t sv[32], dv[32];
+            tmem_ld32(trow + cST + ch * 32, sv);
+            tmem_ld32(trow + cDPT + ch * 32, dv);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int q0 = i * TILE + ch * 32 + 2 * e;
-            float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), c, -lse2[q0]));
-            float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), c, -lse2[q0 + 1]));
-            p0 = (kv_ok && q0 < N) ? p0 : 0.f;
-            p1 = (kv_ok && q0 + 1 < N) ? p1 : 0.f;
-            const float d0 = p0 * (__uint_as_float(dv[2 * e]) - delta[q0]) * p.scale;
-            const float d1 = p1 * (__uint_as_float(dv[2 * e + 1]) - delta[q0 + 1]) * p.scale;
-            pp[e] = pack_bf16x2(p0, p1);
-            ds[e] = pack_bf16x2(d0, d1);
+            for (int e = 0; e < 16; ++e) {
+              const int q0 = i * TILE + ch * 32 + 2 * e;
+              float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), c, -lse2[q0]));
+              float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), c, -lse2[q0 + 1]));
+              p0 = (kv_ok && q0 < N) ? p0 : 0.f;
+              p1 = (kv_ok && q0 + 1 < N) ? p1 : 0.f;
+              const float d0 = p0 * (__uint_as_float(dv[2 * e]) - delta[q0]) * p.scale;
+              const float d1 = p1 * (__uint_as_float(dv[2 * e + 1]) - delta[q0 + 1]) * p.scale;
+              pp[e] = pack_bf16x2(p0, p1);
+              ds[e] = pack_bf16x2(d0, d1);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { pp[e] = 0u; ds[e] = 0u; }
           }
-          tmem_st16(trow + cST + ch * 16, pp);    // PT  (bf16) aliases ST columns already consumed
-          tmem_st16(trow + cDPT + ch * 16, ds);   // dST (bf16) aliases dPT
+          // PT / dST (bf16) alias the ST / dPT columns.  Chunk ch writes columns [16ch, 16ch+16): for hf = 1 those
+          // are columns 32..63 = fp32 chunk 1 of the OTHER warp half -> order the two halves with a named barrier.
+          if (cc == 0 && hf == 1) asm volatile("bar.sync 2, 256;" ::: "memory");
+          tmem_st16(trow + cST + ch * 16, pp);
+          tmem_st16(trow + cDPT + ch * 16, ds);
+          if (cc == 1 && hf == 0) { tmem_st_wait(); asm volatile("bar.arrive 2, 256;" ::: "memory"); }
           // dS^T row of this kv index into the MN-major smem operand: 32 q values = 4 x 16 B
           const uint32_t rbase = sDS + (ch >> 1) * kTileBytes + (t >> 3) * 1024 + (t & 7) * 128;
 #pragma unroll
@@ -355,41 +362,34 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
         mbar_arrive(bar_p);
         ph ^= 1u;
       }
-      // ---- dV_j, dK_j complete
+      // ---- dV_j, dK_j complete: each warp half writes 32 of the 64 head-dim columns
       mbar_wait(bar_acc, acc_ph);
       acc_ph ^= 1u;
       tc_fence_after();
-      uint32_t v[64];
-      uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-      uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-      float f[64];
-      tmem_ld32(trow + cDV, lo);
-      tmem_ld32(trow + cDV + 32, hi);
-      tmem_ld_wait();
-      if (kv_ok) {
+      uint32_t v[32];
+      auto store32 = [&](bf16* dst) {
 #pragma unroll
-        for (int e = 0; e < 64; ++e) f[e] = __uint_as_float(v[e]);
-        st_row_bf16(p.dqkv + size_t(row0 + kv) * 3 * D + 2 * D + h * DH, f);
-      }
-      tmem_ld32(trow + cDK, lo);
-      tmem_ld32(trow + cDK + 32, hi);
+        for (int jj = 0; jj < 4; ++jj) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[8 * jj + 0]), __uint_as_float(v[8 * jj + 1]));
+          u.y = pack_bf16x2(__uint_as_float(v[8 * jj + 2]), __uint_as_float(v[8 * jj + 3]));
+          u.z = pack_bf16x2(__uint_as_float(v[8 * jj + 4]), __uint_as_float(v[8 * jj + 5]));
+          u.w = pack_bf16x2(__uint_as_float(v[8 * jj + 6]), __uint_as_float(v[8 * jj + 7]));
+          reinterpret_cast<uint4*>(dst)[jj] = u;
+        }
+      };
+      tmem_ld32(trow + cDV + hf * 32, v);
       tmem_ld_wait();
-      if (kv_ok) {
-#pragma unroll
-        for (int e = 0; e < 64; ++e) f[e] = __uint_as_float(v[e]);
-        st_row_bf16(p.dqkv + size_t(row0 + kv) * 3 * D + D + h * DH, f);
-      }
+      if (kv_ok) store32(p.dqkv + size_t(row0 + kv) * 3 * D + 2 * D + h * DH + hf * 32);
+      tmem_ld32(trow + cDK + hf * 32, v);
+      tmem_ld_wait();
+      if (kv_ok) store32(p.dqkv + size_t(row0 + kv) * 3 * D + D + h * DH + hf * 32);
       if (j == ntiles - 1) {
         for (int i = 0; i < ntiles; ++i) {
           const int qr = i * TILE + t;
-          tmem_ld32(trow + cDQ + i * 64, lo);
-          tmem_ld32(trow + cDQ + i * 64 + 32, hi);
+          tmem_ld32(trow + cDQ + i * 64 + hf * 32, v);
           tmem_ld_wait();
-          if (qr < N) {
-#pragma unroll
-            for (int e = 0; e < 64; ++e) f[e] = __uint_as_float(v[e]);
-            st_row_bf16(p.dqkv + size_t(row0 + qr) * 3 * D + h * DH, f);
-          }
+          if (qr < N) store32(p.dqkv + size_t(row0 + qr) * 3 * D + h * DH + hf * 32);
         }
       }
       tc_fence_before();
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -453,7 +453,7 @@ int attn_fwd_tc(const ngu_attn_desc& d, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e, "attn_fwd_tc attr");
     attr = true;
   }
-  attn_fwd_tc_kernel<<<d.B * d.H, kFwdThreads, kFwdSmem, st>>>(p);
+  attn_fwd_tc_kernel<<<d.B * d.H * ((d.N + TILE - 1) / TILE), kFwdThreads, kFwdSmem, st>>>(p);
   return check_launch("attn_fwd_tc");
 }
 

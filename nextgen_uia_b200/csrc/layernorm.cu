@@ -449,7 +449,8 @@ int mona_pre_bwd(const ngu_mona_pre_bwd_desc& d, cudaStream_t s) {
   if (d.D == 768) return d.dtype == NGU_F32 ? mona_pre_bwd_t<float, 768>(d, s) : mona_pre_bwd_t<bf16, 768>(d, s);
   if (d.D == 1024) return d.dtype == NGU_F32 ? mona_pre_bwd_t<float, 1024>(d, s) : mona_pre_bwd_t<bf16, 1024>(d, s);
   if (d.D == 256) return d.dtype == NGU_F32 ? mona_pre_bwd_t<float, 256>(d, s) : mona_pre_bwd_t<bf16, 256>(d, s);
-  set_last_error("mona_pre_bwd: embed dim %d not instantiated (256, 768, 1024)", d.D);
+  if (d.D == 512) return d.dtype == NGU_F32 ? mona_pre_bwd_t<float, 512>(d, s) : mona_pre_bwd_t<bf16, 512>(d, s);
+  set_last_error("mona_pre_bwd: embed dim %d not instantiated (256, 512, 768, 1024)", d.D);
   return NGU_ERR_SHAPE;
 }
 

@@ -28,36 +28,47 @@ def _seed(training):
     return int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
 
 
+class BlockSpec:
+    """What BlockFunction needs from a transformer block, independent of the attribute names of the host module:
+    timm Block (norm1/attn.qkv/attn.proj/norm2/mlp.fc1/mlp.fc2) and the OpenAI-CLIP ResidualAttentionBlock
+    (ln_1/attn.in_proj_*/attn.out_proj/ln_2/mlp.c_fc/mlp.c_proj) both map onto it."""
+
+    __slots__ = ("ln1", "ln2", "qkv", "proj", "fc1", "fc2", "heads", "act", "causal")
+
+    def __init__(self, ln1, ln2, qkv, proj, fc1, fc2, heads, act, causal=False):
+        self.ln1, self.ln2, self.qkv, self.proj, self.fc1, self.fc2 = ln1, ln2, qkv, proj, fc1, fc2
+        self.heads, self.act, self.causal = heads, act, causal
+
+
 class BlockFunction(torch.autograd.Function):
     """One pre-LN transformer block on [B,N,D] with frozen base weights (+ optional LoRA on qkv / proj)."""
 
     @staticmethod
-    def forward(ctx, x, blk, qkv_bias, proj_bias, qA, qB, pA, pB):
+    def forward(ctx, x, spec, qkv_bias, proj_bias, qA, qB, pA, pB):
         B, N, D = x.shape
-        H = blk.attn.num_heads
+        H = spec.heads
         dh = D // H
         M = B * N
         x2 = x.contiguous().view(M, D)
         dt = x2.dtype
-        eps = blk.norm1.eps
-        pq, pp = Proj(blk.attn.qkv, dt), Proj(blk.attn.proj, dt)
-        p1, p2 = Proj(blk.mlp.fc1, dt), Proj(blk.mlp.fc2, dt)
-        act = blk.act_kind
+        pq, pp = Proj(spec.qkv, dt), Proj(spec.proj, dt)
+        p1, p2 = Proj(spec.fc1, dt), Proj(spec.fc2, dt)
+        act = spec.act
         sq, sp = _seed(pq.p > 0), _seed(pp.p > 0)
 
-        xn, m1, r1 = ops.ln_fwd(x2, blk.norm1.weight.detach(), blk.norm1.bias.detach(), eps)
+        xn, m1, r1 = ops.ln_fwd(x2, spec.ln1.weight.detach(), spec.ln1.bias.detach(), spec.ln1.eps)
         qkv, sv_q = proj_fwd(xn, pq, seed=sq)
-        ao, lse = ops.attn_fwd_packed(qkv, B, N, H, dh)
+        ao, lse = ops.attn_fwd_packed(qkv, B, N, H, dh, causal=spec.causal)
         x1, sv_p = proj_fwd(ao, pp, aux=x2, aux_mode=L.AUX_RESIDUAL, seed=sp)
-        xn2, m2, r2 = ops.ln_fwd(x1, blk.norm2.weight.detach(), blk.norm2.bias.detach(), blk.norm2.eps)
+        xn2, m2, r2 = ops.ln_fwd(x1, spec.ln2.weight.detach(), spec.ln2.bias.detach(), spec.ln2.eps)
         (hact, hder), _ = proj_fwd(xn2, p1, act=act, save_pre=True)   # hder = act'(pre), what backward multiplies by
         y, _ = proj_fwd(hact, p2, aux=x1, aux_mode=L.AUX_RESIDUAL)
 
         ctx.save_for_backward(x2, m1, r1, qkv, ao, lse, x1, m2, r2, hder)
         ctx.lora_saved = (sv_q, sv_p)
         ctx.projs = (pq, pp, p1, p2)
-        ctx.blk = blk
-        ctx.dims = (B, N, D, H, dh, act)
+        ctx.spec = spec
+        ctx.dims = (B, N, D, H, dh)
         return y.view(B, N, D)
 
     @staticmethod
@@ -65,21 +76,21 @@ class BlockFunction(torch.autograd.Function):
         x2, m1, r1, qkv, ao, lse, x1, m2, r2, hder = ctx.saved_tensors
         pq, pp, p1, p2 = ctx.projs
         sv_q, sv_p = ctx.lora_saved
-        blk = ctx.blk
-        B, N, D, H, dh, act = ctx.dims
+        spec = ctx.spec
+        B, N, D, H, dh = ctx.dims
         need = ctx.needs_input_grad
         dy2 = dy.contiguous().view(B * N, D)
         # MLP:  y = x1 + fc2(act(fc1(LN2 x1)))
         dhpre = ops.gemm(dy2, p2.WT, aux=hder, aux_mode=L.AUX_DACT)                   # (dy W2) * act'(pre)
         dxn2 = ops.gemm(dhpre, p1.WT)
-        dx1 = ops.ln_bwd(dxn2, x1, m2, r2, blk.norm2.weight.detach(), dres=dy2)      # dy + LN2bwd
+        dx1 = ops.ln_bwd(dxn2, x1, m2, r2, spec.ln2.weight.detach(), dres=dy2)        # dy + LN2bwd
         # attention:  x1 = x + proj(attn(qkv(LN1 x)))
         dao, dpb, dpA, dpB = proj_bwd(dx1, pp, sv_p, need_dx=True, need_bias=need[3])
-        dqkv = ops.attn_bwd_packed(qkv, ao, lse, dao, B, N, H, dh)
+        dqkv = ops.attn_bwd_packed(qkv, ao, lse, dao, B, N, H, dh, causal=spec.causal)
         dxn, dqb, dqA, dqB = proj_bwd(dqkv, pq, sv_q, need_dx=need[0], need_bias=need[2])
         dx = None
         if need[0]:
-            dx = ops.ln_bwd(dxn, x2, m1, r1, blk.norm1.weight.detach(), dres=dx1).view(B, N, D)
+            dx = ops.ln_bwd(dxn, x2, m1, r1, spec.ln1.weight.detach(), dres=dx1).view(B, N, D)
         return dx, None, dqb, dpb, dqA, dqB, dpA, dpB
 
 
@@ -115,7 +126,8 @@ class Block(nn.Module):
 
     def forward(self, x, **kwargs):
         q, p = self.attn.qkv, self.attn.proj
-        return BlockFunction.apply(x, self, q.bias, p.bias,
+        spec = BlockSpec(self.norm1, self.norm2, q, p, self.mlp.fc1, self.mlp.fc2, self.attn.num_heads, self.act_kind)
+        return BlockFunction.apply(x, spec, q.bias, p.bias,
                                    getattr(q, "w_lora_A", None), getattr(q, "w_lora_B", None),
                                    getattr(p, "w_lora_A", None), getattr(p, "w_lora_B", None))
 

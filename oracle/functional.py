@@ -92,6 +92,71 @@ def encode_image(p, images, cfg, taps=None):
 
 
 # ---------------------------------------------------------------------------------------------------
+# OpenAI CLIP towers (reference: src/third_party/openai_clip/model.py, vendored in the reference tree)
+# ---------------------------------------------------------------------------------------------------
+def clip_block(x, p, prefix, heads, causal=False, lora=None):
+    """ResidualAttentionBlock on batch-first x [B,N,D] (the reference runs it sequence-first; the arithmetic is
+    per token/per image so the layouts are equivalent).  model.py:199-202: x += attn(ln_1 x); x += mlp(ln_2 x) with
+    nn.MultiheadAttention (packed in_proj q|k|v, model.py:195-197), QuickGELU x*sigmoid(1.702x) (:172-174), LN eps 1e-5.
+    With `lora` = (r, alpha) the attention is PlainMultiheadAttentionLoRA (lora.py:155-199): separate q/k/v/proj
+    LinearLoRA projections."""
+    B, N, D = x.shape
+    dh = D // heads
+    h = F.layer_norm(x, (D,), p[f"{prefix}ln_1.weight"], p[f"{prefix}ln_1.bias"], 1e-5)
+    if lora is None:
+        qkv = F.linear(h, p[f"{prefix}attn.in_proj_weight"], p[f"{prefix}attn.in_proj_bias"])
+        q, k, v = qkv.split(D, dim=-1)
+    else:
+        r, alpha = lora
+        q = lora_linear(h, p, f"{prefix}attn.q_proj.", r, alpha)
+        k = lora_linear(h, p, f"{prefix}attn.k_proj.", r, alpha)
+        v = lora_linear(h, p, f"{prefix}attn.v_proj.", r, alpha)
+    sh = lambda t: t.reshape(B, N, heads, dh).transpose(1, 2)
+    s = (sh(q) @ sh(k).transpose(-1, -2)) * dh ** -0.5
+    if causal:
+        s = s + torch.full((N, N), float("-inf"), dtype=s.dtype).triu(1)
+    a = (torch.softmax(s, -1) @ sh(v)).transpose(1, 2).reshape(B, N, D)
+    if lora is None:
+        a = F.linear(a, p[f"{prefix}attn.out_proj.weight"], p[f"{prefix}attn.out_proj.bias"])
+    else:
+        a = lora_linear(a, p, f"{prefix}attn.proj.", lora[0], lora[1])
+    x = x + a
+    h = F.layer_norm(x, (D,), p[f"{prefix}ln_2.weight"], p[f"{prefix}ln_2.bias"], 1e-5)
+    h = F.linear(h, p[f"{prefix}mlp.c_fc.weight"], p[f"{prefix}mlp.c_fc.bias"])
+    h = h * torch.sigmoid(1.702 * h)
+    return x + F.linear(h, p[f"{prefix}mlp.c_proj.weight"], p[f"{prefix}mlp.c_proj.bias"])
+
+
+def clip_encode_image(p, images, cfg):
+    """VisionTransformer.forward, model.py:233-257, with Mona after each block when injected (mona.py:563-571:
+    adapter gets [N,B,D] and (grid, grid))."""
+    v = "visual."
+    P = cfg["patch"]
+    x = F.conv2d(images, p[f"{v}conv1.weight"], None, stride=P)
+    B, D, gh, gw = x.shape
+    x = x.reshape(B, D, -1).permute(0, 2, 1)
+    x = torch.cat([p[f"{v}class_embedding"].expand(B, 1, D), x], 1) + p[f"{v}positional_embedding"]
+    x = F.layer_norm(x, (D,), p[f"{v}ln_pre.weight"], p[f"{v}ln_pre.bias"], 1e-5)
+    for i in range(cfg["depth"]):
+        x = clip_block(x, p, f"{v}transformer.resblocks.{i}.", cfg["heads"], False, cfg.get("lora"))
+        mp = f"{v}transformer.resblocks.{i}.mona."
+        if f"{mp}gamma" in p:
+            x = mona(x, p, mp, (gh, gw), True)
+    x = F.layer_norm(x[:, 0], (D,), p[f"{v}ln_post.weight"], p[f"{v}ln_post.bias"], 1e-5)
+    return x @ p[f"{v}proj"]
+
+
+def clip_encode_text(p, text, cfg):
+    """CLIP.encode_text, model.py:361-374 (causal mask from build_attention_mask :344-350, EOT = argmax token id)."""
+    x = p["token_embedding.weight"][text] + p["positional_embedding"]
+    D = x.shape[-1]
+    for i in range(cfg["text_layers"]):
+        x = clip_block(x, p, f"transformer.resblocks.{i}.", cfg["text_heads"], True)
+    x = F.layer_norm(x, (D,), p["ln_final.weight"], p["ln_final.bias"], 1e-5)
+    return x[torch.arange(x.shape[0]), text.argmax(-1)] @ p["text_projection"]
+
+
+# ---------------------------------------------------------------------------------------------------
 # BERT text tower (pinned deps transformers 4.57.1 BertModel + open_clip HFTextEncoder; restated)
 # ---------------------------------------------------------------------------------------------------
 def encode_text(p, ids, cfg):

@@ -105,6 +105,58 @@ def main():
                     "temperature": 0.07}, os.path.join(out_dir, f"{tag}.pt"))
         print(tag, "ok; reference == oracle (fp64), golden written")
 
+    # ---- vendored OpenAI CLIP (ViT tower with Mona, and with LoRA) ------------------------------------------
+    rclip = load_ref("src/third_party/openai_clip/model.py", "ref_clip_model")
+    cfg = dict(patch=16, depth=1, heads=4, text_layers=1, text_heads=1)
+    for tag in ("clip_mona", "clip_lora"):
+        torch.manual_seed(17)
+        # the vendored LayerNorm casts to fp32 (model.py:168), so the reference tower runs in fp32; the oracle runs in fp64
+        m = rclip.CLIP(64, 32, 1, 256, 16, 8, 50, 64, 1, 1).float()
+        with torch.no_grad():  # bf16-representable weights keep the fixture small (stored as bf16)
+            for prm in m.parameters():
+                prm.copy_(prm.bfloat16().float())
+        for prm in m.parameters():
+            prm.requires_grad = False
+        if tag == "clip_mona":
+            rmona.inject_mona_variant_to_clip(m, variant="baseline", bottleneck_dim=64)
+            key = "mona"
+        else:
+            rlora.inject_lora_to_clip(m, lora_r=8, lora_alpha=32, lora_dropout=0.1)
+            key = "lora"
+        m = m.float().eval()
+        with torch.no_grad():
+            for n, prm in m.named_parameters():
+                if n.endswith("gamma"):
+                    prm.copy_(torch.randn(prm.shape) * 0.3)
+                if n.endswith("w_lora_B"):
+                    prm.copy_(torch.randn(prm.shape) * 0.05)
+                if key in n:
+                    prm.copy_(prm.bfloat16().float())
+        trainable = [n for n, _ in m.named_parameters() if key in n.lower()]
+        for n, prm in m.named_parameters():
+            prm.requires_grad = n in trainable
+        images = torch.rand(3, 3, 32, 32).float()
+        text = torch.randint(1, 48, (3, 8)); text[:, -1] = 49
+        gi = torch.randn(3, 64).float()
+        fi = m.encode_image(images)
+        with torch.no_grad():
+            ft = m.encode_text(text)
+        grads = torch.autograd.grad((fi * gi).sum(), [dict(m.named_parameters())[n] for n in trainable])
+        sd = {k: v.detach() for k, v in m.state_dict().items()}
+        p = {k: (v.double().clone().requires_grad_(k in trainable) if v.is_floating_point() else v) for k, v in sd.items()}
+        c2 = dict(cfg, lora=(8, 32)) if tag == "clip_lora" else cfg
+        fo = OF.clip_encode_image(p, images.double(), c2)
+        to = OF.clip_encode_text(p, text, c2)
+        go = torch.autograd.grad((fo * gi.double()).sum(), [p[n] for n in trainable])
+        rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+        assert rel(fo, fi) < 1e-5 and rel(to, ft) < 1e-5, (tag, rel(fo, fi), rel(to, ft))
+        for n_, a, b in zip(trainable, go, grads):
+            assert rel(a, b) < 1e-4, (tag, n_, rel(a, b))
+        torch.save({"state": {k: (v.bfloat16() if v.is_floating_point() else v) for k, v in sd.items()}, "images": images.float(), "text": text,
+                    "gi": gi.float(), "fi": fi.detach().float(), "ft": ft.float(), "trainable": trainable,
+                    "grads": {n: g_.float() for n, g_ in zip(trainable, grads)}, "cfg": c2}, os.path.join(out_dir, f"{tag}.pt"))
+        print(tag, "ok; vendored reference CLIP == oracle (fp64), golden written")
+
     # ---- RNG-stream parity of the drop-in constructors ---------------------------------------------------
     torch.set_default_dtype(torch.float32)
     from nextgen_uia_b200.adapters.mona import BaselineMona as MyMona

@@ -75,3 +75,16 @@ def test_oracle_global_batch_equals_concat():
     full, _ = OF.info_nce(I, T)
     halves = [OF.info_nce(I[:4], T[:4])[0], OF.info_nce(I[4:], T[4:])[0]]
     assert abs(float(full) - float(sum(halves) / 2)) > 1e-3  # local-only losses differ: global negatives matter
+
+
+@pytest.mark.parametrize("tag", ["clip_mona", "clip_lora"])
+def test_oracle_clip_matches_vendored_reference_golden(golden, tag):
+    """oracle restatement of the vendored OpenAI CLIP towers vs outputs of the reference model itself."""
+    g = golden(tag)
+    p = {k: (v.double().requires_grad_(k in g["trainable"]) if v.is_floating_point() else v) for k, v in g["state"].items()}
+    fi = OF.clip_encode_image(p, g["images"].double(), g["cfg"])
+    ft = OF.clip_encode_text(p, g["text"], g["cfg"])
+    assert relerr(fi, g["fi"]) < 1e-5 and relerr(ft, g["ft"]) < 1e-5
+    grads = torch.autograd.grad((fi * g["gi"].double()).sum(), [p[n] for n in g["trainable"]])
+    for n, gr in zip(g["trainable"], grads):
+        assert relerr(gr, g["grads"][n]) < 1e-4, n

@@ -216,3 +216,38 @@ def test_zero_shot_argmax_matches_oracle():
         tf = [model.encode_text(p.to(dev())).float().cpu() for p in prompts]
     got = OF.zero_shot_predict(fi, tf)
     assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("tag", ["clip_mona", "clip_lora"])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_openai_clip_golden(golden, tag, dtype):
+    """OpenAI-CLIP layout (sequence-first blocks, nn.MultiheadAttention, QuickGELU, LN eps 1e-5; config-4 family):
+    image features, text features (causal tower) and every adapter gradient vs the vendored reference model's outputs
+    (tests/golden/clip_*.pt, made by oracle/make_golden.py from src/third_party/openai_clip/model.py + mona.py / lora.py)."""
+    from nextgen_uia_b200.openai_clip import CLIP
+    from src.adapters import inject_mona_variant_to_clip, inject_lora_to_clip
+    g = golden(tag)
+    m = CLIP(64, 32, 1, 256, 16, 8, 50, 64, 1, 1)
+    for p in m.parameters():
+        p.requires_grad = False
+    if tag == "clip_mona":
+        inject_mona_variant_to_clip(m, variant="baseline", bottleneck_dim=64)
+    else:
+        inject_lora_to_clip(m, lora_r=8, lora_alpha=32, lora_dropout=0.1)
+    m.load_state_dict({k: (v.float() if v.is_floating_point() else v) for k, v in g["state"].items()}, strict=True)
+    for n, p in m.named_parameters():
+        p.requires_grad = n in g["trainable"]
+    m = m.to(dev()).eval().set_compute_dtype(dtype)
+    fi = m.encode_image(g["images"].to(dev()))
+    ft = m.encode_text(g["text"].to(dev()))
+    (fi * g["gi"].to(dev(), dtype)).sum().backward()
+    assert relerr(fi, g["fi"]) < TOL[dtype] and relerr(ft, g["ft"]) < TOL[dtype]
+    num = den = 0.0
+    for n, p in m.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None, n
+            d = p.grad.double().cpu() - g["grads"][n].double()
+            num += float((d * d).sum()); den += float((g["grads"][n].double() ** 2).sum())
+            if dtype == torch.float32:
+                assert relerr(p.grad, g["grads"][n]) < 1e-3, n
+    assert (num / den) ** 0.5 < (3e-2 if dtype == torch.bfloat16 else 1e-3)

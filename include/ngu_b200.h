@@ -134,9 +134,16 @@ int ngu_mona_pre_bwd(const ngu_mona_pre_bwd_desc* d, void* stream);
 typedef struct ngu_mona_conv_weights {
   const float* k3; const float* b3; const float* k5; const float* b5; const float* k7; const float* b7;
   const float* P; const float* bp;
+  /* variants (NULL = baseline behaviour):
+   *   freq   [C]        FreqEnhancedMonaOp.freq_filter (mona.py:279): rfft2 -> x f_c -> irfft2 == per-channel scale of the conv input
+   *   ne_*              NoiseAwareMonaOp.noise_estimator (mona.py:170-176): GAP -> 1x1 (C -> C/4) -> ReLU -> 1x1 (C/4 -> 3) -> softmax
+   *                     = per-image weights of the three depthwise branches (replacing the fixed 1/3) */
+  const float* freq;
+  const float* ne_w1; const float* ne_b1; const float* ne_w2; const float* ne_b2;
 } ngu_mona_conv_weights;
 typedef struct ngu_mona_conv_grads {
   float* dk3; float* db3; float* dk5; float* db5; float* dk7; float* db7; float* dP; float* dbp; float* db1;
+  float* dfreq; float* dne_w1; float* dne_b1; float* dne_w2; float* dne_b2;
 } ngu_mona_conv_grads;
 typedef struct ngu_mona_conv_desc {
   const void* h; void* g;          /* forward: h -> g */

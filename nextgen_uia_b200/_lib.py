@@ -61,11 +61,11 @@ class MonaPreBwdDesc(ctypes.Structure):
 
 
 class MonaConvWeights(ctypes.Structure):
-    _fields_ = [(n, _c_void_p) for n in ("k3", "b3", "k5", "b5", "k7", "b7", "P", "bp")]
+    _fields_ = [(n, _c_void_p) for n in ("k3", "b3", "k5", "b5", "k7", "b7", "P", "bp", "freq", "ne_w1", "ne_b1", "ne_w2", "ne_b2")]
 
 
 class MonaConvGrads(ctypes.Structure):
-    _fields_ = [(n, _c_void_p) for n in ("dk3", "db3", "dk5", "db5", "dk7", "db7", "dP", "dbp", "db1")]
+    _fields_ = [(n, _c_void_p) for n in ("dk3", "db3", "dk5", "db5", "dk7", "db7", "dP", "dbp", "db1", "dfreq", "dne_w1", "dne_b1", "dne_w2", "dne_b2")]
 
 
 class MonaConvDesc(ctypes.Structure):

@@ -30,27 +30,35 @@ def _next_seed():
 
 
 class MonaFunction(torch.autograd.Function):
-    """y = x + project2(dropout(gelu(convstage(project1(LN(x)*gamma + x*gammax)))))  on [B,N,D]."""
+    """y = x + project2(dropout(gelu(convstage(project1(LN(x)*gamma + x*gammax)))))  on [B,N,D].
+    Variant tensors (freq_filter, noise-estimator weights) are None for the baseline adapter."""
 
     @staticmethod
     def forward(ctx, x, norm_w, norm_b, gamma, gammax, w1, b1, k3, b3, k5, b5, k7, b7, pw, pb, w2, b2,
-                hw, has_cls, drop_p, seed):
+                freq, ne_w1, ne_b1, ne_w2, ne_b2, hw, has_cls, drop_p, seed):
         B, N, D = x.shape
         C = w1.shape[0]
         x2 = x.contiguous().view(B * N, D)
         dt = x2.dtype
         u, mean, rstd = ops.ln_fwd(x2, norm_w, norm_b, _LN_EPS, gamma=gamma, gammax=gammax)
         h = ops.gemm(u, ops.cast(w1, dt), bias=b1)                                   # [M, C]
-        conv_w = (k3, b3, k5, b5, k7, b7, pw, pb)
+        conv_w = (k3, b3, k5, b5, k7, b7, pw, pb, freq, ne_w1, ne_b1, ne_w2, ne_b2)
         g = ops.mona_conv_fwd(h.view(B, N, C), conv_w, hw, has_cls, drop_p, seed)     # [B, N, C]
         y = ops.gemm(g.view(B * N, C), ops.cast(w2, dt), bias=b2, aux=x2, aux_mode=L.AUX_RESIDUAL)
-        ctx.save_for_backward(x2, mean, rstd, u, h, g, norm_w, norm_b, gamma, gammax, w1, k3, b3, k5, b5, k7, b7, pw, pb, w2)
+        ctx.save_for_backward(x2, mean, rstd, u, h, g, norm_w, norm_b, gamma, gammax, w1, k3, b3, k5, b5, k7, b7, pw, pb, w2,
+                              *[t for t in (freq, ne_w1, ne_b1, ne_w2, ne_b2) if t is not None])
+        ctx.variant = (freq is not None, ne_w1 is not None)
         ctx.meta = (B, N, D, C, hw, has_cls, drop_p, seed)
         return y.view(B, N, D)
 
     @staticmethod
     def backward(ctx, dy):
-        (x2, mean, rstd, u, h, g, norm_w, norm_b, gamma, gammax, w1, k3, b3, k5, b5, k7, b7, pw, pb, w2) = ctx.saved_tensors
+        sv = ctx.saved_tensors
+        (x2, mean, rstd, u, h, g, norm_w, norm_b, gamma, gammax, w1, k3, b3, k5, b5, k7, b7, pw, pb, w2) = sv[:20]
+        has_freq, has_noise = ctx.variant
+        extra = list(sv[20:])
+        freq = extra.pop(0) if has_freq else None
+        ne_w1, ne_b1, ne_w2, ne_b2 = (extra if has_noise else [None] * 4)
         B, N, D, C, hw, has_cls, drop_p, seed = ctx.meta
         dev, dt = x2.device, x2.dtype
         dy2 = dy.contiguous().view(B * N, D)
@@ -62,8 +70,10 @@ class MonaFunction(torch.autograd.Function):
         # conv stage (recomputes z / a from h), also yields d project1.bias
         dk3, db3, dk5, db5, dk7, db7 = z(*k3.shape), z(C), z(*k5.shape), z(C), z(*k7.shape), z(C)
         dpw, dpb, db1 = z(*pw.shape), z(C), z(C)
-        dh = ops.mona_conv_bwd(h.view(B, N, C), dg.view(B, N, C), (k3, b3, k5, b5, k7, b7, pw, pb),
-                               (dk3, db3, dk5, db5, dk7, db7, dpw, dpb, db1), hw, has_cls, drop_p, seed)
+        dfreq = z(C) if has_freq else None
+        dn = [z(*t.shape) for t in (ne_w1, ne_b1, ne_w2, ne_b2)] if has_noise else [None] * 4
+        dh = ops.mona_conv_bwd(h.view(B, N, C), dg.view(B, N, C), (k3, b3, k5, b5, k7, b7, pw, pb, freq, ne_w1, ne_b1, ne_w2, ne_b2),
+                               (dk3, db3, dk5, db5, dk7, db7, dpw, dpb, db1, dfreq, *dn), hw, has_cls, drop_p, seed)
         dh2 = dh.view(B * N, C)
         # project1:  h = u W1^T + b1
         dw1 = ops.wgrad(u, dh2).t().contiguous()                                      # [C, D]
@@ -72,27 +82,78 @@ class MonaFunction(torch.autograd.Function):
         dnw, dnb, dgam, dgamx, db2 = z(D), z(D), z(D), z(D), z(D)
         dx = ops.mona_pre_bwd(du, dy2, x2, mean, rstd, norm_w, norm_b, gamma, gammax, dnw, dnb, dgam, dgamx, db2)
         return (dx.view(B, N, D), dnw, dnb, dgam, dgamx, dw1, db1, dk3, db3, dk5, db5, dk7, db7, dpw, dpb, dw2, db2,
-                None, None, None, None)
+                dfreq, dn[0], dn[1], dn[2], dn[3], None, None, None, None)
 
 
-class BaselineMonaOp(nn.Module):
-    """Parameter container for the multi-scale depthwise stage (reference mona.py:75-93).
-    forward() exists for API parity (NCHW in/out) and runs the same fused stage kernel."""
+class _MonaOpBase(nn.Module):
+    """Parameter container for the multi-scale depthwise stage.  forward() is not used by the adapters (the fused
+    stage kernel consumes the parameters directly)."""
 
-    def __init__(self, in_features):
-        super().__init__()
+    def _build_convs(self, in_features):
         self.conv1 = nn.Conv2d(in_features, in_features, kernel_size=3, padding=1, groups=in_features)
         self.conv2 = nn.Conv2d(in_features, in_features, kernel_size=5, padding=2, groups=in_features)
         self.conv3 = nn.Conv2d(in_features, in_features, kernel_size=7, padding=3, groups=in_features)
         self.projector = nn.Conv2d(in_features, in_features, kernel_size=1)
 
-    def stage_weights(self):
-        return (self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
-                self.conv3.weight, self.conv3.bias, self.projector.weight, self.projector.bias)
+    def _build_noise_estimator(self, in_features):
+        self.noise_estimator = nn.Sequential(
+            nn.AdaptiveAvgPool2d(1),
+            nn.Conv2d(in_features, in_features // 4, 1),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(in_features // 4, 3, 1),
+            nn.Softmax(dim=1),
+        )
+
+    def variant_tensors(self):
+        """(freq_filter, ne_w1, ne_b1, ne_w2, ne_b2) with None for absent parts."""
+        freq = getattr(self, "freq_filter", None)
+        ne = getattr(self, "noise_estimator", None)
+        if ne is None:
+            return freq, None, None, None, None
+        return freq, ne[1].weight, ne[1].bias, ne[3].weight, ne[3].bias
+
+
+class BaselineMonaOp(_MonaOpBase):
+    """reference mona.py:75-93"""
+
+    def __init__(self, in_features):
+        super().__init__()
+        self._build_convs(in_features)
+
+
+class NoiseAwareMonaOp(_MonaOpBase):
+    """reference mona.py:159-196: per-image softmax weights of the three depthwise branches."""
+
+    def __init__(self, in_features):
+        super().__init__()
+        self._build_convs(in_features)
+        self._build_noise_estimator(in_features)
+
+
+class FreqEnhancedMonaOp(_MonaOpBase):
+    """reference mona.py:261-296: learnable per-channel frequency filter (rfft2 -> x f_c -> irfft2 == scale by f_c)."""
+
+    def __init__(self, in_features):
+        super().__init__()
+        self._build_convs(in_features)
+        self.freq_filter = nn.Parameter(torch.ones(in_features))
+
+
+class HybridNoiseFreqMonaOp(_MonaOpBase):
+    """reference mona.py:370-425: frequency filter, then noise-aware branch weights."""
+
+    def __init__(self, in_features):
+        super().__init__()
+        self._build_convs(in_features)
+        self.freq_filter = nn.Parameter(torch.ones(in_features))
+        self._build_noise_estimator(in_features)
 
 
 class BaselineMona(nn.Module):
-    """Baseline Mona adapter.  forward(x [N,B,D], hw_shapes) -> [N,B,D]   (reference mona.py:96-151)."""
+    """Baseline Mona adapter.  forward(x [N,B,D], hw_shapes) -> [N,B,D]   (reference mona.py:96-151).
+    The variants below differ only in the `adapter_conv` stage."""
+
+    op_class = BaselineMonaOp
 
     def __init__(self, in_dim, bottleneck_dim=64):
         super().__init__()
@@ -100,7 +161,7 @@ class BaselineMona(nn.Module):
         self.nonlinear = torch.nn.functional.gelu  # attribute kept for parity; the kernel applies exact-erf GELU
         self.project2 = nn.Linear(bottleneck_dim, in_dim)
         self.dropout = nn.Dropout(p=0.1)
-        self.adapter_conv = BaselineMonaOp(bottleneck_dim)
+        self.adapter_conv = self.op_class(bottleneck_dim)
         self.norm = nn.LayerNorm(in_dim)
         self.gamma = nn.Parameter(torch.ones(in_dim) * 1e-6)
         self.gammax = nn.Parameter(torch.ones(in_dim))
@@ -116,14 +177,31 @@ class BaselineMona(nn.Module):
         p = self.dropout.p if (self.training and self.dropout.p > 0) else 0.0
         seed = _next_seed() if p > 0 else 0
         c = self.adapter_conv
+        freq, ne_w1, ne_b1, ne_w2, ne_b2 = c.variant_tensors()
         return MonaFunction.apply(xb, self.norm.weight, self.norm.bias, self.gamma, self.gammax,
                                   self.project1.weight, self.project1.bias,
                                   c.conv1.weight, c.conv1.bias, c.conv2.weight, c.conv2.bias, c.conv3.weight, c.conv3.bias,
                                   c.projector.weight, c.projector.bias,
-                                  self.project2.weight, self.project2.bias, hw, has_cls, p, seed)
+                                  self.project2.weight, self.project2.bias,
+                                  freq, ne_w1, ne_b1, ne_w2, ne_b2, hw, has_cls, p, seed)
 
     def forward(self, x, hw_shapes=None):
         return self.forward_batch_first(x.permute(1, 0, 2), hw_shapes).permute(1, 0, 2)
+
+
+class NoiseAwareMona(BaselineMona):
+    """reference mona.py:198-258"""
+    op_class = NoiseAwareMonaOp
+
+
+class FreqEnhancedMona(BaselineMona):
+    """reference mona.py:298-367 (the default --mona_variant of src/models/biomedclip/finetune.py:76)"""
+    op_class = FreqEnhancedMonaOp
+
+
+class HybridNoiseFreqMona(BaselineMona):
+    """reference mona.py:427-492 (what scripts/biomedclip.sh uses)"""
+    op_class = HybridNoiseFreqMonaOp
 
 
 class BatchFirstMonaWrapper(nn.Module):
@@ -141,7 +219,7 @@ class BatchFirstMonaWrapper(nn.Module):
         return m(x.permute(1, 0, 2), hw_shapes).permute(1, 0, 2)
 
 
-_VARIANTS = {"baseline": BaselineMona}
+_VARIANTS = {"baseline": BaselineMona, "noise_aware": NoiseAwareMona, "freq_enhanced": FreqEnhancedMona, "hybrid": HybridNoiseFreqMona}
 
 
 def register_variant(name, cls):

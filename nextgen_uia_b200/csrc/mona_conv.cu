@@ -256,33 +256,80 @@ mona_conv_bwd_kernel(const T* __restrict__ h, const T* __restrict__ dg, T* __res
 // =====================================================================================================
 constexpr int kStrip = 8;
 
+constexpr int CH = C / 4;  // noise-estimator hidden width (reference: in_features // 4)
+
 struct FastSmem {
-  float kc[49][C];
-  float bc[C];
-  float pt[C][C];  // pt[i][o] = P[o][i]
+  float kc[49][C];   // effective merged stencil: f_c * (w1 k3 + w2 k5 + w3 k7) + delta
+  float bc[C];       // w1 b3 + w2 b5 + w3 b7
+  float pt[C][C];    // pt[i][o] = P[o][i]
   float bp[C];
+  // variant state (baseline: f = 1, w = 1/3)
+  float fr[C];       // freq_filter
+  float hm[C];       // mean over positions of h (per channel)
+  float part[4][C];  // scratch for the per-channel reductions
+  float hid[CH];     // ReLU(W1 gap + b1)
+  float wbr[4];      // branch weights w1, w2, w3 (softmax) [+ pad]
+  float dwbr[4];     // backward: d loss / d w_i
+  float dgap[C];     // backward: d loss / d gap_c
 };
 
+// Loads the image tile and the projector, evaluates the variant prologue (frequency scale, noise-estimator branch
+// weights) and builds the effective merged stencil.  Ends with a __syncthreads().
 template <typename T>
 NGU_DEVINL void fast_load_common(FastSmem& s, T* hs, const T* hb, const ngu_mona_conv_weights& w, int HW, int has_cls) {
-  for (int i = threadIdx.x; i < 49 * C; i += kThreads) {
-    const int c = i % C, t = i / C;
-    const int ky = t / 7, kx = t % 7;
-    float v = w.k7[c * 49 + t];
-    if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) v += w.k5[c * 25 + (ky - 1) * 5 + (kx - 1)];
-    if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) v += w.k3[c * 9 + (ky - 2) * 3 + (kx - 2)];
-    v *= (1.0f / 3.0f);
-    if (t == 24) v += 1.0f;
-    s.kc[t][c] = v;
-  }
+  const int c = threadIdx.x & (C - 1), grp = threadIdx.x >> 6;
   for (int i = threadIdx.x; i < C * C; i += kThreads) s.pt[i % C][i / C] = w.P[i];
   if (threadIdx.x < C) {
-    s.bc[threadIdx.x] = (w.b3[threadIdx.x] + w.b5[threadIdx.x] + w.b7[threadIdx.x]) * (1.0f / 3.0f);
     s.bp[threadIdx.x] = w.bp[threadIdx.x];
+    s.fr[threadIdx.x] = w.freq ? w.freq[threadIdx.x] : 1.0f;
   }
   constexpr int V = Vec<T>::N;
   const T* src = hb + has_cls * C;
   for (int i = threadIdx.x * V; i < HW * C; i += kThreads * V) *reinterpret_cast<uint4*>(hs + i) = *reinterpret_cast<const uint4*>(src + i);
+  __syncthreads();
+  if (w.ne_w1 != nullptr) {
+    // noise estimator: gap_c = f_c * mean_p h[p][c]  ->  hid = relu(W1 gap + b1)  ->  w = softmax(W2 hid + b2)
+    float a = 0.f;
+    for (int p = grp; p < HW; p += kThreads / C) a += to_f32<T>(hs[p * C + c]);
+    s.part[grp][c] = a;
+    __syncthreads();
+    if (threadIdx.x < C) s.hm[c] = (s.part[0][c] + s.part[1][c] + s.part[2][c] + s.part[3][c]) / float(HW);
+    __syncthreads();
+    if (threadIdx.x < CH) {
+      float acc = w.ne_b1[threadIdx.x];
+      for (int i = 0; i < C; ++i) acc = fmaf(w.ne_w1[threadIdx.x * C + i], s.fr[i] * s.hm[i], acc);
+      s.hid[threadIdx.x] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float lg[3];
+      for (int i = 0; i < 3; ++i) {
+        float acc = w.ne_b2[i];
+        for (int j = 0; j < CH; ++j) acc = fmaf(w.ne_w2[i * CH + j], s.hid[j], acc);
+        lg[i] = acc;
+      }
+      const float mx = fmaxf(lg[0], fmaxf(lg[1], lg[2]));
+      const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), e2 = expf(lg[2] - mx);
+      const float inv = 1.f / (e0 + e1 + e2);
+      s.wbr[0] = e0 * inv; s.wbr[1] = e1 * inv; s.wbr[2] = e2 * inv;
+    }
+  } else if (threadIdx.x == 0) {
+    s.wbr[0] = s.wbr[1] = s.wbr[2] = 1.0f / 3.0f;
+  }
+  __syncthreads();
+  const float w1 = s.wbr[0], w2 = s.wbr[1], w3 = s.wbr[2];
+  for (int i = threadIdx.x; i < 49 * C; i += kThreads) {
+    const int cc = i % C, t = i / C;
+    const int ky = t / 7, kx = t % 7;
+    float v = w3 * w.k7[cc * 49 + t];
+    if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) v = fmaf(w2, w.k5[cc * 25 + (ky - 1) * 5 + (kx - 1)], v);
+    if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) v = fmaf(w1, w.k3[cc * 9 + (ky - 2) * 3 + (kx - 2)], v);
+    v *= s.fr[cc];
+    if (t == 24) v += 1.0f;
+    s.kc[t][cc] = v;
+  }
+  if (threadIdx.x < C) s.bc[threadIdx.x] = w1 * w.b3[threadIdx.x] + w2 * w.b5[threadIdx.x] + w3 * w.b7[threadIdx.x];
+  __syncthreads();
 }
 
 // out[y][x0 + j] = bias + sum_{ky,kx} k[ky*7 + (FLIP ? 6-kx : kx)] * in[y + (FLIP ? 3-ky : ky-3)][x0 + j + kx - 3]   (channel c)
@@ -472,11 +519,124 @@ mona_conv_bwd_fast_kernel(const T* __restrict__ h, const T* __restrict__ dg, T* 
     }
   }
   __syncthreads();
-  // ---- phase 5: dh = transposed stencil of dz;  phase 6: stencil weight grads dk[t] = sum_p dz[p] h[p + off_t]
-  float dbc_acc = 0.f;
-  float dk[49];
+  // ---- phase 5: correlation sums G[t][c] = sum_p dz[p][c] h[p + off_t][c]  and  S[c] = sum_p dz[p][c]
+  //      (z = f_c * sum_t kw[c][t] h[p+off_t] + h + bias, kw = sum_i w_i k_i  =>  every stencil-side gradient is a
+  //      contraction of G / S); accumulated across the four position groups with shared-memory atomics.
+  float* Gs = reinterpret_cast<float*>(das);          // [49][C] floats (12.5 KB) — da is dead after phase 4
+  float* Ss = s.part[0];                               // [C]
+  for (int i = threadIdx.x; i < 49 * C; i += kThreads) Gs[i] = 0.f;
+  if (threadIdx.x < C) Ss[threadIdx.x] = 0.f;
+  __syncthreads();
+  {
+    float dk[49];
 #pragma unroll
-  for (int t = 0; t < 49; ++t) dk[t] = 0.f;
+    for (int t = 0; t < 49; ++t) dk[t] = 0.f;
+    float dbc_acc = 0.f;
+    for (int st = grp; st < H * spr; st += kThreads / C) {
+      const int y = st / spr, x0 = (st % spr) * kStrip;
+      float dzv[kStrip];
+#pragma unroll
+      for (int j = 0; j < kStrip; ++j) {
+        dzv[j] = (x0 + j < W) ? to_f32<T>(zs[(y * W + x0 + j) * C + c]) : 0.f;
+        dbc_acc += dzv[j];
+      }
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky) {
+        const int yy = y + ky - 3;
+        if (yy < 0 || yy >= H) continue;
+        float win[kStrip + 6];
+#pragma unroll
+        for (int i = 0; i < kStrip + 6; ++i) {
+          const int xx = x0 + i - 3;
+          win[i] = (xx >= 0 && xx < W) ? to_f32<T>(hs[(yy * W + xx) * C + c]) : 0.f;
+        }
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          float a = dk[ky * 7 + kx];
+#pragma unroll
+          for (int j = 0; j < kStrip; ++j) a = fmaf(dzv[j], win[j + kx], a);
+          dk[ky * 7 + kx] = a;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 49; ++t) atomicAdd(&Gs[t * C + c], dk[t]);
+    atomicAdd(&Ss[c], dbc_acc);
+  }
+  __syncthreads();
+  // ---- phase 6: stencil / bias / frequency / branch-weight gradients from G and S
+  const float w1 = s.wbr[0], w2 = s.wbr[1], w3 = s.wbr[2];
+  if (threadIdx.x < C) {
+    const float f = s.fr[c], Sc = Ss[c];
+    float q1 = 0.f, q2 = 0.f, q3 = 0.f;  // q_i = sum_{t in branch i} k_i[c][t] G[t][c]
+    for (int t = 0; t < 49; ++t) {
+      const int ky = t / 7, kx = t % 7;
+      const float g = Gs[t * C + c];
+      q3 = fmaf(w.k7[c * 49 + t], g, q3);
+      atomicAdd(gr.dk7 + c * 49 + t, w3 * f * g);
+      if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) {
+        const int u = (ky - 1) * 5 + (kx - 1);
+        q2 = fmaf(w.k5[c * 25 + u], g, q2);
+        atomicAdd(gr.dk5 + c * 25 + u, w2 * f * g);
+      }
+      if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) {
+        const int u = (ky - 2) * 3 + (kx - 2);
+        q1 = fmaf(w.k3[c * 9 + u], g, q1);
+        atomicAdd(gr.dk3 + c * 9 + u, w1 * f * g);
+      }
+    }
+    atomicAdd(gr.db3 + c, w1 * Sc);
+    atomicAdd(gr.db5 + c, w2 * Sc);
+    atomicAdd(gr.db7 + c, w3 * Sc);
+    // direct frequency-filter gradient: d z / d f_c = sum_t kw[c][t] h[p + off_t]
+    s.part[1][c] = w1 * q1 + w2 * q2 + w3 * q3;
+    // branch-weight gradient contributions of this channel
+    s.part[2][c] = f * q1 + w.b3[c] * Sc;
+    s.part[3][c] = f * q2 + w.b5[c] * Sc;
+    s.dgap[c] = f * q3 + w.b7[c] * Sc;  // (temporarily) third branch contribution
+  }
+  __syncthreads();
+  float cst = 0.f;  // constant added to dh at every position of channel c (through the global average pool)
+  if (w.ne_w1 != nullptr) {
+    if (threadIdx.x < 3) {
+      const float* src = threadIdx.x == 0 ? s.part[2] : threadIdx.x == 1 ? s.part[3] : s.dgap;
+      float a = 0.f;
+      for (int i = 0; i < C; ++i) a += src[i];
+      s.dwbr[threadIdx.x] = a;
+    }
+    __syncthreads();
+    // softmax backward -> d logits; then the two 1x1 layers
+    const float dot = w1 * s.dwbr[0] + w2 * s.dwbr[1] + w3 * s.dwbr[2];
+    const float dl0 = w1 * (s.dwbr[0] - dot), dl1 = w2 * (s.dwbr[1] - dot), dl2 = w3 * (s.dwbr[2] - dot);
+    __syncthreads();  // everyone has read dwbr / dgap(temp) before they are overwritten
+    if (threadIdx.x < CH) {
+      const int j = threadIdx.x;
+      const float hj = s.hid[j];
+      atomicAdd(gr.dne_w2 + 0 * CH + j, dl0 * hj);
+      atomicAdd(gr.dne_w2 + 1 * CH + j, dl1 * hj);
+      atomicAdd(gr.dne_w2 + 2 * CH + j, dl2 * hj);
+      const float dh_ = hj > 0.f ? (w.ne_w2[0 * CH + j] * dl0 + w.ne_w2[1 * CH + j] * dl1 + w.ne_w2[2 * CH + j] * dl2) : 0.f;
+      s.hid[j] = dh_;  // reuse as d hid
+      atomicAdd(gr.dne_b1 + j, dh_);
+    }
+    if (threadIdx.x == 0) { atomicAdd(gr.dne_b2 + 0, dl0); atomicAdd(gr.dne_b2 + 1, dl1); atomicAdd(gr.dne_b2 + 2, dl2); }
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float dg = 0.f;
+      const float gap = s.fr[c] * s.hm[c];
+      for (int j = 0; j < CH; ++j) {
+        dg = fmaf(w.ne_w1[j * C + c], s.hid[j], dg);
+        atomicAdd(gr.dne_w1 + j * C + c, s.hid[j] * gap);
+      }
+      s.dgap[c] = dg;
+    }
+    __syncthreads();
+    cst = s.dgap[c] * s.fr[c] / float(HW);
+    if (threadIdx.x < C && gr.dfreq) atomicAdd(gr.dfreq + c, s.part[1][c] + s.dgap[c] * s.hm[c]);
+  } else {
+    if (threadIdx.x < C && gr.dfreq && w.freq) atomicAdd(gr.dfreq + c, s.part[1][c]);
+  }
+  // ---- phase 7: dh = transposed effective stencil of dz (+ the pooled-path constant)
   {
     float k[49];
 #pragma unroll
@@ -484,78 +644,28 @@ mona_conv_bwd_fast_kernel(const T* __restrict__ h, const T* __restrict__ dg, T* 
     for (int st = grp; st < H * spr; st += kThreads / C) {
       const int y = st / spr, x0 = (st % spr) * kStrip;
       float acc[kStrip];
-      stencil_strip<T, true>(zs, k, 0.f, y, x0, H, W, c, acc);
+      stencil_strip<T, true>(zs, k, cst, y, x0, H, W, c, acc);
 #pragma unroll
       for (int j = 0; j < kStrip; ++j)
         if (x0 + j < W) { dhb[(has_cls + y * W + x0 + j) * C + c] = from_f32<T>(acc[j]); db1_acc += acc[j]; }
     }
   }
-  for (int st = grp; st < H * spr; st += kThreads / C) {
-    const int y = st / spr, x0 = (st % spr) * kStrip;
-    float dzv[kStrip];
-#pragma unroll
-    for (int j = 0; j < kStrip; ++j) {
-      dzv[j] = (x0 + j < W) ? to_f32<T>(zs[(y * W + x0 + j) * C + c]) : 0.f;
-      dbc_acc += dzv[j];
-    }
-#pragma unroll
-    for (int ky = 0; ky < 7; ++ky) {
-      const int yy = y + ky - 3;
-      if (yy < 0 || yy >= H) continue;
-      float win[kStrip + 6];
-#pragma unroll
-      for (int i = 0; i < kStrip + 6; ++i) {
-        const int xx = x0 + i - 3;
-        win[i] = (xx >= 0 && xx < W) ? to_f32<T>(hs[(yy * W + xx) * C + c]) : 0.f;
-      }
-#pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        float a = dk[ky * 7 + kx];
-#pragma unroll
-        for (int j = 0; j < kStrip; ++j) a = fmaf(dzv[j], win[j + kx], a);
-        dk[ky * 7 + kx] = a;
-      }
-    }
-  }
-  __syncthreads();
-  // cross-group reduction of dk through smem (reuses the z / da tiles), then one atomic per (tap, channel)
-  float* red = reinterpret_cast<float*>(zs);  // needs 4*49*64 floats = 50,176 B <= 2 tiles when HW*C*sizeof(T)*2 >= that
-  const bool red_ok = size_t(HW) * C * sizeof(T) * 2 >= size_t(4) * 49 * C * sizeof(float);
-  if (red_ok) {
-#pragma unroll
-    for (int t = 0; t < 49; ++t) red[(grp * 49 + t) * C + c] = dk[t];
-    __syncthreads();
-    for (int i = threadIdx.x; i < 49 * C; i += kThreads) {
-      const int t = i / C, cc = i % C;
-      const float v = (red[(0 * 49 + t) * C + cc] + red[(1 * 49 + t) * C + cc] + red[(2 * 49 + t) * C + cc] + red[(3 * 49 + t) * C + cc]) * (1.0f / 3.0f);
-      const int ky = t / 7, kx = t % 7;
-      atomicAdd(gr.dk7 + cc * 49 + t, v);
-      if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) atomicAdd(gr.dk5 + cc * 25 + (ky - 1) * 5 + (kx - 1), v);
-      if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) atomicAdd(gr.dk3 + cc * 9 + (ky - 2) * 3 + (kx - 2), v);
-    }
-  } else {
-#pragma unroll
-    for (int t = 0; t < 49; ++t) {
-      const float v = dk[t] * (1.0f / 3.0f);
-      const int ky = t / 7, kx = t % 7;
-      atomicAdd(gr.dk7 + c * 49 + t, v);
-      if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) atomicAdd(gr.dk5 + c * 25 + (ky - 1) * 5 + (kx - 1), v);
-      if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) atomicAdd(gr.dk3 + c * 9 + (ky - 2) * 3 + (kx - 2), v);
-    }
-  }
-  {
-    const float bsum = dbc_acc * (1.0f / 3.0f);
-    atomicAdd(gr.db3 + c, bsum);
-    atomicAdd(gr.db5 + c, bsum);
-    atomicAdd(gr.db7 + c, bsum);
-    atomicAdd(gr.db1 + c, db1_acc);
-  }
+  atomicAdd(gr.db1 + c, db1_acc);
+}
+
+// h tile + z tile (+ da tile in backward; the da region is reused as the [49][C] fp32 correlation buffer, so it
+// is at least that large)
+template <typename T>
+size_t fast_smem_bytes(int HW, bool bwd) {
+  const size_t tile = size_t(HW) * C * sizeof(T);
+  const size_t da = tile > size_t(49) * C * sizeof(float) ? tile : size_t(49) * C * sizeof(float);
+  return sizeof(FastSmem) + 2 * tile + (bwd ? da : 0);
 }
 
 template <typename T>
 bool fast_ok(const ngu_mona_conv_desc& d, bool bwd) {
   const int HW = d.H * d.W;
-  const size_t smem = sizeof(FastSmem) + size_t(HW) * C * sizeof(T) * (bwd ? 3 : 2);
+  const size_t smem = fast_smem_bytes<T>(HW, bwd);
   return d.W <= 16 && d.H <= 16 && smem <= 227 * 1024;
 }
 
@@ -565,7 +675,7 @@ int conv_smem_bytes(int HW, bool bwd) { return int(sizeof(ConvSmem)) + HW * C * 
 template <typename T>
 int launch_fwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
   if (fast_ok<T>(d, false)) {
-    const int smf = int(sizeof(FastSmem)) + d.H * d.W * C * int(sizeof(T)) * 2;
+    const int smf = int(fast_smem_bytes<T>(d.H * d.W, false));
     cudaError_t e = cudaFuncSetAttribute(mona_conv_fwd_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
     if (e != cudaSuccess) return cuda_status(e, "mona_conv_fwd attr");
     mona_conv_fwd_fast_kernel<T><<<d.B, kThreads, smf, st>>>(reinterpret_cast<const T*>(d.h), reinterpret_cast<T*>(d.g), d.w, d.N, d.H,
@@ -583,7 +693,7 @@ int launch_fwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
 template <typename T>
 int launch_bwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
   if (fast_ok<T>(d, true)) {
-    const int smf = int(sizeof(FastSmem)) + d.H * d.W * C * int(sizeof(T)) * 3;
+    const int smf = int(fast_smem_bytes<T>(d.H * d.W, true));
     cudaError_t e = cudaFuncSetAttribute(mona_conv_bwd_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
     if (e != cudaSuccess) return cuda_status(e, "mona_conv_bwd attr");
     mona_conv_bwd_fast_kernel<T><<<d.B, kThreads, smf, st>>>(reinterpret_cast<const T*>(d.h), reinterpret_cast<const T*>(d.dg),
@@ -611,14 +721,28 @@ int validate(const ngu_mona_conv_desc& d, const char* what) {
   return NGU_OK;
 }
 
+int validate_variant(const ngu_mona_conv_desc& d, const char* what, bool bwd) {
+  const bool noise = d.w.ne_w1 != nullptr;
+  if (noise && !(d.w.ne_b1 && d.w.ne_w2 && d.w.ne_b2)) { set_last_error("%s: noise estimator needs w1, b1, w2, b2", what); return NGU_ERR_ARG; }
+  if ((noise || d.w.freq) && !(d.H <= 16 && d.W <= 16)) {
+    set_last_error("%s: Mona variants (frequency filter / noise estimator) are built for grids up to 16x16 (got %dx%d)", what, d.H, d.W);
+    return NGU_ERR_SHAPE;
+  }
+  if (bwd && noise && !(d.gr.dne_w1 && d.gr.dne_b1 && d.gr.dne_w2 && d.gr.dne_b2)) { set_last_error("%s: missing noise-estimator gradient buffers", what); return NGU_ERR_ARG; }
+  if (bwd && d.w.freq && !d.gr.dfreq) { set_last_error("%s: missing freq_filter gradient buffer", what); return NGU_ERR_ARG; }
+  return NGU_OK;
+}
+
 }  // namespace
 
 int mona_conv_fwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
   if (int rc = validate(d, "mona_conv_fwd")) return rc;
+  if (int rc = validate_variant(d, "mona_conv_fwd", false)) return rc;
   return d.dtype == NGU_F32 ? launch_fwd<float>(d, st) : launch_fwd<bf16>(d, st);
 }
 int mona_conv_bwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
   if (int rc = validate(d, "mona_conv_bwd")) return rc;
+  if (int rc = validate_variant(d, "mona_conv_bwd", true)) return rc;
   return d.dtype == NGU_F32 ? launch_bwd<float>(d, st) : launch_bwd<bf16>(d, st);
 }
 

@@ -136,15 +136,19 @@ def mona_pre_bwd(du, dy, x, mean, rstd, w, b, gamma, gammax, dw, db, dgamma, dga
 def _conv_desc(h, weights, hw, has_cls, drop_p, seed):
     B, N, C = h.shape
     d = L.MonaConvDesc()
-    k3, b3, k5, b5, k7, b7, P, bp = weights
+    k3, b3, k5, b5, k7, b7, P, bp = weights[:8]
     d.w.k3, d.w.b3, d.w.k5, d.w.b5, d.w.k7, d.w.b7, d.w.P, d.w.bp = (_f32(t).data_ptr() for t in (k3, b3, k5, b5, k7, b7, P, bp))
+    if len(weights) > 8:  # variants: (freq, ne_w1, ne_b1, ne_w2, ne_b2), each tensor or None
+        freq, w1, b1, w2, b2 = weights[8:13]
+        d.w.freq = _p(freq)
+        d.w.ne_w1, d.w.ne_b1, d.w.ne_w2, d.w.ne_b2 = _p(w1), _p(b1), _p(w2), _p(b2)
     d.B, d.N, d.H, d.W, d.C, d.has_cls = B, N, hw[0], hw[1], C, int(has_cls)
     d.drop_p, d.seed, d.dtype = float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _dt(h)
     return d
 
 
 def mona_conv_fwd(h, weights, hw, has_cls, drop_p=0.0, seed=0):
-    """h [B,N,C] -> g = dropout(gelu(conv-stage(h))); weights = (k3,b3,k5,b5,k7,b7,P,bp) fp32."""
+    """h [B,N,C] -> g = dropout(gelu(conv-stage(h))); weights = (k3,b3,k5,b5,k7,b7,P,bp[,freq,ne_w1,ne_b1,ne_w2,ne_b2]) fp32."""
     _need_cuda(h)
     assert h.is_contiguous()
     g = torch.empty_like(h)
@@ -161,7 +165,9 @@ def mona_conv_bwd(h, dg, weights, grads, hw, has_cls, drop_p=0.0, seed=0):
     dh = torch.empty_like(h)
     d = _conv_desc(h, weights, hw, has_cls, drop_p, seed)
     d.h, d.dg, d.dh = h.data_ptr(), dg.data_ptr(), dh.data_ptr()
-    (d.gr.dk3, d.gr.db3, d.gr.dk5, d.gr.db5, d.gr.dk7, d.gr.db7, d.gr.dP, d.gr.dbp, d.gr.db1) = (_f32(t).data_ptr() for t in grads)
+    (d.gr.dk3, d.gr.db3, d.gr.dk5, d.gr.db5, d.gr.dk7, d.gr.db7, d.gr.dP, d.gr.dbp, d.gr.db1) = (_f32(t).data_ptr() for t in grads[:9])
+    if len(grads) > 9:
+        d.gr.dfreq, d.gr.dne_w1, d.gr.dne_b1, d.gr.dne_w2, d.gr.dne_b2 = (_p(t) for t in grads[9:14])
     L.check(L.lib().ngu_mona_conv_bwd(_byref(d), _stream()), "ngu_mona_conv_bwd")
     return dh
 

@@ -18,12 +18,21 @@ def mona_conv_stage(h, p, prefix, hw, has_cls):
     H, W = hw
     sp = h[:, 1:, :] if has_cls else h
     z = sp.reshape(B, H, W, C).permute(0, 3, 1, 2)                                  # NCHW, mona.py:135
-    acc = 0
-    for name, pad in (("conv1", 1), ("conv2", 2), ("conv3", 3)):                   # 3x3, 5x5, 7x7 depthwise
-        acc = acc + F.conv2d(z, p[f"{prefix}adapter_conv.{name}.weight"], p[f"{prefix}adapter_conv.{name}.bias"],
-                             padding=pad, groups=C)
-    z = acc / 3.0 + z                                                               # mona.py:89
-    z = z + F.conv2d(z, p[f"{prefix}adapter_conv.projector.weight"], p[f"{prefix}adapter_conv.projector.bias"])  # :91-93
+    ident = z
+    ac = f"{prefix}adapter_conv."
+    if f"{ac}freq_filter" in p:                                                     # mona.py:283-286 / :395-398
+        zf = torch.fft.rfft2(z, dim=(-2, -1)) * p[f"{ac}freq_filter"].view(1, -1, 1, 1)
+        z = torch.fft.irfft2(zf, s=(H, W), dim=(-2, -1))
+    branches = [F.conv2d(z, p[f"{ac}{name}.weight"], p[f"{ac}{name}.bias"], padding=pad, groups=C)
+                for name, pad in (("conv1", 1), ("conv2", 2), ("conv3", 3))]        # 3x3, 5x5, 7x7 depthwise
+    if f"{ac}noise_estimator.1.weight" in p:                                        # mona.py:170-176, :187-192
+        g = z.mean(dim=(2, 3), keepdim=True)
+        g = F.relu(F.conv2d(g, p[f"{ac}noise_estimator.1.weight"], p[f"{ac}noise_estimator.1.bias"]))
+        wts = torch.softmax(F.conv2d(g, p[f"{ac}noise_estimator.3.weight"], p[f"{ac}noise_estimator.3.bias"]), dim=1)
+        z = sum(b * wts[:, i:i + 1] for i, b in enumerate(branches)) + ident
+    else:
+        z = sum(branches) / 3.0 + ident                                             # mona.py:89
+    z = z + F.conv2d(z, p[f"{ac}projector.weight"], p[f"{ac}projector.bias"])       # mona.py:91-93
     sp = z.permute(0, 2, 3, 1).reshape(B, H * W, C)
     return torch.cat([h[:, :1, :], sp], 1) if has_cls else sp
 

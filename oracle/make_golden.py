@@ -64,6 +64,37 @@ def main():
                     "grads": {k: g.float() for (k, _), g in zip(params, grads[1:])}}, os.path.join(out_dir, f"{tag}.pt"))
         print(tag, "ok; reference == oracle (fp64), golden written")
 
+    # ---- Mona variants (noise-aware / frequency-enhanced / hybrid), 6x6 grid + CLS ---------------------------
+    for tag, cls in {"mona_noise": rmona.NoiseAwareMona, "mona_freq": rmona.FreqEnhancedMona, "mona_hybrid": rmona.HybridNoiseFreqMona}.items():
+        torch.manual_seed(23)
+        D, hw, B = 256, (6, 6), 3
+        m = rmona.BatchFirstMonaWrapper(cls(D, 64)).double().eval()
+        with torch.no_grad():
+            m.clip_mona.gamma.copy_(torch.randn(D) * 0.5)
+            if hasattr(m.clip_mona.adapter_conv, "freq_filter"):
+                m.clip_mona.adapter_conv.freq_filter.copy_(1 + 0.3 * torch.randn(64))
+            if hasattr(m.clip_mona.adapter_conv, "noise_estimator"):
+                for prm in m.clip_mona.adapter_conv.noise_estimator.parameters():
+                    prm.mul_(3.0)  # spread the softmax so the branch weights are not ~1/3
+        N = hw[0] * hw[1] + 1
+        x = torch.randn(B, N, D, requires_grad=True)
+        gy = torch.randn(B, N, D)
+        y = m(x, hw)
+        params = list(m.named_parameters())
+        grads = torch.autograd.grad((y * gy).sum(), [x] + [p for _, p in params])
+        sd = {k: v.detach() for k, v in m.state_dict().items()}
+        p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        xo = x.detach().clone().requires_grad_(True)
+        yo = OF.mona(xo, p, "clip_mona.", hw, True)
+        go = torch.autograd.grad((yo * gy).sum(), [xo] + [p[k] for k, _ in params])
+        assert torch.allclose(yo, y, atol=1e-10, rtol=1e-10), tag
+        for a, b in zip(go, grads):
+            assert torch.allclose(a, b, atol=1e-9, rtol=1e-9), tag
+        torch.save({"state": {k: v.float() for k, v in sd.items()}, "x": x.detach().float(), "gy": gy.float(), "hw": hw,
+                    "has_cls": True, "y": y.detach().float(), "dx": grads[0].float(),
+                    "grads": {k: g_.float() for (k, _), g_ in zip(params, grads[1:])}}, os.path.join(out_dir, f"{tag}.pt"))
+        print(tag, "ok; reference == oracle (fp64), golden written")
+
     # ---- LinearLoRA ----------------------------------------------------------------------------------
     torch.manual_seed(11)
     lin = torch.nn.Linear(256, 384).double()
@@ -165,6 +196,12 @@ def main():
     torch.manual_seed(3); b = MyMona(768, 64)
     sa, sb = a.state_dict(), b.state_dict()
     assert list(sa.keys()) == list(sb.keys()) and all(torch.equal(sa[k], sb[k]) for k in sa), "Mona init stream differs"
+    from nextgen_uia_b200.adapters import mona as my_mona
+    for nm in ("NoiseAwareMona", "FreqEnhancedMona", "HybridNoiseFreqMona"):
+        torch.manual_seed(4); a = getattr(rmona, nm)(768, 64)
+        torch.manual_seed(4); b = getattr(my_mona, nm)(768, 64)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys()) and all(torch.equal(sa[k], sb[k]) for k in sa), nm + " init stream differs"
     torch.manual_seed(5); l0 = torch.nn.Linear(768, 2304); a = rlora.LinearLoRA(l0, r=8, lora_alpha=32, dropout_rate=0.1)
     torch.manual_seed(5); l1 = torch.nn.Linear(768, 2304); b = MyLoRA(l1, r=8, lora_alpha=32, dropout_rate=0.1)
     sa, sb = a.state_dict(), b.state_dict()

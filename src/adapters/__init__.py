@@ -6,6 +6,12 @@ version exports every adapter symbol that HAS an implementation in the reference
 from nextgen_uia_b200.adapters.mona import (  # noqa: F401
     BaselineMona,
     BaselineMonaOp,
+    NoiseAwareMona,
+    NoiseAwareMonaOp,
+    FreqEnhancedMona,
+    FreqEnhancedMonaOp,
+    HybridNoiseFreqMona,
+    HybridNoiseFreqMonaOp,
     BatchFirstMonaWrapper,
     inject_mona_variant_to_clip,
     inject_mona_variant_to_open_clip,
@@ -19,7 +25,8 @@ from nextgen_uia_b200.adapters.lora import (  # noqa: F401
 )
 
 __all__ = [
-    "BaselineMona", "BaselineMonaOp", "BatchFirstMonaWrapper",
+    "BaselineMona", "BaselineMonaOp", "NoiseAwareMona", "NoiseAwareMonaOp", "FreqEnhancedMona", "FreqEnhancedMonaOp",
+    "HybridNoiseFreqMona", "HybridNoiseFreqMonaOp", "BatchFirstMonaWrapper",
     "inject_mona_variant_to_clip", "inject_mona_variant_to_open_clip",
     "LoRALayer", "LinearLoRA", "PlainMultiheadAttentionLoRA",
     "inject_lora_to_clip", "inject_lora_to_biomedclip",

@@ -10,7 +10,7 @@ from conftest import relerr
 from oracle import functional as OF
 
 
-@pytest.mark.parametrize("name", ["mona_cls", "mona_nocls"])
+@pytest.mark.parametrize("name", ["mona_cls", "mona_nocls", "mona_noise", "mona_freq", "mona_hybrid"])
 def test_oracle_mona_matches_reference_golden(golden, name):
     g = golden(name)
     p = {k: v.double().requires_grad_(True) for k, v in g["state"].items()}

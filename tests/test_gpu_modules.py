@@ -13,14 +13,16 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.mark.parametrize("name", ["mona_cls", "mona_nocls"])
+@pytest.mark.parametrize("name", ["mona_cls", "mona_nocls", "mona_noise", "mona_freq", "mona_hybrid"])
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_mona_golden(golden, name, dtype):
-    """BatchFirstMonaWrapper(BaselineMona) forward + all grads vs the reference module's outputs."""
-    from src.adapters import BaselineMona, BatchFirstMonaWrapper
+    """BatchFirstMonaWrapper(<Mona variant>) forward + all grads vs the reference module's outputs."""
+    import src.adapters as A
+    from src.adapters import BatchFirstMonaWrapper
+    cls = {"mona_noise": A.NoiseAwareMona, "mona_freq": A.FreqEnhancedMona, "mona_hybrid": A.HybridNoiseFreqMona}.get(name, A.BaselineMona)
     g = golden(name)
     D = g["x"].shape[-1]
-    m = BatchFirstMonaWrapper(BaselineMona(D, 64))
+    m = BatchFirstMonaWrapper(cls(D, 64))
     m.load_state_dict(g["state"], strict=True)
     m = m.to(dev()).eval()
     x = g["x"].to(dev(), dtype).requires_grad_(True)

@@ -212,6 +212,24 @@ int ngu_colsum(const void* X, int ldx, float* out, int T, int C, int dtype, void
  * backward (same mask from the same seed). */
 int ngu_dropout(const void* x, void* out, int64_t n, float p, uint64_t seed, int accumulate, int dtype, void* stream);
 
+/*
+ * Fused optimiser step on flat fp32 buffers: clip_grad_norm_(max_norm) + AdamW + optional skip on a non-finite loss
+ * (src/models/biomedclip/finetune.py:244-255, :281-285, :296-303; torch.optim.AdamW semantics).
+ *   ngu_sqnorm : *out += sum x^2   (caller zeroes *out; feed the result to ngu_adamw_step.gsq)
+ */
+int ngu_sqnorm(const float* x, int64_t n, float* out, void* stream);
+typedef struct ngu_adamw_desc {
+  float* param; float* grad; float* m; float* v;
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay;
+  int step;                /* 1-based update count (bias correction) */
+  float max_norm;          /* <= 0 disables clipping */
+  const float* gsq;        /* device scalar: squared global grad norm (after the all-reduce), or NULL */
+  const float* loss;       /* device scalar: if non-finite the update is skipped, or NULL */
+  int zero_grad;           /* zero the gradient buffer after use */
+} ngu_adamw_desc;
+int ngu_adamw_step(const ngu_adamw_desc* d, void* stream);
+
 /* Patch-embed im2col (stride == kernel, timm PatchEmbed / CLIP conv1): images fp32 NCHW [B,3,R,R]
  * -> [B*(R/P)^2, 3*P*P]; and token assembly x0[b,0]=cls+pos[0], x0[b,1+p]=patch[b,p]+pos[1+p]. */
 int ngu_patchify(const float* img, void* out, int B, int R, int P, int dtype, void* stream);

@@ -92,6 +92,12 @@ class InfoNceDesc(ctypes.Structure):
                 ("Bg", _c_int), ("Bl", _c_int), ("r0", _c_int), ("E", _c_int), ("temperature", _c_float)]
 
 
+class AdamWDesc(ctypes.Structure):
+    _fields_ = [("param", _c_void_p), ("grad", _c_void_p), ("m", _c_void_p), ("v", _c_void_p), ("n", _i64),
+                ("lr", _c_float), ("beta1", _c_float), ("beta2", _c_float), ("eps", _c_float), ("weight_decay", _c_float),
+                ("step", _c_int), ("max_norm", _c_float), ("gsq", _c_void_p), ("loss", _c_void_p), ("zero_grad", _c_int)]
+
+
 # every symbol include/ngu_b200.h declares: name -> (restype, argtypes)
 def _P(t):
     return ctypes.POINTER(t)
@@ -116,6 +122,8 @@ PROTOTYPES = {
     "ngu_wgrad": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "ngu_colsum": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "ngu_dropout": (_c_int, [_c_void_p, _c_void_p, _i64, _c_float, _u64, _c_int, _c_int, _c_void_p]),
+    "ngu_sqnorm": (_c_int, [_c_void_p, _i64, _c_void_p, _c_void_p]),
+    "ngu_adamw_step": (_c_int, [_P(AdamWDesc), _c_void_p]),
     "ngu_patchify": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "ngu_assemble_tokens": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "ngu_embed_tokens": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),

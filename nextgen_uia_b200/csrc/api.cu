@@ -79,6 +79,8 @@ int ngu_colsum(const void* X, int ldx, float* out, int T, int C, int dtype, void
 int ngu_dropout(const void* x, void* out, int64_t n, float p, uint64_t seed, int accumulate, int dtype, void* stream) {
   return dropout(x, out, size_t(n), p, seed, accumulate, dtype, NGU_STREAM);
 }
+int ngu_sqnorm(const float* x, int64_t n, float* out, void* stream) { return sqnorm(x, size_t(n), out, NGU_STREAM); }
+int ngu_adamw_step(const ngu_adamw_desc* d, void* stream) { NGU_NONNULL(d, "ngu_adamw_step"); return adamw_step(*d, NGU_STREAM); }
 int ngu_patchify(const float* img, void* out, int B, int R, int P, int dtype, void* stream) {
   return patchify(img, out, B, R, P, dtype, NGU_STREAM);
 }

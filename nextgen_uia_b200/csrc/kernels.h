@@ -36,6 +36,9 @@ bool wgrad_tc_supported(int ldx, int ldy, int ldd, int Mo, int No, int dtype, co
 int wgrad_tc(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int T, int Mo, cudaStream_t s);
 int colsum(const void* X, int ldx, float* out, int Tn, int Cn, int dtype, cudaStream_t s);
 
+int sqnorm(const float* x, size_t n, float* out, cudaStream_t s);
+int adamw_step(const ngu_adamw_desc& d, cudaStream_t s);
+
 void count_launch(int n = 1);
 
 }  // namespace ngu

@@ -43,33 +43,47 @@ def setup_lora(model, r=16, alpha=32, dropout=0.1, num_layers=None):
 
 
 class GradBuckets:
-    """Flat fp32 gradient buckets (one per group of parameters) with async SUM all-reduce.
+    """One flat fp32 gradient buffer; each bucket (group of parameters, e.g. one transformer layer) is a contiguous
+    slice of it with an async SUM all-reduce.
 
-    Parameters' .grad tensors are views into the flat bucket, so the collective runs on one contiguous
-    buffer per bucket and the optimiser sees the reduced values without a copy."""
+    Parameters' .grad tensors are views into the flat buffer, so the collective runs on one contiguous slice per
+    bucket and the fused optimiser walks a single buffer.  With `flatten_params=True` the parameters' storage is
+    re-pointed into a matching flat fp32 buffer as well (values preserved)."""
 
-    def __init__(self, params, bucket_of, group=None):
+    enabled = True
+
+    def __init__(self, params, bucket_of, group=None, flatten_params=False):
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.buckets = {}
+        order = {}
         for p in params:
-            self.buckets.setdefault(bucket_of(p), []).append(p)
+            order.setdefault(bucket_of(p), []).append(p)
+        self.buckets = order
+        self.params = [p for ps in order.values() for p in ps]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_param = torch.empty(n, device=dev, dtype=torch.float32) if flatten_params else None
         self.flat = {}
         self.pending = {}
         self.works = []
         self.comm_stream = None
-        for key, ps in self.buckets.items():
-            n = sum(p.numel() for p in ps)
-            flat = torch.zeros(n, device=ps[0].device, dtype=torch.float32)
-            off = 0
+        off = 0
+        for key, ps in order.items():
+            start = off
             for p in ps:
-                p.grad = flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
-            self.flat[key] = flat
+                k = p.numel()
+                p.grad = self.flat_grad[off:off + k].view_as(p)
+                if flatten_params:
+                    with torch.no_grad():
+                        self.flat_param[off:off + k].copy_(p.detach().reshape(-1))
+                        p.data = self.flat_param[off:off + k].view_as(p)
+                off += k
+            self.flat[key] = self.flat_grad[start:off]
         if self.world > 1:
-            if params and params[0].is_cuda:
+            if self.params and self.params[0].is_cuda:
                 self.comm_stream = torch.cuda.Stream()
-            for key, ps in self.buckets.items():
+            for key, ps in order.items():
                 for p in ps:
                     p.register_post_accumulate_grad_hook(self._make_hook(key, len(ps)))
 
@@ -95,8 +109,6 @@ class GradBuckets:
             self.comm_stream.wait_event(ev)
             self.works.append(dist.all_reduce(self.flat[key], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
-    enabled = True
-
     def wait(self):
         for w in self.works:
             w.wait()
@@ -105,15 +117,50 @@ class GradBuckets:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def zero(self):
-        for f in self.flat.values():
-            f.zero_()
+        self.flat_grad.zero_()
+
+
+def cosine_lr(base_lr, eta_min, t, t_max):
+    """closed form of torch.optim.lr_scheduler.CosineAnnealingLR after t scheduler steps (finetune.py:255)."""
+    return eta_min + (base_lr - eta_min) * (1.0 + math.cos(math.pi * t / t_max)) / 2.0
+
+
+class FusedAdamW:
+    """clip_grad_norm_ + AdamW + cosine LR + zero_grad in two kernel launches over the flat buffers
+    (finetune.py:244-255, :296-303).  State (exp_avg, exp_avg_sq) is flat fp32 like the parameters."""
+
+    def __init__(self, buckets, lr, betas, eps, weight_decay, grad_clip, total_updates, lr_min):
+        assert buckets.flat_param is not None, "FusedAdamW needs GradBuckets(flatten_params=True)"
+        self.b = buckets
+        self.base_lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.grad_clip, self.t_max, self.lr_min = grad_clip, total_updates, lr_min
+        self.m = torch.zeros_like(buckets.flat_param)
+        self.v = torch.zeros_like(buckets.flat_param)
+        self.gsq = torch.zeros(1, device=buckets.flat_param.device, dtype=torch.float32)
+        self.updates = 0
+
+    @property
+    def lr(self):
+        return cosine_lr(self.base_lr, self.lr_min, self.updates, self.t_max)
+
+    def step(self, loss=None):
+        from . import ops
+        lr = self.lr
+        self.updates += 1
+        gsq = None
+        if self.grad_clip and self.grad_clip > 0:
+            self.gsq.zero_()
+            ops.sqnorm(self.b.flat_grad, self.gsq)
+            gsq = self.gsq
+        ops.adamw_step(self.b.flat_param, self.b.flat_grad, self.m, self.v, lr=lr, betas=self.betas, eps=self.eps,
+                       weight_decay=self.wd, step=self.updates, max_norm=self.grad_clip or 0.0, gsq=gsq, loss=loss, zero_grad=True)
 
 
 class Trainer:
     """The training micro-step of finetune.py:272-303 on the B200 path, data-parallel when torch.distributed is up."""
 
     def __init__(self, model, temperature=0.07, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.01, grad_clip=1.0,
-                 accumulation_steps=1, total_updates=1000, lr_min=1e-8):
+                 accumulation_steps=1, total_updates=1000, lr_min=1e-8, fused_optimizer=True):
         from .losses import InfoNCELoss
         self.model = model
         self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
@@ -128,12 +175,18 @@ class Trainer:
                     return int(parts[i + 1])
             return -1
 
-        self.buckets = GradBuckets(self.params, bucket_of)
-        self.optimizer = torch.optim.AdamW(self.params, lr=lr, betas=betas, weight_decay=weight_decay, fused=True)
-        self.scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizer, T_max=total_updates, eta_min=lr_min)
+        on_gpu = bool(self.params) and self.params[0].is_cuda
+        self.fused = fused_optimizer and on_gpu
+        self.buckets = GradBuckets(self.params, bucket_of, flatten_params=self.fused)
         self.grad_clip = grad_clip
         self.accum = accumulation_steps
         self.micro = 0
+        if self.fused:
+            self.optimizer = FusedAdamW(self.buckets, lr, betas, 1e-8, weight_decay, grad_clip, total_updates, lr_min)
+            self.scheduler = None
+        else:
+            self.optimizer = torch.optim.AdamW(self.params, lr=lr, betas=betas, weight_decay=weight_decay)
+            self.scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(self.optimizer, T_max=total_updates, eta_min=lr_min)
 
     def micro_step(self, images, ids):
         """One micro-batch: encode, loss, backward (+ optimizer update at accumulation boundaries).
@@ -148,9 +201,14 @@ class Trainer:
         self.micro += 1
         if last:
             self.buckets.wait()
-            if self.grad_clip and self.grad_clip > 0:
-                torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip, foreach=True)
-            self.optimizer.step()
-            self.scheduler.step()
-            self.buckets.zero()
+            if self.fused:
+                # global-norm clip + AdamW + cosine LR + zero_grad on device; a non-finite loss skips the update
+                # (the reference's `if not torch.isfinite(loss): continue`, finetune.py:281-285, without the host sync)
+                self.optimizer.step(loss=loss.detach().float().view(1))
+            else:
+                if self.grad_clip and self.grad_clip > 0:
+                    torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip)
+                self.optimizer.step()
+                self.scheduler.step()
+                self.buckets.zero()
         return loss.detach()

@@ -334,3 +334,22 @@ def infonce_normalize_bwd(dxhat, xhat, norm, gscale, dtype):
     L.check(L.lib().ngu_infonce_normalize_bwd(dxhat.data_ptr(), xhat.data_ptr(), norm.data_ptr(), _p(gscale), dx.data_ptr(), B, E,
                                               _dt(dx), _stream()), "ngu_infonce_normalize_bwd")
     return dx
+
+
+def sqnorm(x, out):
+    """out[0] += sum(x^2) for a flat fp32 buffer."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.float32
+    L.check(L.lib().ngu_sqnorm(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "ngu_sqnorm")
+
+
+def adamw_step(param, grad, m, v, *, lr, betas, eps, weight_decay, step, max_norm=0.0, gsq=None, loss=None, zero_grad=True):
+    _need_cuda(param)
+    for t in (param, grad, m, v):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
+    d = L.AdamWDesc()
+    d.param, d.grad, d.m, d.v, d.n = param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel()
+    d.lr, d.beta1, d.beta2, d.eps, d.weight_decay = float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay)
+    d.step, d.max_norm = int(step), float(max_norm)
+    d.gsq, d.loss, d.zero_grad = _p(gsq), _p(loss), int(zero_grad)
+    L.check(L.lib().ngu_adamw_step(_byref(d), _stream()), "ngu_adamw_step")

@@ -162,3 +162,34 @@ def test_infonce_golden(golden, name, dtype):
     if dtype == torch.float32:
         assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-4
         assert relerr(I.grad, g["dI"]) < 1e-4 and relerr(T.grad, g["dT"]) < 1e-4
+
+
+def test_fused_adamw_matches_torch():
+    """clip_grad_norm_(1.0) + torch.optim.AdamW(betas=(0.9,0.95), wd=0.01) + CosineAnnealingLR, 5 updates."""
+    from nextgen_uia_b200 import dp
+    torch.manual_seed(0)
+    shapes = [(64, 768), (768,), (64, 1, 7, 7), (3, 16, 1, 1)]
+    ref = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone().to(dev())) for p in ref]
+    opt = torch.optim.AdamW(ref, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.01)
+    sch = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=20, eta_min=1e-8)
+    gb = dp.GradBuckets(mine, lambda p: 0, flatten_params=True)
+    fo = dp.FusedAdamW(gb, 1e-3, (0.9, 0.95), 1e-8, 0.01, 1.0, 20, 1e-8)
+    for it in range(5):
+        gs = [torch.randn(s) * (3.0 if it % 2 == 0 else 0.01) for s in shapes]   # alternately clipped / not clipped
+        for p, g_ in zip(ref, gs):
+            p.grad = g_.clone()
+        for p, g_ in zip(mine, gs):
+            p.grad.copy_(g_.to(dev()))
+        torch.nn.utils.clip_grad_norm_(ref, max_norm=1.0)
+        opt.step(); sch.step()
+        fo.step()
+        for a, b in zip(mine, ref):
+            assert relerr(a, b) < 1e-5
+        assert float(gb.flat_grad.abs().sum()) == 0.0
+    # non-finite loss: update skipped, grads still zeroed
+    before = [p.detach().clone() for p in mine]
+    for p in mine:
+        p.grad.fill_(1.0)
+    fo.step(loss=torch.full((1,), float("nan"), device=dev()))
+    assert all(torch.equal(a, b) for a, b in zip(mine, before)) and float(gb.flat_grad.abs().sum()) == 0.0

@@ -35,7 +35,7 @@ class MonaFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, norm_w, norm_b, gamma, gammax, w1, b1, k3, b3, k5, b5, k7, b7, pw, pb, w2, b2,
-                freq, ne_w1, ne_b1, ne_w2, ne_b2, hw, has_cls, drop_p, seed):
+                freq, ne_w1, ne_b1, ne_w2, ne_b2, hw, has_cls, drop_p, seed, owner=None):
         B, N, D = x.shape
         C = w1.shape[0]
         x2 = x.contiguous().view(B * N, D)
@@ -48,6 +48,7 @@ class MonaFunction(torch.autograd.Function):
         ctx.save_for_backward(x2, mean, rstd, u, h, g, norm_w, norm_b, gamma, gammax, w1, k3, b3, k5, b5, k7, b7, pw, pb, w2,
                               *[t for t in (freq, ne_w1, ne_b1, ne_w2, ne_b2) if t is not None])
         ctx.variant = (freq is not None, ne_w1 is not None)
+        ctx.owner = owner
         ctx.meta = (B, N, D, C, hw, has_cls, drop_p, seed)
         return y.view(B, N, D)
 
@@ -62,27 +63,60 @@ class MonaFunction(torch.autograd.Function):
         B, N, D, C, hw, has_cls, drop_p, seed = ctx.meta
         dev, dt = x2.device, x2.dtype
         dy2 = dy.contiguous().view(B * N, D)
-        z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+        # Gradient sink: when the trainer has pre-allocated flat fp32 .grad buffers for this adapter's parameters
+        # (dp.GradBuckets), the kernels accumulate straight into them (they all accumulate with += / atomics) and
+        # autograd gets None -> no per-parameter zero-fill and add kernels.
+        owner = ctx.owner
+        sink = None
+        if owner is not None:
+            ps = list(owner.parameters())
+            if ps and all(getattr(p, "_ngu_sink", None) is not None and p.grad is not None for p in ps):
+                sink = ps[0]._ngu_sink
+        c = owner.adapter_conv if owner is not None else None
+
+        def buf(param_attr, shape):
+            if sink is not None:
+                return param_attr.grad
+            return torch.zeros(*shape, device=dev, dtype=torch.float32)
+
         # project2:  y = x + g W2^T + b2
         dg = ops.gemm(dy2, ops.cast(w2, dt, transpose=True))                          # [M, C] = dy W2
         g2 = g.view(B * N, C)
-        dw2 = ops.wgrad(dy2, g2)                                                      # [D, C]
+        dw2 = buf(owner.project2.weight if sink else None, (D, C))
+        ops.wgrad(dy2, g2, out=dw2)                                                   # [D, C]
         # conv stage (recomputes z / a from h), also yields d project1.bias
-        dk3, db3, dk5, db5, dk7, db7 = z(*k3.shape), z(C), z(*k5.shape), z(C), z(*k7.shape), z(C)
-        dpw, dpb, db1 = z(*pw.shape), z(C), z(C)
-        dfreq = z(C) if has_freq else None
-        dn = [z(*t.shape) for t in (ne_w1, ne_b1, ne_w2, ne_b2)] if has_noise else [None] * 4
+        if sink is not None:
+            dk3, db3, dk5, db5, dk7, db7 = (c.conv1.weight.grad, c.conv1.bias.grad, c.conv2.weight.grad, c.conv2.bias.grad,
+                                            c.conv3.weight.grad, c.conv3.bias.grad)
+            dpw, dpb, db1 = c.projector.weight.grad, c.projector.bias.grad, owner.project1.bias.grad
+            vt = c.variant_tensors()
+            dfreq = vt[0].grad if has_freq else None
+            dn = [t.grad for t in vt[1:]] if has_noise else [None] * 4
+        else:
+            z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+            dk3, db3, dk5, db5, dk7, db7 = z(*k3.shape), z(C), z(*k5.shape), z(C), z(*k7.shape), z(C)
+            dpw, dpb, db1 = z(*pw.shape), z(C), z(C)
+            dfreq = z(C) if has_freq else None
+            dn = [z(*t.shape) for t in (ne_w1, ne_b1, ne_w2, ne_b2)] if has_noise else [None] * 4
         dh = ops.mona_conv_bwd(h.view(B, N, C), dg.view(B, N, C), (k3, b3, k5, b5, k7, b7, pw, pb, freq, ne_w1, ne_b1, ne_w2, ne_b2),
                                (dk3, db3, dk5, db5, dk7, db7, dpw, dpb, db1, dfreq, *dn), hw, has_cls, drop_p, seed)
         dh2 = dh.view(B * N, C)
         # project1:  h = u W1^T + b1
-        dw1 = ops.wgrad(u, dh2).t().contiguous()                                      # [C, D]
+        dw1t = ops.wgrad(u, dh2)                                                      # [D, C] = dW1^T
         du = ops.gemm(dh2, ops.cast(w1, dt, transpose=True))                          # [M, D] = dh W1
         # LN mix + residual
-        dnw, dnb, dgam, dgamx, db2 = z(D), z(D), z(D), z(D), z(D)
+        if sink is not None:
+            dnw, dnb, dgam, dgamx, db2 = owner.norm.weight.grad, owner.norm.bias.grad, owner.gamma.grad, owner.gammax.grad, owner.project2.bias.grad
+        else:
+            dnw, dnb, dgam, dgamx, db2 = (torch.zeros(D, device=dev, dtype=torch.float32) for _ in range(5))
         dx = ops.mona_pre_bwd(du, dy2, x2, mean, rstd, norm_w, norm_b, gamma, gammax, dnw, dnb, dgam, dgamx, db2)
-        return (dx.view(B, N, D), dnw, dnb, dgam, dgamx, dw1, db1, dk3, db3, dk5, db5, dk7, db7, dpw, dpb, dw2, db2,
-                dfreq, dn[0], dn[1], dn[2], dn[3], None, None, None, None)
+        if sink is not None:
+            owner.project1.weight.grad.add_(dw1t.t())
+            buckets, key, count = sink
+            buckets.notify(key, count)
+            return (dx.view(B, N, D),) + (None,) * 26
+        return (dx.view(B, N, D), dnw, dnb, dgam, dgamx, dw1t.t().contiguous(), db1, dk3, db3, dk5, db5, dk7, db7, dpw, dpb, dw2, db2,
+                dfreq, dn[0], dn[1], dn[2], dn[3], None, None, None, None, None)
 
 
 class _MonaOpBase(nn.Module):
@@ -183,7 +217,7 @@ class BaselineMona(nn.Module):
                                   c.conv1.weight, c.conv1.bias, c.conv2.weight, c.conv2.bias, c.conv3.weight, c.conv3.bias,
                                   c.projector.weight, c.projector.bias,
                                   self.project2.weight, self.project2.bias,
-                                  freq, ne_w1, ne_b1, ne_w2, ne_b2, hw, has_cls, p, seed)
+                                  freq, ne_w1, ne_b1, ne_w2, ne_b2, hw, has_cls, p, seed, self)
 
     def forward(self, x, hw_shapes=None):
         return self.forward_batch_first(x.permute(1, 0, 2), hw_shapes).permute(1, 0, 2)

@@ -66,6 +66,7 @@ class GradBuckets:
         self.flat_param = torch.empty(n, device=dev, dtype=torch.float32) if flatten_params else None
         self.flat = {}
         self.pending = {}
+        self.launched = set()
         self.works = []
         self.comm_stream = None
         off = 0
@@ -80,6 +81,7 @@ class GradBuckets:
                         p.data = self.flat_param[off:off + k].view_as(p)
                 off += k
             self.flat[key] = self.flat_grad[start:off]
+        self._mark_sinks()
         if self.world > 1:
             if self.params and self.params[0].is_cuda:
                 self.comm_stream = torch.cuda.Stream()
@@ -87,8 +89,33 @@ class GradBuckets:
                 for p in ps:
                     p.register_post_accumulate_grad_hook(self._make_hook(key, len(ps)))
 
+    def _mark_sinks(self):
+        """Adapters whose parameters all sit in ONE bucket may accumulate their gradients straight into the flat buffer
+        from their own backward (adapters/mona.py MonaFunction) and then call notify() instead of the autograd hooks."""
+        for key, ps in self.buckets.items():
+            owners = {}
+            for p in ps:
+                owners.setdefault(getattr(p, "_ngu_owner", None), []).append(p)
+            for owner, ops_ in owners.items():
+                if owner is not None:
+                    for p in ops_:
+                        p._ngu_sink = (self, key, len(ops_))
+
+    def notify(self, key, count):
+        """`count` parameters of bucket `key` have their gradients accumulated (called from a fused backward)."""
+        total = len(self.buckets[key])
+        c = self.pending.get(key, 0) + count
+        if c >= total:
+            self.pending[key] = 0
+            if self.world > 1:
+                self._launch(key)
+        else:
+            self.pending[key] = c
+
     def _make_hook(self, key, count):
         def hook(_p):
+            if getattr(_p, "_ngu_sink", None) is not None:
+                return  # this parameter's gradient is accumulated by its adapter's own backward (notify())
             c = self.pending.get(key, 0) + 1
             if c == count:
                 self.pending[key] = 0
@@ -98,8 +125,9 @@ class GradBuckets:
         return hook
 
     def _launch(self, key):
-        if not self.enabled:
+        if not self.enabled or key in self.launched:
             return
+        self.launched.add(key)
         if self.comm_stream is None:  # CPU tensors (gloo): no stream juggling
             self.works.append(dist.all_reduce(self.flat[key], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
             return
@@ -113,6 +141,7 @@ class GradBuckets:
         for w in self.works:
             w.wait()
         self.works = []
+        self.launched.clear()
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
@@ -177,6 +206,12 @@ class Trainer:
 
         on_gpu = bool(self.params) and self.params[0].is_cuda
         self.fused = fused_optimizer and on_gpu
+        if on_gpu:
+            from .adapters.mona import BaselineMona
+            for mod in model.modules():  # let Mona adapters write their gradients straight into the flat buffer
+                if isinstance(mod, BaselineMona) and all(p.requires_grad for p in mod.parameters()):
+                    for p in mod.parameters():
+                        p._ngu_owner = mod
         self.buckets = GradBuckets(self.params, bucket_of, flatten_params=self.fused)
         self.grad_clip = grad_clip
         self.accum = accumulation_steps

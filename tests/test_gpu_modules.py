@@ -253,3 +253,17 @@ def test_openai_clip_golden(golden, tag, dtype):
             if dtype == torch.float32:
                 assert relerr(p.grad, g["grads"][n]) < 1e-3, n
     assert (num / den) ** 0.5 < (3e-2 if dtype == torch.bfloat16 else 1e-3)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_data_parallel_two_gpus(mode):
+    """SURVEY.md §8e on real GPUs: 2 ranks (NCCL), all-gathered features -> global loss == single-process oracle on the
+    concatenated batch, SUM-all-reduced adapter gradients == oracle gradients.  Skipped on a 1-GPU box."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = str(29600 + os.getpid() % 300)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", port, os.path.join(root, "tools", "dp_check.py"), mode], capture_output=True, text=True, timeout=300)
+    assert "DP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

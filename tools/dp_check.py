@@ -51,5 +51,8 @@ if rank == 0:
             if e > worst[1]: worst = (n, e)
     print(f"[{dtype}] world={world} global loss {float(loss):.6f} vs oracle {float(lo):.6f} rel {abs(float(loss)-float(lo))/float(lo):.2e}; "
           f"grad L2 relerr {(num/den)**0.5:.3e}; worst tensor {worst}")
+    tol_l, tol_g = (1e-5, 1e-3) if dtype == torch.float32 else (1e-2, 0.15)
+    ok = abs(float(loss) - float(lo)) / float(lo) < tol_l and (num / den) ** 0.5 < tol_g
+    print("DP_CHECK_OK" if ok else "DP_CHECK_FAIL", flush=True)
 dist.barrier()
 dist.destroy_process_group()

@@ -29,7 +29,7 @@ FLOP_PER_IMAGE_MONA = 83.2e9  # vision fwd+bwd (frozen-weight 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU (configs[1]: 256)")
@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -257,6 +257,7 @@ def main():
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMA GEMM, all launches of one step)", "achieved": ach, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "traffic_note": "aggregate over shapes; per-shape DRAM bytes (QKV launch: 81 MB read + 180 MB write vs 313 MB algorithmic) in profiles/r1_gemm_qkv_ncu_full_summary.txt",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "gemm_ms_per_step": t_ms, "gemm_share_of_step": t_ms / (ms / args.steps), "gemm_launches_per_step": len(recs),
                 "step_tflops_algorithmic": FLOP_PER_IMAGE_MONA * B / (ms / args.steps * 1e-3) / 1e12}

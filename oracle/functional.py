@@ -136,7 +136,7 @@ def clip_block(x, p, prefix, heads, causal=False, lora=None):
     return x + F.linear(h, p[f"{prefix}mlp.c_proj.weight"], p[f"{prefix}mlp.c_proj.bias"])
 
 
-def clip_encode_image(p, images, cfg):
+def clip_encode_image(p, images, cfg, taps=None, tap_layers=()):
     """VisionTransformer.forward, model.py:233-257, with Mona after each block when injected (mona.py:563-571:
     adapter gets [N,B,D] and (grid, grid))."""
     v = "visual."
@@ -151,6 +151,8 @@ def clip_encode_image(p, images, cfg):
         mp = f"{v}transformer.resblocks.{i}.mona."
         if f"{mp}gamma" in p:
             x = mona(x, p, mp, (gh, gw), True)
+        if taps is not None and i in tap_layers:     # clipseg_adapter.py:60-68 (hidden states after listed blocks, NLD)
+            taps.append(x)
     x = F.layer_norm(x[:, 0], (D,), p[f"{v}ln_post.weight"], p[f"{v}ln_post.bias"], 1e-5)
     return x @ p[f"{v}proj"]
 

@@ -267,3 +267,59 @@ def test_data_parallel_two_gpus(mode):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", port, os.path.join(root, "tools", "dp_check.py"), mode], capture_output=True, text=True, timeout=300)
     assert "DP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_clipseg_adapter_vs_oracle(dtype):
+    """Config-5 family: CLIP ViT encoder (kernels) with Mona re-enabled after the backbone freeze, hidden-state taps,
+    causal text conditioning, HF CLIPSegDecoder (PyTorch).  Logits and the gradients of decoder + Mona parameters vs the
+    CPU oracle (oracle towers + the same decoder weights on CPU)."""
+    import copy
+    from transformers import CLIPSegConfig
+    from transformers.models.clipseg.modeling_clipseg import CLIPSegDecoder
+    from nextgen_uia_b200.openai_clip import CLIP
+    from nextgen_uia_b200.clipseg_adapter import CLIPSegAdapter
+    from src.adapters import inject_mona_variant_to_clip
+    from oracle import functional as OF
+    torch.manual_seed(0)
+    cfg = CLIPSegConfig(extract_layers=[0, 1, 2], reduce_dim=32, decoder_num_attention_heads=2, decoder_intermediate_size=64,
+                        projection_dim=64, vision_config=dict(hidden_size=256, image_size=64, patch_size=16))
+    dec = CLIPSegDecoder(cfg).float()
+    clip = CLIP(64, 64, 3, 256, 16, 8, 50, 64, 1, 1)
+    inject_mona_variant_to_clip(clip, variant="baseline", bottleneck_dim=64)
+    with torch.no_grad():
+        for n, p in clip.named_parameters():
+            if n.endswith("gamma"):
+                p.copy_(torch.randn(p.shape) * 0.2)
+    model = CLIPSegAdapter(clip, decoder=dec)
+    model.freeze_clip_backbone()
+    assert model.unfreeze_adapters() == 3 * 16
+    sd = {k: v.detach().double() if v.is_floating_point() else v for k, v in clip.state_dict().items()}
+    dec64 = copy.deepcopy(dec).double()
+    images = torch.rand(2, 3, 64, 64)
+    ids = torch.randint(1, 48, (2, 8)); ids[:, -1] = 49
+    gl = torch.randn(2, 2, 64, 64)
+    # oracle
+    trainable = [n for n, p in clip.named_parameters() if p.requires_grad]
+    p64 = {k: (v.clone().requires_grad_(k in trainable) if v.is_floating_point() else v) for k, v in sd.items()}
+    taps = []
+    ocfg = dict(patch=16, depth=3, heads=4, text_layers=1, text_heads=1)
+    OF.clip_encode_image(p64, images.double(), ocfg, taps=taps, tap_layers=(0, 1, 2))
+    cond = OF.clip_encode_text(p64, ids, ocfg).detach()
+    lo = dec64(hidden_states=tuple(taps), conditional_embeddings=cond)[0].view(2, -1, 64, 64)
+    lo = torch.cat([-lo, lo], 1)
+    go = torch.autograd.grad((lo * gl.double()).sum(), [p64[n] for n in trainable] + list(dec64.parameters()))
+    # kernels
+    model = model.to(dev()).eval()
+    clip.set_compute_dtype(dtype)
+    logits = model(images.to(dev()), input_ids=ids.to(dev()))
+    (logits.float() * gl.to(dev())).sum().backward()
+    tol = 5e-2 if dtype == torch.bfloat16 else 1e-3
+    assert logits.shape == (2, 2, 64, 64) and relerr(logits, lo) < tol
+    num = den = 0.0
+    got = [dict(clip.named_parameters())[n].grad for n in trainable] + [p.grad for p in model.decoder.parameters()]
+    for a, b in zip(got, go):
+        assert a is not None
+        d = a.double().cpu() - b
+        num += float((d * d).sum()); den += float((b * b).sum())
+    assert (num / den) ** 0.5 < (8e-2 if dtype == torch.bfloat16 else 1e-3)

@@ -157,6 +157,48 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def block_microbench(dev, B, iters=10):
+    """One ViT-B/16 encoder block with the Mona adapter and LoRA (r=8) on qkv/proj, forward + backward."""
+    from nextgen_uia_b200.vit import Block
+    from nextgen_uia_b200.adapters.mona import BaselineMona, BatchFirstMonaWrapper
+    from nextgen_uia_b200.adapters.lora import LinearLoRA
+    torch.manual_seed(3)
+    blk = Block(768, 12)
+    for p in blk.parameters():
+        p.requires_grad = False
+    blk.attn.qkv = LinearLoRA(blk.attn.qkv, r=8, lora_alpha=32, dropout_rate=0.0)
+    blk.attn.proj = LinearLoRA(blk.attn.proj, r=8, lora_alpha=32, dropout_rate=0.0)
+    mona = BatchFirstMonaWrapper(BaselineMona(768, 64))
+    blk, mona = blk.to(dev), mona.to(dev).eval()
+    x = (torch.randn(B, 197, 768, device=dev) * 0.5).bfloat16().requires_grad_(True)
+    g = torch.randn(B, 197, 768, device=dev).bfloat16()
+
+    def step():
+        y = mona(blk(x), (14, 14))
+        y.backward(g)
+        x.grad = None
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf = 6.10e9 * B / (ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    return {"what": "ViT-B/16 block + Mona + LoRA(r=8,qkv+proj) fwd+bwd, [B,197,768] bf16, 6.10 GFLOP/image algorithmic",
+            "ms": ms, "tflops": tf, "frac_of_measured_sustained_peak": tf / peak, "frac_of_nominal_2250": tf / 2250.0}
+
+
 # -------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -262,6 +304,12 @@ def main():
                 "gemm_ms_per_step": t_ms, "gemm_share_of_step": t_ms / (ms / args.steps), "gemm_launches_per_step": len(recs),
                 "step_tflops_algorithmic": FLOP_PER_IMAGE_MONA * B / (ms / args.steps * 1e-3) / 1e12}
 
+    # ---- block-level figure the north_star target is stated on: one ViT-B/16 block + Mona + LoRA(r=8, qkv+proj), fwd+bwd,
+    #      on [B,197,768] bf16; algorithmic 6.10 GFLOP per image
+    block = None
+    if rank == 0:
+        block = block_microbench(dev, B)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, sec, cores = cpu_reference_rate(3, 1, args.cpu_batch, args.depth)
@@ -282,6 +330,7 @@ def main():
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "block": block,
             "loss_last": losses[-1] if losses else None,
         }
         print(json.dumps(line), flush=True)

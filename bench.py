@@ -157,7 +157,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def block_microbench(dev, B, iters=10):
+def block_microbench(dev, B, iters=10, profile=False):
     """One ViT-B/16 encoder block with the Mona adapter and LoRA (r=8) on qkv/proj, forward + backward."""
     from nextgen_uia_b200.vit import Block
     from nextgen_uia_b200.adapters.mona import BaselineMona, BatchFirstMonaWrapper
@@ -182,11 +182,15 @@ def block_microbench(dev, B, iters=10):
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if profile:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for _ in range(iters):
         step()
     e1.record()
     torch.cuda.synchronize()
+    if profile:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1) / iters
     tf = 6.10e9 * B / (ms * 1e-3) / 1e12
     peaks = {}

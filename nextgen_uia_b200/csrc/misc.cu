@@ -109,15 +109,42 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const T* __restrict__ X
     }
 }
 
-// column sums of a [T, C] activation into fp32 (bias gradients)
+// column sums of a [T, C] activation into fp32 (bias gradients): CTA = 8 warps over a 32-vector-wide column tile,
+// each warp walks rows with 16-byte loads, cross-warp reduce in smem, one atomic per column per CTA.
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ X, int ldx, float* __restrict__ out, int Tn, int Cn, int tchunk) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Cn) return;
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, int ldx, float* __restrict__ out, int Tn, int Cn, int tchunk) {
+  constexpr int V = Vec<T>::N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = (blockIdx.x * 32 + lane) * V;
   const int t0 = blockIdx.y * tchunk, t1 = min(Tn, t0 + tchunk);
-  float s = 0.f;
-  for (int t = t0; t < t1; ++t) s += to_f32<T>(X[size_t(t) * ldx + c]);
-  atomicAdd(out + c, s);
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  if (c0 + V <= Cn) {
+    for (int t = t0 + warp; t < t1; t += 8) {
+      float v[V];
+      Vec<T>::load(X + size_t(t) * ldx + c0, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += v[i];
+    }
+  } else {
+    for (int t = t0 + warp; t < t1; t += 8)
+      for (int i = 0; i < V; ++i)
+        if (c0 + i < Cn) acc[i] += to_f32<T>(X[size_t(t) * ldx + c0 + i]);
+  }
+  __shared__ float red[8][32 * V + 1];
+#pragma unroll
+  for (int i = 0; i < V; ++i) red[warp][lane * V + i] = acc[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < 32 * V; j += 256) {
+    const int c = blockIdx.x * 32 * V + j;
+    if (c < Cn) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][j];
+      atomicAdd(out + c, s);
+    }
+  }
 }
 
 // out = (accumulate ? out : 0) + x * mask(seed, i) / (1-p)   (LoRA input dropout, src/adapters/lora.py:82-83)
@@ -188,12 +215,17 @@ int wgrad_simt(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd
 }
 int colsum(const void* X, int ldx, float* out, int Tn, int Cn, int dtype, cudaStream_t st) {
   if (Tn <= 0 || Cn <= 0) { set_last_error("colsum: empty"); return NGU_ERR_SHAPE; }
-  int splits = (Tn + 255) / 256;
-  if (splits > 1024) splits = 1024;
+  const int V = dtype == NGU_F32 ? 4 : 8;
+  if ((ldx % V) || (reinterpret_cast<uintptr_t>(X) & 15)) { set_last_error("colsum: rows must be 16-byte aligned"); return NGU_ERR_ALIGN; }
+  const int ctile = 32 * V;
+  const int gx = (Cn + ctile - 1) / ctile;
+  int splits = (sm_count() * 4 + gx - 1) / gx;
+  if (splits > (Tn + 63) / 64) splits = (Tn + 63) / 64;
+  if (splits < 1) splits = 1;
   const int tchunk = (Tn + splits - 1) / splits;
-  dim3 grid((Cn + 127) / 128, (Tn + tchunk - 1) / tchunk);
-  if (dtype == NGU_F32) colsum_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(X), ldx, out, Tn, Cn, tchunk);
-  else colsum_kernel<bf16><<<grid, 128, 0, st>>>(reinterpret_cast<const bf16*>(X), ldx, out, Tn, Cn, tchunk);
+  dim3 grid(gx, (Tn + tchunk - 1) / tchunk);
+  if (dtype == NGU_F32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(X), ldx, out, Tn, Cn, tchunk);
+  else colsum_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(X), ldx, out, Tn, Cn, tchunk);
   return check_launch("colsum");
 }
 

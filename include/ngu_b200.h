@@ -151,8 +151,9 @@ typedef struct ngu_mona_conv_desc {
   ngu_mona_conv_weights w;
   ngu_mona_conv_grads gr;
   int B, N, H, W, C, has_cls;
-  float drop_p; uint64_t seed;     /* dropout p (0 = eval) and Philox seed; backward regenerates the mask */
+  float drop_p; uint64_t seed;     /* dropout p (0 = eval) and counter-RNG seed; backward regenerates the mask */
   int dtype;
+  int force_simt;                  /* tests: run the bf16 stage on CUDA cores instead of mma.sync */
 } ngu_mona_conv_desc;
 int ngu_mona_conv_fwd(const ngu_mona_conv_desc* d, void* stream);
 int ngu_mona_conv_bwd(const ngu_mona_conv_desc* d, void* stream);

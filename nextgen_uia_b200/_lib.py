@@ -72,7 +72,7 @@ class MonaConvDesc(ctypes.Structure):
     _fields_ = [("h", _c_void_p), ("g", _c_void_p), ("dg", _c_void_p), ("dh", _c_void_p),
                 ("w", MonaConvWeights), ("gr", MonaConvGrads),
                 ("B", _c_int), ("N", _c_int), ("H", _c_int), ("W", _c_int), ("C", _c_int), ("has_cls", _c_int),
-                ("drop_p", _c_float), ("seed", _u64), ("dtype", _c_int)]
+                ("drop_p", _c_float), ("seed", _u64), ("dtype", _c_int), ("force_simt", _c_int)]
 
 
 class AttnDesc(ctypes.Structure):

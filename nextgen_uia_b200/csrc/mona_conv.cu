@@ -653,6 +653,478 @@ mona_conv_bwd_fast_kernel(const T* __restrict__ h, const T* __restrict__ dg, T* 
   atomicAdd(gr.db1 + c, db1_acc);
 }
 
+// =====================================================================================================
+// bf16 product path: same algorithm, with the three projector contractions (z P^T, da^T z, da P) on the tensor
+// cores (mma.sync m16n8k16, bf16 in / fp32 accumulate, operands via ldmatrix from 128-byte-swizzled smem tiles).
+// The depthwise stencil and its correlation sums stay on CUDA cores (no contraction over channels to exploit).
+// Tiles hs / zs / das are [HWp][64] bf16 with HWp = HW rounded up to 16 (pad rows zero); element (p, c) lives at
+// p*64 + (((c >> 3) ^ (p & 7)) << 3) + (c & 7)   (16-byte chunks XOR-swizzled by the row, so ldmatrix is conflict free).
+// =====================================================================================================
+NGU_DEVINL int swz(int p, int c) { return p * C + ((((c >> 3) ^ (p & 7))) << 3) + (c & 7); }
+NGU_DEVINL uint32_t tile_addr(uint32_t base, int row, int chunk) { return base + uint32_t(row) * 128u + (uint32_t((chunk ^ (row & 7))) << 4); }
+NGU_DEVINL void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+NGU_DEVINL void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+NGU_DEVINL void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct TcSmem {
+  float kc[49][C];
+  float bc[C];
+  float bp[C];
+  float fr[C];
+  float hm[C];
+  float part[4][C];
+  float hid[CH];
+  float wbr[4];
+  float dwbr[4];
+  float dgap[C];
+};
+
+// acc[nt][.] (16 rows x 64 cols) = A[rt*16 .. +16][0..64) * Bm, A from a swizzled tile; Bm(k, n) = Pb[n][k] (TRANS_B = false,
+// i.e. A P^T) or Pb[k][n] (TRANS_B = true, i.e. A P), Pb = projector weight [o][i] as a swizzled bf16 tile.
+template <bool TRANS_B>
+NGU_DEVINL void proj_mma(float (&acc)[8][4], uint32_t tileA, int rt, uint32_t pb, int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4];
+    ldsm_x4(a, tile_addr(tileA, rt * 16 + (lane & 15), kk * 2 + (lane >> 4)));
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      if (!TRANS_B) ldsm_x4(b, tile_addr(pb, (2 * np + (lane >> 4)) * 8 + (lane & 7), kk * 2 + ((lane >> 3) & 1)));
+      else ldsm_x4_t(b, tile_addr(pb, kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), 2 * np + (lane >> 4)));
+      mma16816(acc[2 * np], a, b[0], b[1]);
+      mma16816(acc[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+// image tile, projector (bf16, swizzled), variant prologue, effective stencil.  Ends with __syncthreads().
+NGU_DEVINL void tc_load_common(TcSmem& s, bf16* hs, bf16* pbs, const bf16* hb, const ngu_mona_conv_weights& w, int HW, int HWp, int has_cls) {
+  const int c = threadIdx.x & (C - 1), grp = threadIdx.x >> 6;
+  for (int i = threadIdx.x; i < C * C; i += kThreads) pbs[swz(i / C, i % C)] = __float2bfloat16_rn(w.P[i]);
+  if (threadIdx.x < C) {
+    s.bp[threadIdx.x] = w.bp[threadIdx.x];
+    s.fr[threadIdx.x] = w.freq ? w.freq[threadIdx.x] : 1.0f;
+  }
+  const bf16* src = hb + has_cls * C;
+  for (int i = threadIdx.x; i < HWp * 8; i += kThreads) {  // one 16-byte chunk per thread-iteration
+    const int p = i >> 3, ch = i & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (p < HW) v = *reinterpret_cast<const uint4*>(src + p * C + ch * 8);
+    *reinterpret_cast<uint4*>(hs + p * C + ch * 8) = v;   // h stays LINEAR: only the streaming stencils read it
+  }
+  __syncthreads();
+  if (w.ne_w1 != nullptr) {
+    float a = 0.f;
+    for (int p = grp; p < HW; p += kThreads / C) a += __bfloat162float(hs[p * C + c]);
+    s.part[grp][c] = a;
+    __syncthreads();
+    if (threadIdx.x < C) s.hm[c] = (s.part[0][c] + s.part[1][c] + s.part[2][c] + s.part[3][c]) / float(HW);
+    __syncthreads();
+    if (threadIdx.x < CH) {
+      float acc = w.ne_b1[threadIdx.x];
+      for (int i = 0; i < C; ++i) acc = fmaf(w.ne_w1[threadIdx.x * C + i], s.fr[i] * s.hm[i], acc);
+      s.hid[threadIdx.x] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float lg[3];
+      for (int i = 0; i < 3; ++i) {
+        float acc = w.ne_b2[i];
+        for (int j = 0; j < CH; ++j) acc = fmaf(w.ne_w2[i * CH + j], s.hid[j], acc);
+        lg[i] = acc;
+      }
+      const float mx = fmaxf(lg[0], fmaxf(lg[1], lg[2]));
+      const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), e2 = expf(lg[2] - mx);
+      const float inv = 1.f / (e0 + e1 + e2);
+      s.wbr[0] = e0 * inv; s.wbr[1] = e1 * inv; s.wbr[2] = e2 * inv;
+    }
+  } else if (threadIdx.x == 0) {
+    s.wbr[0] = s.wbr[1] = s.wbr[2] = 1.0f / 3.0f;
+  }
+  __syncthreads();
+  const float w1 = s.wbr[0], w2 = s.wbr[1], w3 = s.wbr[2];
+  for (int i = threadIdx.x; i < 49 * C; i += kThreads) {
+    const int cc = i % C, t = i / C;
+    const int ky = t / 7, kx = t % 7;
+    float v = w3 * w.k7[cc * 49 + t];
+    if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) v = fmaf(w2, w.k5[cc * 25 + (ky - 1) * 5 + (kx - 1)], v);
+    if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) v = fmaf(w1, w.k3[cc * 9 + (ky - 2) * 3 + (kx - 2)], v);
+    v *= s.fr[cc];
+    if (t == 24) v += 1.0f;
+    s.kc[t][cc] = v;
+  }
+  if (threadIdx.x < C) s.bc[threadIdx.x] = w1 * w.b3[threadIdx.x] + w2 * w.b5[threadIdx.x] + w3 * w.b7[threadIdx.x];
+  __syncthreads();
+}
+
+// Streaming depthwise stencil on a LINEAR bf16 tile [HW][C]: one thread owns channel c and a 4-wide column strip and
+// walks the rows once, keeping the 7 output rows that the current input row touches in a rolling register window
+// (10 loads per 196 FMAs instead of 13 per 49).  emit(y, acc[4]) receives each finished output row.
+//   FLIP = false: out[y][x] = bias + sum k[ky][kx]   in[y+ky-3][x+kx-3]
+//   FLIP = true : out[y][x] = bias + sum k[ky][kx]   in[y-(ky-3)][x-(kx-3)]     (transposed stencil)
+constexpr int kSW = 4;  // strip width
+template <bool FLIP, typename Emit>
+NGU_DEVINL void stencil_stream(const bf16* in, const float (&k)[49], float bias, int x0, int H, int W, int c, Emit emit) {
+  float acc[7][kSW];
+#pragma unroll
+  for (int s_ = 0; s_ < 7; ++s_)
+#pragma unroll
+    for (int j = 0; j < kSW; ++j) acc[s_][j] = bias;
+  for (int yy = 0; yy < H + 3; ++yy) {
+    if (yy < H) {
+      float win[kSW + 6];
+      const bf16* rowp = in + (yy * W) * C + c;
+#pragma unroll
+      for (int i = 0; i < kSW + 6; ++i) {
+        const int xx = x0 + i - 3;
+        win[i] = (unsigned(xx) < unsigned(W)) ? __bfloat162float(rowp[xx * C]) : 0.f;
+      }
+#pragma unroll
+      for (int s_ = 0; s_ < 7; ++s_) {
+        const int ky = FLIP ? s_ : 6 - s_;   // slot s_ <-> output row yy - 3 + s_
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const float kv = k[ky * 7 + (FLIP ? 6 - kx : kx)];
+#pragma unroll
+          for (int j = 0; j < kSW; ++j) acc[s_][j] = fmaf(kv, win[j + kx], acc[s_][j]);
+        }
+      }
+    }
+    const int yo = yy - 3;
+    if (yo >= 0) emit(yo, acc[0]);
+#pragma unroll
+    for (int s_ = 0; s_ < 6; ++s_)
+#pragma unroll
+      for (int j = 0; j < kSW; ++j) acc[s_][j] = acc[s_ + 1][j];
+#pragma unroll
+    for (int j = 0; j < kSW; ++j) acc[6][j] = bias;
+  }
+}
+
+// z = stencil(h): h linear, z written into the swizzled tile (ldmatrix operand of the projector MMAs)
+NGU_DEVINL void conv_phase_stream(const TcSmem& s, const bf16* hs, bf16* zs, int H, int W, int c, int grp) {
+  float k[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) k[t] = s.kc[t][c];
+  for (int x0 = grp * kSW; x0 < W; x0 += (kThreads / C) * kSW) {
+    stencil_stream<false>(hs, k, s.bc[c], x0, H, W, c, [&](int y, const float (&a)[kSW]) {
+#pragma unroll
+      for (int j = 0; j < kSW; ++j)
+        if (x0 + j < W) zs[swz(y * W + x0 + j, c)] = __float2bfloat16_rn(a[j]);
+    });
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+mona_conv_fwd_tc_kernel(const bf16* __restrict__ h, bf16* __restrict__ g, ngu_mona_conv_weights w, int N, int H, int W,
+                        int has_cls, float drop_p, uint64_t seed) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(smem_dyn);
+  const int HW = H * W, HWp = (HW + 15) & ~15;
+  bf16* pbs = reinterpret_cast<bf16*>(smem_dyn + ((sizeof(TcSmem) + 1023) & ~size_t(1023)));
+  bf16* hs = pbs + C * C;
+  bf16* zs = hs + HWp * C;
+  const int img = blockIdx.x;
+  const bf16* hb = h + size_t(img) * N * C;
+  bf16* gb = g + size_t(img) * N * C;
+  const int c = threadIdx.x & (C - 1), grp = threadIdx.x >> 6;
+  for (int i = threadIdx.x; i < (HWp - HW) * 8; i += kThreads)  // zero the pad rows of z
+    *reinterpret_cast<uint4*>(zs + (HW + (i >> 3)) * C + ((i & 7) << 3)) = make_uint4(0, 0, 0, 0);
+  tc_load_common(s, hs, pbs, hb, w, HW, HWp, has_cls);
+  if (has_cls && grp == 0) {
+    float v = gelu_erf(__bfloat162float(hb[c]));
+    if (drop_p > 0.f) v *= dropout_scale(seed, (uint64_t(img) * N) * C + c, drop_p);
+    gb[c] = __float2bfloat16_rn(v);
+  }
+  conv_phase_stream(s, hs, zs, H, W, c, grp);
+  __syncthreads();
+  // a = z + bp + z P^T  ->  g = dropout(gelu(a))
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+  const uint32_t zs_u = smem_u32(zs), pb_u = smem_u32(pbs);
+  for (int rt = warp; rt < HWp / 16; rt += kThreads / 32) {
+    float acc[8][4];
+    proj_mma<false>(acc, zs_u, rt, pb_u, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int r = rt * 16 + gq + hh * 8, cc = nt * 8 + 2 * tq;
+        if (r < HW) {
+          const float2 zz = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(zs + swz(r, cc)));
+          float v0 = gelu_erf(acc[nt][2 * hh] + zz.x + s.bp[cc]);
+          float v1 = gelu_erf(acc[nt][2 * hh + 1] + zz.y + s.bp[cc + 1]);
+          if (drop_p > 0.f) {
+            const uint64_t e = (uint64_t(img) * N + has_cls + r) * C + cc;
+            v0 *= dropout_scale(seed, e, drop_p);
+            v1 *= dropout_scale(seed, e + 1, drop_p);
+          }
+          *reinterpret_cast<uint32_t*>(gb + (has_cls + r) * C + cc) = pack_bf16x2(v0, v1);
+        }
+      }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+mona_conv_bwd_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dg, bf16* __restrict__ dh, ngu_mona_conv_weights w,
+                        ngu_mona_conv_grads gr, int N, int H, int W, int has_cls, float drop_p, uint64_t seed) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(smem_dyn);
+  const int HW = H * W, HWp = (HW + 15) & ~15;
+  bf16* pbs = reinterpret_cast<bf16*>(smem_dyn + ((sizeof(TcSmem) + 1023) & ~size_t(1023)));
+  bf16* hs = pbs + C * C;
+  bf16* zs = hs + HWp * C;    // z, later dz
+  bf16* das = zs + HWp * C;   // da; later reused as the fp32 [49][C] correlation buffer
+  const int img = blockIdx.x;
+  const bf16* hb = h + size_t(img) * N * C;
+  const bf16* dgb = dg + size_t(img) * N * C;
+  bf16* dhb = dh + size_t(img) * N * C;
+  const int c = threadIdx.x & (C - 1), grp = threadIdx.x >> 6;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+  for (int i = threadIdx.x; i < (HWp - HW) * 8; i += kThreads) {
+    *reinterpret_cast<uint4*>(zs + (HW + (i >> 3)) * C + ((i & 7) << 3)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(das + (HW + (i >> 3)) * C + ((i & 7) << 3)) = make_uint4(0, 0, 0, 0);
+  }
+  tc_load_common(s, hs, pbs, hb, w, HW, HWp, has_cls);
+  float db1_acc = 0.f;
+  if (has_cls && grp == 0) {
+    float v = __bfloat162float(dgb[c]) * gelu_erf_grad(__bfloat162float(hb[c]));
+    if (drop_p > 0.f) v *= dropout_scale(seed, (uint64_t(img) * N) * C + c, drop_p);
+    dhb[c] = __float2bfloat16_rn(v);
+    db1_acc += v;
+  }
+  // ---- phase 1: z = stencil(h)
+  conv_phase_stream(s, hs, zs, H, W, c, grp);
+  __syncthreads();
+  const uint32_t zs_u = smem_u32(zs), da_u = smem_u32(das), pb_u = smem_u32(pbs);
+  // ---- phase 2: da = dg * mask * gelu'(z + bp + z P^T)
+  for (int rt = warp; rt < HWp / 16; rt += kThreads / 32) {
+    float acc[8][4];
+    proj_mma<false>(acc, zs_u, rt, pb_u, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int r = rt * 16 + gq + hh * 8, cc = nt * 8 + 2 * tq;
+        float v0 = 0.f, v1 = 0.f;
+        if (r < HW) {
+          const float2 zz = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(zs + swz(r, cc)));
+          const float2 gg = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dgb + (has_cls + r) * C + cc));
+          v0 = gg.x * gelu_erf_grad(acc[nt][2 * hh] + zz.x + s.bp[cc]);
+          v1 = gg.y * gelu_erf_grad(acc[nt][2 * hh + 1] + zz.y + s.bp[cc + 1]);
+          if (drop_p > 0.f) {
+            const uint64_t e = (uint64_t(img) * N + has_cls + r) * C + cc;
+            v0 *= dropout_scale(seed, e, drop_p);
+            v1 *= dropout_scale(seed, e + 1, drop_p);
+          }
+        }
+        *reinterpret_cast<uint32_t*>(das + swz(r, cc)) = pack_bf16x2(v0, v1);
+      }
+  }
+  __syncthreads();
+  // ---- phase 3: dP[o][i] += sum_p da[p][o] z[p][i]  (A = da^T, B = z, both read transposed from k-major tiles);  dbp
+  {
+    const int mt = warp & 3, nh = warp >> 2;
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    for (int kt = 0; kt < HWp / 16; ++kt) {
+      uint32_t a[4];
+      ldsm_x4_t(a, tile_addr(da_u, kt * 16 + (lane >> 4) * 8 + (lane & 7), mt * 2 + ((lane >> 3) & 1)));
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b[4];
+        ldsm_x4_t(b, tile_addr(zs_u, kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), nh * 4 + np * 2 + (lane >> 4)));
+        mma16816(acc[2 * np], a, b[0], b[1]);
+        mma16816(acc[2 * np + 1], a, b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int o = mt * 16 + gq + hh * 8, i = (nh * 4 + nt) * 8 + 2 * tq;
+        atomicAdd(gr.dP + o * C + i, acc[nt][2 * hh]);
+        atomicAdd(gr.dP + o * C + i + 1, acc[nt][2 * hh + 1]);
+      }
+    // dbp[o] = sum_p da[p][o]
+    float a = 0.f;
+    for (int p = grp; p < HW; p += kThreads / C) a += __bfloat162float(das[swz(p, c)]);
+    atomicAdd(gr.dbp + c, a);
+  }
+  __syncthreads();
+  // ---- phase 4: dz = da + da P   (overwrites z)
+  for (int rt = warp; rt < HWp / 16; rt += kThreads / 32) {
+    float acc[8][4];
+    proj_mma<true>(acc, da_u, rt, pb_u, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int r = rt * 16 + gq + hh * 8, cc = nt * 8 + 2 * tq;
+        const float2 dd = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(das + swz(r, cc)));
+        // dz is only read by the streaming stencils from here on: store it LINEAR
+        *reinterpret_cast<uint32_t*>(zs + r * C + cc) = pack_bf16x2(acc[nt][2 * hh] + dd.x, acc[nt][2 * hh + 1] + dd.y);
+      }
+  }
+  __syncthreads();
+  // ---- phase 5: correlation sums G[t][c] = sum_p dz[p][c] h[p + off_t][c], S[c] = sum_p dz[p][c]
+  //      streamed over the rows of h with the 7 dz rows it pairs with held in a rolling register window
+  float* Gs = reinterpret_cast<float*>(das);
+  float* Ss = s.part[0];
+  for (int i = threadIdx.x; i < 49 * C; i += kThreads) Gs[i] = 0.f;
+  if (threadIdx.x < C) Ss[threadIdx.x] = 0.f;
+  __syncthreads();
+  for (int x0 = grp * kSW; x0 < W; x0 += (kThreads / C) * kSW) {
+    float G[49];
+#pragma unroll
+    for (int t = 0; t < 49; ++t) G[t] = 0.f;
+    float dsum = 0.f;
+    float dzb[7][kSW];  // slot s_ <-> dz row yy - 3 + s_
+    auto load_dz = [&](int y, float (&dst)[kSW]) {
+#pragma unroll
+      for (int j = 0; j < kSW; ++j) {
+        dst[j] = (unsigned(y) < unsigned(H) && x0 + j < W) ? __bfloat162float(zs[(y * W + x0 + j) * C + c]) : 0.f;
+        dsum += dst[j];
+      }
+    };
+#pragma unroll
+    for (int s_ = 0; s_ < 7; ++s_) load_dz(s_ - 3, dzb[s_]);
+    for (int yy = 0; yy < H; ++yy) {
+      float win[kSW + 6];
+      const bf16* rowp = hs + (yy * W) * C + c;
+#pragma unroll
+      for (int i = 0; i < kSW + 6; ++i) {
+        const int xx = x0 + i - 3;
+        win[i] = (unsigned(xx) < unsigned(W)) ? __bfloat162float(rowp[xx * C]) : 0.f;
+      }
+#pragma unroll
+      for (int s_ = 0; s_ < 7; ++s_) {
+        const int ky = 6 - s_;  // h row yy = dz row (yy - 3 + s_) + ky - 3
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          float a = G[ky * 7 + kx];
+#pragma unroll
+          for (int j = 0; j < kSW; ++j) a = fmaf(dzb[s_][j], win[j + kx], a);
+          G[ky * 7 + kx] = a;
+        }
+      }
+#pragma unroll
+      for (int s_ = 0; s_ < 6; ++s_)
+#pragma unroll
+        for (int j = 0; j < kSW; ++j) dzb[s_][j] = dzb[s_ + 1][j];
+      load_dz(yy + 4, dzb[6]);
+    }
+#pragma unroll
+    for (int t = 0; t < 49; ++t) atomicAdd(&Gs[t * C + c], G[t]);
+    atomicAdd(&Ss[c], dsum);
+  }
+  __syncthreads();
+  // ---- phase 6: stencil / bias / frequency / branch-weight gradients from G and S (same as the generic fast kernel)
+  const float w1 = s.wbr[0], w2 = s.wbr[1], w3 = s.wbr[2];
+  if (threadIdx.x < C) {
+    const float f = s.fr[c], Sc = Ss[c];
+    float q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    for (int t = 0; t < 49; ++t) {
+      const int ky = t / 7, kx = t % 7;
+      const float g_ = Gs[t * C + c];
+      q3 = fmaf(w.k7[c * 49 + t], g_, q3);
+      atomicAdd(gr.dk7 + c * 49 + t, w3 * f * g_);
+      if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) {
+        const int u = (ky - 1) * 5 + (kx - 1);
+        q2 = fmaf(w.k5[c * 25 + u], g_, q2);
+        atomicAdd(gr.dk5 + c * 25 + u, w2 * f * g_);
+      }
+      if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) {
+        const int u = (ky - 2) * 3 + (kx - 2);
+        q1 = fmaf(w.k3[c * 9 + u], g_, q1);
+        atomicAdd(gr.dk3 + c * 9 + u, w1 * f * g_);
+      }
+    }
+    atomicAdd(gr.db3 + c, w1 * Sc);
+    atomicAdd(gr.db5 + c, w2 * Sc);
+    atomicAdd(gr.db7 + c, w3 * Sc);
+    s.part[1][c] = w1 * q1 + w2 * q2 + w3 * q3;
+    s.part[2][c] = f * q1 + w.b3[c] * Sc;
+    s.part[3][c] = f * q2 + w.b5[c] * Sc;
+    s.dgap[c] = f * q3 + w.b7[c] * Sc;
+  }
+  __syncthreads();
+  float cst = 0.f;
+  if (w.ne_w1 != nullptr) {
+    if (threadIdx.x < 3) {
+      const float* src = threadIdx.x == 0 ? s.part[2] : threadIdx.x == 1 ? s.part[3] : s.dgap;
+      float a = 0.f;
+      for (int i = 0; i < C; ++i) a += src[i];
+      s.dwbr[threadIdx.x] = a;
+    }
+    __syncthreads();
+    const float dot = w1 * s.dwbr[0] + w2 * s.dwbr[1] + w3 * s.dwbr[2];
+    const float dl0 = w1 * (s.dwbr[0] - dot), dl1 = w2 * (s.dwbr[1] - dot), dl2 = w3 * (s.dwbr[2] - dot);
+    __syncthreads();
+    if (threadIdx.x < CH) {
+      const int j = threadIdx.x;
+      const float hj = s.hid[j];
+      atomicAdd(gr.dne_w2 + 0 * CH + j, dl0 * hj);
+      atomicAdd(gr.dne_w2 + 1 * CH + j, dl1 * hj);
+      atomicAdd(gr.dne_w2 + 2 * CH + j, dl2 * hj);
+      const float dh_ = hj > 0.f ? (w.ne_w2[0 * CH + j] * dl0 + w.ne_w2[1 * CH + j] * dl1 + w.ne_w2[2 * CH + j] * dl2) : 0.f;
+      s.hid[j] = dh_;
+      atomicAdd(gr.dne_b1 + j, dh_);
+    }
+    if (threadIdx.x == 0) { atomicAdd(gr.dne_b2 + 0, dl0); atomicAdd(gr.dne_b2 + 1, dl1); atomicAdd(gr.dne_b2 + 2, dl2); }
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float dgv = 0.f;
+      const float gap = s.fr[c] * s.hm[c];
+      for (int j = 0; j < CH; ++j) {
+        dgv = fmaf(w.ne_w1[j * C + c], s.hid[j], dgv);
+        atomicAdd(gr.dne_w1 + j * C + c, s.hid[j] * gap);
+      }
+      s.dgap[c] = dgv;
+    }
+    __syncthreads();
+    cst = s.dgap[c] * s.fr[c] / float(HW);
+    if (threadIdx.x < C && gr.dfreq) atomicAdd(gr.dfreq + c, s.part[1][c] + s.dgap[c] * s.hm[c]);
+  } else {
+    if (threadIdx.x < C && gr.dfreq && w.freq) atomicAdd(gr.dfreq + c, s.part[1][c]);
+  }
+  // ---- phase 7: dh = transposed effective stencil of dz (+ pooled-path constant)
+  {
+    float k[49];
+#pragma unroll
+    for (int t = 0; t < 49; ++t) k[t] = s.kc[t][c];
+    for (int x0 = grp * kSW; x0 < W; x0 += (kThreads / C) * kSW) {
+      stencil_stream<true>(zs, k, cst, x0, H, W, c, [&](int y, const float (&a)[kSW]) {
+#pragma unroll
+        for (int j = 0; j < kSW; ++j)
+          if (x0 + j < W) { dhb[(has_cls + y * W + x0 + j) * C + c] = __float2bfloat16_rn(a[j]); db1_acc += a[j]; }
+      });
+    }
+  }
+  atomicAdd(gr.db1 + c, db1_acc);
+}
+
+size_t tc_smem_bytes(int HW, bool bwd) {
+  const size_t HWp = (size_t(HW) + 15) & ~size_t(15);
+  const size_t tile = HWp * C * 2;
+  const size_t da = tile > size_t(49) * C * sizeof(float) ? tile : size_t(49) * C * sizeof(float);
+  return ((sizeof(TcSmem) + 1023) & ~size_t(1023)) + size_t(C) * C * 2 + 2 * tile + (bwd ? da : 0);
+}
+
 // h tile + z tile (+ da tile in backward; the da region is reused as the [49][C] fp32 correlation buffer, so it
 // is at least that large)
 template <typename T>
@@ -674,6 +1146,14 @@ int conv_smem_bytes(int HW, bool bwd) { return int(sizeof(ConvSmem)) + HW * C * 
 
 template <typename T>
 int launch_fwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
+  if (sizeof(T) == 2 && fast_ok<T>(d, false) && !d.force_simt) {
+    const int smf = int(tc_smem_bytes(d.H * d.W, false));
+    cudaError_t e = cudaFuncSetAttribute(mona_conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
+    if (e != cudaSuccess) return cuda_status(e, "mona_conv_fwd attr");
+    mona_conv_fwd_tc_kernel<<<d.B, kThreads, smf, st>>>(reinterpret_cast<const bf16*>(d.h), reinterpret_cast<bf16*>(d.g), d.w, d.N, d.H, d.W,
+                                                          d.has_cls, d.drop_p, d.seed);
+    return check_launch("mona_conv_fwd");
+  }
   if (fast_ok<T>(d, false)) {
     const int smf = int(fast_smem_bytes<T>(d.H * d.W, false));
     cudaError_t e = cudaFuncSetAttribute(mona_conv_fwd_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
@@ -692,6 +1172,14 @@ int launch_fwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
 }
 template <typename T>
 int launch_bwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
+  if (sizeof(T) == 2 && fast_ok<T>(d, true) && !d.force_simt) {
+    const int smf = int(tc_smem_bytes(d.H * d.W, true));
+    cudaError_t e = cudaFuncSetAttribute(mona_conv_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
+    if (e != cudaSuccess) return cuda_status(e, "mona_conv_bwd attr");
+    mona_conv_bwd_tc_kernel<<<d.B, kThreads, smf, st>>>(reinterpret_cast<const bf16*>(d.h), reinterpret_cast<const bf16*>(d.dg),
+                                                          reinterpret_cast<bf16*>(d.dh), d.w, d.gr, d.N, d.H, d.W, d.has_cls, d.drop_p, d.seed);
+    return check_launch("mona_conv_bwd");
+  }
   if (fast_ok<T>(d, true)) {
     const int smf = int(fast_smem_bytes<T>(d.H * d.W, true));
     cudaError_t e = cudaFuncSetAttribute(mona_conv_bwd_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);

@@ -30,10 +30,10 @@ constexpr int kNumEpiWarps = 8;
 constexpr int kGemmThreads = 32 * (2 + kNumEpiWarps);
 constexpr int kSlabBytes = 32 * 128;  // 32 rows x 64 bf16
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kPair = false>
 struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kBBytes = (kPair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // pair mode: each CTA holds half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBytes = kNumEpiWarps * kSlabBytes;  // one 32x64 slab per epilogue warp
   static constexpr int kBarBytes = 1024;  // mbarriers + tmem ptr
@@ -101,10 +101,11 @@ NGU_DEVINL void epi_chunk(const uint32_t (&v)[64], const uint4 (&ax)[8], float2 
   }
 }
 
-template <int BLOCK_N, int kCluster>
+template <int BLOCK_N, int kCluster, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  static_assert(!kPair || kCluster == 2, "pair mode is a 2-CTA cluster");
+  using Cfg = GemmCfg<BLOCK_N, kPair>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA0 = smem_base;
@@ -143,17 +144,17 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     tma_prefetch_desc(&p.tmC);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), kCluster);  // released by the MMA warps of every CTA that reads this slot's B tile
+      mbar_init(empty_bar(s), kPair ? 1 : kCluster);  // released by the MMA warp(s) of every CTA that reads this slot
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), (BLOCK_N / 64 >= 2) ? kNumEpiWarps : 4);
+      mbar_init(tempty_bar(a), ((BLOCK_N / 64 >= 2) ? kNumEpiWarps : 4) * (kPair ? 2 : 1));  // pair: both CTAs' epilogues
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(sTmemPtr, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc_2cta(sTmemPtr, Cfg::kTmemCols); tmem_relinquish_2cta(); }
+    else { tmem_alloc(sTmemPtr, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -174,22 +175,30 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
         const int n0 = tile_n0(t);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_arrive_expect_tx(full_bar(s), Cfg::kStageBytes);
           const bool main_k = kb < kb1;
           const int kc = (main_k ? kb : kb - kb1) * BLOCK_K;
           const CUtensorMap* ta = main_k ? &p.tmA : &p.tmA2;
           const CUtensorMap* tb = main_k ? (kCluster > 1 ? &p.tmBh : &p.tmB) : (kCluster > 1 ? &p.tmB2h : &p.tmB2);
-          tma_load_2d(sA0 + s * Cfg::kABytes, ta, full_bar(s), kc, m0, kEvictNormal);
-          // A streams from HBM: warm L2 for the block kPrefetch steps ahead (next tile's rows once this tile's K is done)
-          if (main_k && p.prefetch > 0) {
-            int pk = kb + p.prefetch, pt = t;
-            if (pk >= kb1) { pk -= kb1; pt += tile_stride; }
-            if (pt < num_tiles && pk < kb1) tma_prefetch_l2_2d(&p.tmA, pk * BLOCK_K, tile_m0(pt));
+          if (kPair) {
+            // both CTAs' loads complete on the LEADER's full barrier (it feeds the single issuing MMA thread)
+            const uint32_t lead_full = mapa_cluster(full_bar(s), 0);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);
+            tma_load_2d_2cta(sA0 + s * Cfg::kABytes, ta, lead_full, kc, m0, kEvictNormal);
+            tma_load_2d_2cta(sB0 + s * Cfg::kBBytes, tb, lead_full, kc, n0 + rank * kBRows, kEvictLast);
+          } else {
+            mbar_arrive_expect_tx(full_bar(s), Cfg::kStageBytes);
+            tma_load_2d(sA0 + s * Cfg::kABytes, ta, full_bar(s), kc, m0, kEvictNormal);
+            // A streams from HBM: warm L2 for the block kPrefetch steps ahead (next tile's rows once this tile's K is done)
+            if (main_k && p.prefetch > 0) {
+              int pk = kb + p.prefetch, pt = t;
+              if (pk >= kb1) { pk -= kb1; pt += tile_stride; }
+              if (pt < num_tiles && pk < kb1) tma_prefetch_l2_2d(&p.tmA, pk * BLOCK_K, tile_m0(pt));
+            }
+            if (kCluster > 1)
+              tma_load_2d_mcast(sB0 + s * Cfg::kBBytes + rank * kBRows * BLOCK_K * 2, tb, full_bar(s), kc, n0 + rank * kBRows, kMask, kEvictLast);
+            else
+              tma_load_2d(sB0 + s * Cfg::kBBytes, tb, full_bar(s), kc, n0, kEvictLast);
           }
-          if (kCluster > 1)
-            tma_load_2d_mcast(sB0 + s * Cfg::kBBytes + rank * kBRows * BLOCK_K * 2, tb, full_bar(s), kc, n0 + rank * kBRows, kMask, kEvictLast);
-          else
-            tma_load_2d(sB0 + s * Cfg::kBBytes, tb, full_bar(s), kc, n0, kEvictLast);
           if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
         }
       }
@@ -199,14 +208,15 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     // The whole warp walks the loop (so every value is warp-uniform and lives in uniform registers); one elected
     // lane issues the tcgen05.mma / commit instructions.  Descriptors differ only in their 14-bit address field:
     // desc = base + (byte offset >> 4).
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = make_idesc_bf16(kPair ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+    const bool issuer = !kPair || rank == 0;   // pair mode: only the leader CTA issues (on behalf of both)
     const uint64_t a_base = make_smem_desc_sw128(sA0, 16, 1024);
     const uint64_t b_base = make_smem_desc_sw128(sB0, 16, 1024);
     int s = 0;
     uint32_t ph = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int t = tile_first; t < num_tiles; t += tile_stride) {
+    for (int t = tile_first; issuer && t < num_tiles; t += tile_stride) {
       mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
@@ -219,18 +229,26 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
         const uint64_t ad = a_base + uint64_t((s * Cfg::kABytes) >> 4);
         const uint64_t bd = b_base + uint64_t((s * Cfg::kBBytes) >> 4);
         if (elect_one()) {
+          const int nk = (kext + UMMA_K - 1) / UMMA_K;
           if (kext == BLOCK_K) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_ss(d_tmem, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              if (kPair) umma_ss_2cta(d_tmem, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_ss(d_tmem, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           } else {
-            const int nk = (kext + UMMA_K - 1) / UMMA_K;
-            for (int k = 0; k < nk; ++k)
-              umma_ss(d_tmem, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < nk; ++k) {
+              if (kPair) umma_ss_2cta(d_tmem, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_ss(d_tmem, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           // frees the smem slot once these MMAs have read it (in every CTA whose producer writes into it)
-          if (kCluster > 1) umma_commit_mcast(empty_bar(s), uint16_t((1u << kCluster) - 1u)); else umma_commit(empty_bar(s));
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (kPair) umma_commit_2cta_mcast(empty_bar(s), 3);
+          else if (kCluster > 1) umma_commit_mcast(empty_bar(s), uint16_t((1u << kCluster) - 1u));
+          else umma_commit(empty_bar(s));
+          if (kb == num_kb - 1) {
+            if (kPair) umma_commit_2cta_mcast(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
+          }
         }
         __syncwarp();
         if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
@@ -303,7 +321,9 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
             // all TMEM reads of this accumulator by this warp are done: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+              if (kPair && rank != 0) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc));
+            }
           }
           if (!live) continue;
 
@@ -372,13 +392,13 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
   if (kCluster > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (kPair) tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BLOCK_N, int kCluster>
+template <int BLOCK_N, int kCluster, bool kPair = false>
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, kPair>;
   GemmKernelParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -411,7 +431,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
 
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kCluster, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_status(e, "gemm_tc smem attribute");
     attr_done = true;
   }
@@ -433,7 +453,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kCluster>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kCluster, kPair>, p);
   count_launch(1);
   if (e != cudaSuccess) return cuda_status(e, "gemm_tc launch");
   return cuda_status(cudaGetLastError(), "gemm_tc");
@@ -457,7 +477,24 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   }
   int bn = a.block_n;
   if (bn == 0) bn = (a.N > 128) ? 256 : (a.N > 64 ? 128 : 64);
-  // block_n + 1000 forces the single-CTA (no multicast) variant: tests / tuning
+  // block_n + 2000 forces the CTA-pair (cta_group::2) variant, block_n + 1000 the single-CTA (no multicast) one: tests / tuning
+  if (a.block_n >= 2000) {
+    if (a.M <= BLOCK_M) { set_last_error("gemm_tc: pair mode needs M > 128"); return NGU_ERR_ARG; }
+    switch (a.block_n - 2000) {
+      case 0: case 256: return launch_gemm_tc<256, 2, true>(a, stream);
+      case 128: return launch_gemm_tc<128, 2, true>(a, stream);
+      default: set_last_error("gemm_tc: pair mode supports block_n 128/256"); return NGU_ERR_ARG;
+    }
+  }
+  // Auto: the CTA-pair variant (256x256 tile per SM pair, half the smem traffic per MMA, 6-deep pipeline) wins when the
+  // mainloop dominates; epilogue-heavy launches (GELU + saved derivative, derivative multiply) with a short K stay on the
+  // independent-CTA multicast variant, where one CTA's epilogue never stalls its peer's accumulator.
+  // NGU_GEMM_PAIR: 0 never, 1 heuristic (default), 2 whenever legal.
+  static const int pair_mode = [] { const char* e = getenv("NGU_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  if (a.block_n == 0 && bn == 256 && a.M > BLOCK_M && pair_mode > 0) {
+    const bool heavy_epi = a.act != NGU_ACT_NONE || a.save_pre || a.aux_mode == NGU_AUX_DACT;
+    if (pair_mode >= 2 || !heavy_epi || a.K + a.K2 >= 2048) return launch_gemm_tc<256, 2, true>(a, stream);
+  }
   const bool no_cluster = a.block_n >= 1000;
   if (no_cluster) bn = a.block_n - 1000 ? a.block_n - 1000 : ((a.N > 128) ? 256 : (a.N > 64 ? 128 : 64));
   const bool cluster = !no_cluster && a.M > BLOCK_M;

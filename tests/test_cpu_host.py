@@ -141,3 +141,20 @@ def test_dp_gradient_plumbing_gloo_world2(tmp_path):
     for p in procs:
         out, err = p.communicate(timeout=120)
         assert p.returncode == 0 and "ok" in out, err[-2000:]
+
+
+def test_device_feeder_and_scalar_log_cpu():
+    """Host-side input pipeline and loss log (dp.DeviceFeeder / dp.ScalarLog): order, byte accounting, exhaustion."""
+    from nextgen_uia_b200 import dp
+    batches = [(torch.full((4, 3), float(i)), torch.full((4,), i, dtype=torch.int64)) for i in range(5)]
+    feeder = dp.DeviceFeeder(iter(batches), "cpu")
+    seen = [(int(a[0, 0]), int(b[0])) for a, b in feeder]
+    assert seen == [(i, i) for i in range(5)]
+    assert feeder.h2d_bytes == 5 * (4 * 3 * 4 + 4 * 8)
+    log = dp.ScalarLog()
+    got = []
+    for i in range(5):
+        log.push(torch.tensor(float(i)))
+        got += log.pop_ready()
+    assert got == [0.0, 1.0, 2.0, 3.0]
+    assert log.drain() == [4.0]

@@ -323,3 +323,25 @@ def test_clipseg_adapter_vs_oracle(dtype):
         d = a.double().cpu() - b
         num += float((d * d).sum()); den += float((b * b).sum())
     assert (num / den) ** 0.5 < (8e-2 if dtype == torch.bfloat16 else 1e-3)
+
+
+@pytest.mark.gpu
+def test_device_feeder_overlapped_copies_are_intact():
+    """dp.DeviceFeeder hands out each host batch exactly once and unmodified while compute is queued behind it."""
+    from nextgen_uia_b200 import dp
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    host = [(torch.randn(64, 3, 32, 32, generator=g).pin_memory(), torch.randint(0, 1000, (64, 16), generator=g).pin_memory()) for _ in range(7)]
+    feeder = dp.DeviceFeeder(iter(host), dev)
+    log = dp.ScalarLog()
+    sums, w = [], torch.randn(2048, 2048, device=dev)
+    for im, tx in feeder:
+        for _ in range(20):      # keep the compute stream busy so slot reuse has to honour the `free` events
+            w = torch.tanh(w @ w * 1e-3)
+        log.push(im.double().sum() + tx.double().sum())
+        sums += log.pop_ready()
+    sums += log.drain()
+    ref = [float(a.double().sum() + b.double().sum()) for a, b in host]
+    assert len(sums) == 7 and feeder.h2d_bytes == sum(a.numel() * 4 + b.numel() * 8 for a, b in host)
+    for s, r in zip(sums, ref):
+        assert abs(s - r) <= 1e-3 * max(1.0, abs(r))

@@ -29,6 +29,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 struct AttnTcParams {
   CUtensorMap tmQKV;  // [B*N rows, 3*H*64 cols] bf16, box 64 cols x 128 rows, SWIZZLE_128B
   CUtensorMap tmDO;   // [B*N rows, H*64 cols]   bf16, same box (backward)
+  CUtensorMap tmQKV1, tmDO1;  // backward, N > 128: boxes of ceil16(N - 128) rows for the second tile
   bf16* o;            // [B*N, H*64]
   const bf16* o_in;   // backward: forward output
   const bf16* d_o;    // backward
@@ -194,40 +195,83 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
 // =====================================================================================================
 // backward
 // =====================================================================================================
-constexpr int kBwdThreads = 32 * 9;  // 8 compute warps (kv row = lane quarter, query columns split in halves) + 1 control warp
-constexpr int kBwdSmem = 10 * kTileBytes + 2048 + 1024 + 1024;
+// Persistent, software-pipelined backward.  One CTA per SM walks (batch, head) items.  Roles:
+//   warps 0-15  compute  (kv row = TMEM lane = 32*(warp&3)+lane; warp>>2 picks 16 of the step's 64 query columns)
+//   warp  16    MMA issuer (whole warp walks the loop, one elected lane issues)
+//   warp  17    TMA loader (one lane): fetches tile groups of the NEXT item as soon as the MMAs that read them finish
+//   warps 18-19 statistics: lse*log2e and scale*rowsum(dO * O) of the next item into a double-buffered smem table
+// An item is cut into "steps" of (kv tile j, query tile i, 64-column half).  S^T / dP^T of step s+1 are issued into
+// the other TMEM buffer before the issuer waits for P^T of step s, the dV/dK/dQ accumulators of a kv tile are drained
+// by the compute warps AFTER they have produced the next step's P^T, and the query-tile order alternates between
+// items (j=0: i=0,1  j=1: i=1,0 | next item j=0: i=1,0  j=1: i=0,1) so that every tile group of the next item is free
+// at least one pair before it is needed.  Query extents are trimmed to the padded live length (N = 197: the second
+// query tile costs 64 + 16 columns instead of 128) and the kv extent of dQ to ceil16(live kv rows).
+constexpr int kBwdComputeWarps = 16;
+constexpr int kBwdThreads = 32 * (kBwdComputeWarps + 4);
+constexpr int kBwdSmem = 12 * kTileBytes + 2 * 2048 + 1024 + 1024;
+
+struct BwdStep {
+  int j, i, ii, half, nq;  // ii: position of the pair within its kv tile; nq: live query columns padded to 16 (0 = dead)
+};
+// ntiles is 1 or 2: no divisions on the issuing thread's critical path
+NGU_DEVINL BwdStep bwd_step(int r, int par, int ntiles, int N) {
+  BwdStep s;
+  s.half = r & 1;
+  s.ii = ntiles == 2 ? (r >> 1) & 1 : 0;
+  s.j = ntiles == 2 ? r >> 2 : 0;
+  s.i = ntiles == 2 ? (s.ii ^ s.j ^ par) : 0;
+  int live = N - (s.i * TILE + s.half * 64);
+  live = live < 0 ? 0 : (live > 64 ? 64 : live);
+  s.nq = (live + 15) & ~15;
+  return s;
+}
 
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = base + 2 * kTileBytes, sV = base + 4 * kTileBytes, sDO = base + 6 * kTileBytes;
-  const uint32_t sDS = base + 8 * kTileBytes;                 // [2 q-chunks of 64][128 kv rows][128 B]
-  const uint32_t sStat = base + 10 * kTileBytes;              // lse2[256], delta[256] (fp32)
-  const uint32_t sBar = sStat + 2048;
-  const uint32_t bar_load = sBar, bar_s = sBar + 8, bar_p = sBar + 16, bar_acc = sBar + 24;
-  const uint32_t sTmem = sBar + 32;
-  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  float* lse2 = reinterpret_cast<float*>(gen + 10 * kTileBytes);
-  float* delta = lse2 + 256;
+  const uint32_t sDS = base + 8 * kTileBytes;   // 2 buffers x [2 q-chunks of 64][128 kv rows][128 B]
+  const uint32_t sStat = base + 12 * kTileBytes;  // [2 buffers][lse2[256], delta[256]] fp32
+  const uint32_t sBar = sStat + 2 * 2048;
+  // tile groups: 0 = {K0,V0}  1 = {K1,V1}  2 = {Q0,dO0}  3 = {Q1,dO1}
+  auto bar_full = [&](int g) { return sBar + 8u * g; };           // 4: tile group landed
+  auto bar_free = [&](int g) { return sBar + 32u + 8u * g; };     // 4: tile group no longer read by any MMA
+  auto bar_s = [&](int b) { return sBar + 64u + 8u * b; };        // 2: S^T / dP^T of the buffer complete
+  auto bar_p = [&](int b) { return sBar + 80u + 8u * b; };        // 2: P^T / dS^T of the buffer written (512 arrivals)
+  auto bar_dq = [&](int b) { return sBar + 96u + 8u * b; };       // 2: dQ MMAs that read dS smem buffer b complete
+  auto bar_stat = [&](int b) { return sBar + 112u + 8u * b; };    // 2: lse / delta table b filled (64 arrivals)
+  auto bar_statfree = [&](int b) { return sBar + 128u + 8u * b; };  // 2: compute warps done reading table b (512 arrivals)
+  const uint32_t bar_acc = sBar + 144u;                           // dV_j / dK_j (and dQ after the last j) complete
+  const uint32_t bar_drained = sBar + 152u;                       // accumulators read out (512 arrivals)
+  const uint32_t sTmem = sBar + 160u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int N = p.N, D = p.H * DH;
   const int ntiles = (N + TILE - 1) / TILE;
-  const int row0 = b * N;
-  // TMEM columns
-  constexpr uint32_t cST = 0, cDPT = 128, cDV = 256, cDK = 320, cDQ = 384;
+  const int nraw = ntiles * ntiles * 2;
+  const int items = p.B * p.H;
+  const int n_local = (items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int rows1 = ntiles == 2 ? ((N - TILE + 15) & ~15) : 0;   // rows of the second tile that are fetched
+  // TMEM columns: buffer b holds S^T at b*128 (64 fp32 cols) and dP^T at b*128 + 64
+  constexpr uint32_t cDV = 256, cDK = 320, cDQ = 384;
+  constexpr int kCompute = 32 * kBwdComputeWarps;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmQKV);
     tma_prefetch_desc(&p.tmDO);
-    mbar_init(bar_load, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 256);
+    for (int g = 0; g < 4; ++g) { mbar_init(bar_full(g), 1); mbar_init(bar_free(g), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_s(b), 1);
+      mbar_init(bar_p(b), kCompute);
+      mbar_init(bar_dq(b), 1);
+      mbar_init(bar_stat(b), 64);
+      mbar_init(bar_statfree(b), kCompute);
+    }
     mbar_init(bar_acc, 1);
+    mbar_init(bar_drained, kCompute);
     fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == kBwdComputeWarps) {
     tmem_alloc(sTmem, 512);
     tmem_relinquish();
   }
@@ -237,60 +281,63 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(sTmem));
 
-  if (warp == 8) {
+  if (warp == kBwdComputeWarps + 1) {
+    // ================================ TMA loader ================================
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_load, 4 * ntiles * kTileBytes);
-      for (int t = 0; t < ntiles; ++t) {
-        tma_load_2d(sQ + t * kTileBytes, &p.tmQKV, bar_load, h * DH, row0 + t * TILE);
-        tma_load_2d(sK + t * kTileBytes, &p.tmQKV, bar_load, D + h * DH, row0 + t * TILE);
-        tma_load_2d(sV + t * kTileBytes, &p.tmQKV, bar_load, 2 * D + h * DH, row0 + t * TILE);
-        tma_load_2d(sDO + t * kTileBytes, &p.tmDO, bar_load, h * DH, row0 + t * TILE);
-      }
-      mbar_wait(bar_load, 0);
-      constexpr uint32_t idesc_st = make_idesc_bf16(TILE, TILE);          // ST / dPT: K-major x K-major
-      constexpr uint32_t idesc_ts = make_idesc_bf16(TILE, DH, 0, 1);      // dV / dK: A in TMEM, B MN-major
-      constexpr uint32_t idesc_dq = make_idesc_bf16(TILE, DH, 1, 1);      // dQ: A MN-major (smem), B MN-major
-      uint32_t ph = 0;
-      for (int j = 0; j < ntiles; ++j) {
-        for (int i = 0; i < ntiles; ++i) {
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            umma_ss(tmem + cST, desc_kmajor(sK + j * kTileBytes + k * 32), desc_kmajor(sQ + i * kTileBytes + k * 32), idesc_st, k != 0);
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            umma_ss(tmem + cDPT, desc_kmajor(sV + j * kTileBytes + k * 32), desc_kmajor(sDO + i * kTileBytes + k * 32), idesc_st, k != 0);
-          umma_commit(bar_s);
-          mbar_wait(bar_p, ph);
-          tc_fence_after();
-#pragma unroll
-          for (int s = 0; s < TILE / 16; ++s) {
-            umma_ts(tmem + cDV, tmem + cST + s * 8, desc_mnmajor(sDO + i * kTileBytes + s * 2048, 0), idesc_ts, (i | s) != 0);
-            umma_ts(tmem + cDK, tmem + cDPT + s * 8, desc_mnmajor(sQ + i * kTileBytes + s * 2048, 0), idesc_ts, (i | s) != 0);
-            umma_ss(tmem + cDQ + i * 64, desc_mnmajor(sDS + s * 2048, kTileBytes), desc_mnmajor(sK + j * kTileBytes + s * 2048, 0),
-                    idesc_dq, (j | s) != 0);
+      for (int n = 0; n < n_local; ++n) {
+        const int item = int(blockIdx.x) + n * int(gridDim.x);
+        const int b = item / p.H, h = item - b * p.H;
+        const int row0 = b * N;
+        const uint32_t fph = uint32_t(n - 1) & 1u;
+        auto load_group = [&](int g) {
+          if (n > 0) mbar_wait(bar_free(g), fph);
+          const int t = g & 1;                       // tile index within the sequence
+          const uint32_t off = t * kTileBytes;
+          mbar_arrive_expect_tx(bar_full(g), t ? 2 * rows1 * 128 : 2 * kTileBytes);
+          const CUtensorMap* mq = t ? &p.tmQKV1 : &p.tmQKV;
+          if (g < 2) {
+            tma_load_2d(sK + off, mq, bar_full(g), D + h * DH, row0 + t * TILE);
+            tma_load_2d(sV + off, mq, bar_full(g), 2 * D + h * DH, row0 + t * TILE);
+          } else {
+            tma_load_2d(sQ + off, mq, bar_full(g), h * DH, row0 + t * TILE);
+            tma_load_2d(sDO + off, t ? &p.tmDO1 : &p.tmDO, bar_full(g), h * DH, row0 + t * TILE);
           }
-          ph ^= 1u;
+        };
+        // in the order the item needs them (which is also the order the previous item releases them)
+        load_group(0);
+        if (ntiles == 2) {
+          const int first_i = n & 1;
+          load_group(2 + first_i);
+          load_group(2 + (first_i ^ 1));
+          load_group(1);
+        } else {
+          load_group(2);
         }
-        umma_commit(bar_acc);  // dV_j / dK_j (and, after the last j, dQ) complete
       }
     }
-  } else {
-    const int qd = warp & 3, hf = warp >> 2;     // TMEM lane quarter, query-column half
-    const int t = qd * 32 + lane;                // kv row within the tile (= TMEM lane)
-    // ---- prologue: lse (log2 domain) and delta = rowsum(dO * O) for every query row (one row per thread)
-    {
-      const int r = threadIdx.x;
-      if (r < ntiles * TILE) {
-        float l2 = 0.f, dl = 0.f;
+  } else if (warp >= kBwdComputeWarps + 2) {
+    // ================================ statistics ================================
+    const int l64 = (warp - kBwdComputeWarps - 2) * 32 + lane;
+    for (int n = 0; n < n_local; ++n) {
+      const int item = int(blockIdx.x) + n * int(gridDim.x);
+      const int b = item / p.H, h = item - b * p.H;
+      const int row0 = b * N;
+      // table n&1 was last read by item n-2
+      if (n >= 2) mbar_wait(bar_statfree(n & 1), uint32_t((n >> 1) - 1) & 1u);
+      const uint32_t tab = sStat + (n & 1) * 2048;
+      for (int r = l64; r < ntiles * TILE; r += 64) {
+        // rows past the sequence end: lse = +inf makes every probability of that query column exactly 0
+        float l2 = INFINITY, dl = 0.f;
         if (r < N) {
           l2 = p.lse[(size_t(b) * p.H + h) * N + r] * kLog2e;
           const uint4* po = reinterpret_cast<const uint4*>(p.o_in + size_t(row0 + r) * D + h * DH);
           const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + size_t(row0 + r) * D + h * DH);
+          uint4 a[8], g[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a[j] = __ldg(po + j); g[j] = __ldg(pd + j); }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint4 a = __ldg(po + j), g = __ldg(pd + j);
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+            const uint32_t aw[4] = {a[j].x, a[j].y, a[j].z, a[j].w}, gw[4] = {g[j].x, g[j].y, g[j].z, g[j].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(gw[e]);
@@ -299,105 +346,231 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
             }
           }
         }
-        lse2[r] = l2;
-        delta[r] = dl;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tab + 4u * r), "f"(l2) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tab + 1024u + 4u * r), "f"(dl * p.scale) : "memory");
       }
+      mbar_arrive(bar_stat(n & 1));
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+  } else if (warp == kBwdComputeWarps) {
+    // ================================ MMA issuer ================================
+    // The whole warp walks the loop so that every value is warp-uniform (uniform registers, no per-lane waterfall
+    // around the tcgen05 instructions); one elected lane issues.  This warp is the pacemaker of the kernel: keep
+    // its instruction count small.
+    constexpr uint32_t idesc_ts = make_idesc_bf16(TILE, DH, 0, 1);      // dV / dK: A in TMEM, B MN-major
+    constexpr uint32_t idesc_dq = make_idesc_bf16(TILE, DH, 1, 1);      // dQ: A MN-major (smem), B MN-major
+    const uint64_t dQ0 = desc_kmajor(sQ), dK0 = desc_kmajor(sK), dV0 = desc_kmajor(sV), dDO0 = desc_kmajor(sDO);
+    const uint64_t mQ0 = desc_mnmajor(sQ, 0), mK0 = desc_mnmajor(sK, 0), mDO0 = desc_mnmajor(sDO, 0);
+    const uint64_t mDS0 = desc_mnmajor(sDS, kTileBytes);
+    int w_item = -1;
+    uint32_t w_mask = 0;   // tile groups of item w_item whose full barrier has been observed
+    auto groups_of = [&](const BwdStep& s) { return (1u << s.j) | (1u << (2 + s.i)); };
+    auto issue_s = [&](int n, int r, uint32_t sc, bool blocking) -> bool {
+      const BwdStep s = bwd_step(r, n & 1, ntiles, N);
+      if (n != w_item) { w_item = n; w_mask = 0; }
+      uint32_t need = groups_of(s) & ~w_mask;
+      if (need) {
+        for (int g = 0; g < 4; ++g) {
+          if (!((need >> g) & 1u)) continue;
+          if (blocking) mbar_wait(bar_full(g), n & 1);
+          else if (!__all_sync(0xffffffffu, mbar_try_wait(bar_full(g), n & 1))) return false;
+          w_mask |= 1u << g;
+        }
+      }
+      tc_fence_after();
+      const uint32_t cb = tmem + (sc & 1u) * 128u;
+      const uint32_t idesc_st = make_idesc_bf16(TILE, s.nq);             // S^T / dP^T: K-major x K-major
+      const uint64_t qo = uint64_t((s.i * kTileBytes + s.half * 8192) >> 4), ko = uint64_t((s.j * kTileBytes) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_ss(cb, dK0 + ko + uint64_t(k * 2), dQ0 + qo + uint64_t(k * 2), idesc_st, k != 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_ss(cb + 64, dV0 + ko + uint64_t(k * 2), dDO0 + qo + uint64_t(k * 2), idesc_st, k != 0);
+        umma_commit(bar_s(sc & 1u));
+      }
+      __syncwarp();
+      return true;
+    };
+    auto next_live = [&](int& n, int& r) {   // advance to the next live step, crossing item boundaries
+      for (;;) {
+        if (++r == nraw) { r = 0; ++n; }
+        if (n >= n_local || bwd_step(r, n & 1, ntiles, N).nq > 0) return;
+      }
+    };
+    int n = 0, r = 0;
+    uint32_t sc = 0, pc = 0, jc = 0;
+    if (n_local > 0) issue_s(0, 0, 0, true);
+    while (n < n_local) {
+      int nn = n, nr = r;
+      next_live(nn, nr);
+      // Look-ahead: S^T / dP^T of the next step go out before this step's P^T is awaited -- unless their tiles have
+      // not landed yet; then they are issued after this step's MMAs.
+      const bool ahead = nn < n_local && issue_s(nn, nr, sc + 1, false);
+      const BwdStep s = bwd_step(r, n & 1, ntiles, N);
+      const uint32_t cb = tmem + (sc & 1u) * 128u;
+      const uint64_t qo = uint64_t((s.i * kTileBytes + s.half * 8192) >> 4);
+      const bool first_of_j = s.ii == 0 && s.half == 0;
+      const bool last_half = s.half == 1 || N <= s.i * TILE + 64;
+      const int nks = s.nq >> 4;
+      int nkv = N - s.j * TILE;
+      nkv = nkv > TILE ? TILE : nkv;
+      const int nkvs = (nkv + 15) >> 4;
+      const uint64_t dsd = mDS0 + uint64_t(((pc & 1u) * 2 * kTileBytes) >> 4);
+      const uint64_t kjd = mK0 + uint64_t((s.j * kTileBytes) >> 4);
+      mbar_wait(bar_p(sc & 1u), (sc >> 1) & 1u);
+      // the accumulators of the previous kv tile (and dQ of the previous item) must have been read out
+      if (first_of_j && jc > 0) mbar_wait(bar_drained, (jc - 1u) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        for (int k = 0; k < nks; ++k) {
+          // P^T / dS^T (bf16) of query slice k sit in columns [16k, 16k + 8) of the S^T / dP^T block
+          const uint32_t acc = (first_of_j && k == 0) ? 0u : 1u;
+          umma_ts(tmem + cDV, cb + 16 * k, mDO0 + qo + uint64_t(k * 128), idesc_ts, acc);
+          umma_ts(tmem + cDK, cb + 64 + 16 * k, mQ0 + qo + uint64_t(k * 128), idesc_ts, acc);
+        }
+        if (last_half) {
+          for (int k = 0; k < nkvs; ++k)
+            umma_ss(tmem + cDQ + s.i * 64, dsd + uint64_t(k * 128), kjd + uint64_t(k * 128), idesc_dq, (s.j | k) != 0);
+          umma_commit(bar_dq(pc & 1u));
+          if (s.j == ntiles - 1) umma_commit(bar_free(2 + s.i));   // last kv tile: Q_i / dO_i are done
+          if (s.ii == ntiles - 1) {                                 // last pair of this kv tile
+            umma_commit(bar_free(s.j));
+            umma_commit(bar_acc);
+          }
+        }
+      }
+      __syncwarp();
+      if (last_half) {
+        ++pc;
+        if (s.ii == ntiles - 1) ++jc;
+      }
+      if (nn < n_local && !ahead) issue_s(nn, nr, sc + 1, true);
+      n = nn; r = nr; ++sc;
+    }
+  } else {
+    // ================================ compute ================================
+    const int qd = warp & 3, hq = warp >> 2;     // TMEM lane quarter, 16-column slice of the step's 64 query columns
+    const int t = qd * 32 + lane;                // kv row within the tile (= TMEM lane)
     const uint32_t trow = tmem + (uint32_t(qd * 32) << 16);
     const float c = p.scale * kLog2e;
-    uint32_t ph = 0, acc_ph = 0;
-    for (int j = 0; j < ntiles; ++j) {
-      const int kv = j * TILE + t;
-      const bool kv_ok = kv < N;
-      const bool warp_live = j * TILE + qd * 32 < N;   // any valid kv row in this warp (warp-uniform)
-      for (int i = 0; i < ntiles; ++i) {
-        mbar_wait(bar_s, ph);
+    uint32_t sc = 0, pc = 0, accn = 0;
+    // deferred read-out of dV_j / dK_j (/ dQ): done after the NEXT step's P^T so the issuer never waits for it
+    bool pend = false;
+    int pend_row0 = 0, pend_h = 0, pend_j = 0;
+    auto store16 = [&](bf16* dst, const uint32_t (&v)[16]) {
+      uint4 u0, u1;
+      u0.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+      u0.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+      u0.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]));
+      u0.w = pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+      u1.x = pack_bf16x2(__uint_as_float(v[8]), __uint_as_float(v[9]));
+      u1.y = pack_bf16x2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+      u1.z = pack_bf16x2(__uint_as_float(v[12]), __uint_as_float(v[13]));
+      u1.w = pack_bf16x2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+      reinterpret_cast<uint4*>(dst)[0] = u0;
+      reinterpret_cast<uint4*>(dst)[1] = u1;
+    };
+    auto drain = [&]() {
+      mbar_wait(bar_acc, accn & 1u);
+      ++accn;
+      tc_fence_after();
+      const int kv = pend_j * TILE + t;
+      uint32_t a[16], bq[16];
+      tmem_ld16(trow + cDV + hq * 16, a);
+      tmem_ld16(trow + cDK + hq * 16, bq);
+      tmem_ld_wait();
+      if (kv < N) {
+        bf16* dst = p.dqkv + size_t(pend_row0 + kv) * 3 * D + pend_h * DH + hq * 16;
+        store16(dst + 2 * D, a);
+        store16(dst + D, bq);
+      }
+      if (pend_j == ntiles - 1) {
+        tmem_ld16(trow + cDQ + hq * 16, a);
+        if (ntiles == 2) tmem_ld16(trow + cDQ + 64 + hq * 16, bq);
+        tmem_ld_wait();
+        if (t < N) store16(p.dqkv + size_t(pend_row0 + t) * 3 * D + pend_h * DH + hq * 16, a);
+        if (ntiles == 2 && TILE + t < N) store16(p.dqkv + size_t(pend_row0 + TILE + t) * 3 * D + pend_h * DH + hq * 16, bq);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_drained);
+      pend = false;
+    };
+    for (int n = 0; n < n_local; ++n) {
+      const int item = int(blockIdx.x) + n * int(gridDim.x);
+      const int b = item / p.H, h = item - b * p.H;
+      const int row0 = b * N;
+      const uint32_t tab = sStat + (n & 1) * 2048;
+      mbar_wait(bar_stat(n & 1), (n >> 1) & 1);
+      for (int r = 0; r < nraw; ++r) {
+        const BwdStep s = bwd_step(r, n & 1, ntiles, N);
+        if (s.nq == 0) continue;
+        const int kvb = s.j * TILE + qd * 32;              // first kv row of this warp
+        const bool warp_live = kvb < N;                    // any valid kv row in this warp (warp-uniform)
+        const bool partial = kvb + 32 > N;                 // some rows of the warp are past the end
+        const uint32_t cb = trow + (sc & 1u) * 128u;
+        mbar_wait(bar_s(sc & 1u), (sc >> 1) & 1u);
         tc_fence_after();
-        for (int cc = 0; cc < 2; ++cc) {  // this warp's two 32-column chunks of the 128 query columns
-          const int ch = hf * 2 + cc;
-          const bool chunk_live = warp_live && (i * TILE + ch * 32 < N);
-          uint32_t pp[16], ds[16];
-          if (chunk_live) {
-            uint32_t sv[32], dv[32];
-            tmem_ld32(trow + cST + ch * 32, sv);
-            tmem_ld32(trow + cDPT + ch * 32, dv);
-            tmem_ld_wait();
+        // the dS smem buffer of this pair was last read by the dQ MMAs of pair pc-2
+        if (s.half == 0 && pc >= 2) mbar_wait(bar_dq(pc & 1u), ((pc >> 1) - 1u) & 1u);
+        if (warp_live && hq * 16 < s.nq) {
+          uint32_t sv[16], dv[16], pp[8], ds[8];
+          tmem_ld16(cb + hq * 16, sv);
+          tmem_ld16(cb + 64 + hq * 16, dv);
+          const uint32_t qa = tab + 4u * uint32_t(s.i * TILE + s.half * 64 + hq * 16);
+          float l2[16], dl[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int q0 = i * TILE + ch * 32 + 2 * e;
-              float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), c, -lse2[q0]));
-              float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), c, -lse2[q0 + 1]));
-              p0 = (kv_ok && q0 < N) ? p0 : 0.f;
-              p1 = (kv_ok && q0 + 1 < N) ? p1 : 0.f;
-              const float d0 = p0 * (__uint_as_float(dv[2 * e]) - delta[q0]) * p.scale;
-              const float d1 = p1 * (__uint_as_float(dv[2 * e + 1]) - delta[q0 + 1]) * p.scale;
-              pp[e] = pack_bf16x2(p0, p1);
-              ds[e] = pack_bf16x2(d0, d1);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) { pp[e] = 0u; ds[e] = 0u; }
+          for (int e = 0; e < 4; ++e) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(l2[4 * e]), "=f"(l2[4 * e + 1]), "=f"(l2[4 * e + 2]), "=f"(l2[4 * e + 3]) : "r"(qa + 16u * e));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dl[4 * e]), "=f"(dl[4 * e + 1]), "=f"(dl[4 * e + 2]), "=f"(dl[4 * e + 3]) : "r"(qa + 1024u + 16u * e));
           }
-          // PT / dST (bf16) alias the ST / dPT columns.  Chunk ch writes columns [16ch, 16ch+16): for hf = 1 those
-          // are columns 32..63 = fp32 chunk 1 of the OTHER warp half -> order the two halves with a named barrier.
-          if (cc == 0 && hf == 1) asm volatile("bar.sync 2, 256;" ::: "memory");
-          tmem_st16(trow + cST + ch * 16, pp);
-          tmem_st16(trow + cDPT + ch * 16, ds);
-          if (cc == 1 && hf == 0) { tmem_st_wait(); asm volatile("bar.arrive 2, 256;" ::: "memory"); }
-          // dS^T row of this kv index into the MN-major smem operand: 32 q values = 4 x 16 B
-          const uint32_t rbase = sDS + (ch >> 1) * kTileBytes + (t >> 3) * 1024 + (t & 7) * 128;
+          tmem_ld_wait();
+          const bool row_ok = !partial || (kvb + lane < N);
 #pragma unroll
-          for (int piece = 0; piece < 4; ++piece) {
-            const uint32_t idx = uint32_t((ch & 1) * 4 + piece);
+          for (int e = 0; e < 8; ++e) {
+            // query columns past the end have lse = +inf -> p = 0 exactly; kv rows past the end are zeroed below
+            float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * e]), c, -l2[2 * e]));
+            float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * e + 1]), c, -l2[2 * e + 1]));
+            float d0 = p0 * fmaf(__uint_as_float(dv[2 * e]), p.scale, -dl[2 * e]);
+            float d1 = p1 * fmaf(__uint_as_float(dv[2 * e + 1]), p.scale, -dl[2 * e + 1]);
+            pp[e] = pack_bf16x2(p0, p1);
+            ds[e] = pack_bf16x2(d0, d1);
+          }
+          if (partial && !row_ok) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { pp[e] = 0u; ds[e] = 0u; }
+          }
+          // P^T / dS^T (bf16) go back into the first 8 of the 16 columns this warp alone has just read
+          tmem_st8(cb + hq * 16, pp);
+          tmem_st8(cb + 64 + hq * 16, ds);
+          // dS^T row of this kv index into the MN-major smem operand of dQ: 16 q values = 2 x 16 B
+          const uint32_t rbase = sDS + (pc & 1u) * 2 * kTileBytes + s.half * kTileBytes + (t >> 3) * 1024 + (t & 7) * 128;
+#pragma unroll
+          for (int piece = 0; piece < 2; ++piece) {
+            const uint32_t idx = uint32_t(hq * 2 + piece);
             const uint32_t a = rbase + ((idx ^ uint32_t(t & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(ds[4 * piece]), "r"(ds[4 * piece + 1]),
                          "r"(ds[4 * piece + 2]), "r"(ds[4 * piece + 3])
                          : "memory");
           }
+          tmem_st_wait();
+          fence_proxy_async_smem();
         }
-        tmem_st_wait();
-        fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(bar_p);
-        ph ^= 1u;
-      }
-      // ---- dV_j, dK_j complete: each warp half writes 32 of the 64 head-dim columns
-      mbar_wait(bar_acc, acc_ph);
-      acc_ph ^= 1u;
-      tc_fence_after();
-      uint32_t v[32];
-      auto store32 = [&](bf16* dst) {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(v[8 * jj + 0]), __uint_as_float(v[8 * jj + 1]));
-          u.y = pack_bf16x2(__uint_as_float(v[8 * jj + 2]), __uint_as_float(v[8 * jj + 3]));
-          u.z = pack_bf16x2(__uint_as_float(v[8 * jj + 4]), __uint_as_float(v[8 * jj + 5]));
-          u.w = pack_bf16x2(__uint_as_float(v[8 * jj + 6]), __uint_as_float(v[8 * jj + 7]));
-          reinterpret_cast<uint4*>(dst)[jj] = u;
-        }
-      };
-      tmem_ld32(trow + cDV + hf * 32, v);
-      tmem_ld_wait();
-      if (kv_ok) store32(p.dqkv + size_t(row0 + kv) * 3 * D + 2 * D + h * DH + hf * 32);
-      tmem_ld32(trow + cDK + hf * 32, v);
-      tmem_ld_wait();
-      if (kv_ok) store32(p.dqkv + size_t(row0 + kv) * 3 * D + D + h * DH + hf * 32);
-      if (j == ntiles - 1) {
-        for (int i = 0; i < ntiles; ++i) {
-          const int qr = i * TILE + t;
-          tmem_ld32(trow + cDQ + i * 64 + hf * 32, v);
-          tmem_ld_wait();
-          if (qr < N) store32(p.dqkv + size_t(row0 + qr) * 3 * D + h * DH + hf * 32);
+        mbar_arrive(bar_p(sc & 1u));
+        ++sc;
+        if (pend) drain();
+        const bool last_half = s.half == 1 || N <= s.i * TILE + 64;
+        if (last_half) {
+          ++pc;
+          if (s.ii == ntiles - 1) { pend = true; pend_row0 = row0; pend_h = h; pend_j = s.j; }
         }
       }
-      tc_fence_before();
+      mbar_arrive(bar_statfree(n & 1));
     }
+    if (pend) drain();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kBwdComputeWarps) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -419,6 +592,9 @@ int fill_params(const ngu_attn_desc& d, AttnTcParams& p, bool bwd) {
   if ((rc = make_tmap_2d_bf16(&p.tmQKV, d.q, uint64_t(d.B) * d.N, 3 * D, 3 * D, TILE, DH, true))) return rc;
   if (bwd) {
     if ((rc = make_tmap_2d_bf16(&p.tmDO, d.d_o, uint64_t(d.B) * d.N, D, D, TILE, DH, true))) return rc;
+    const int rows1 = d.N > TILE ? ((d.N - TILE + 15) & ~15) : TILE;
+    if ((rc = make_tmap_2d_bf16(&p.tmQKV1, d.q, uint64_t(d.B) * d.N, 3 * D, 3 * D, rows1, DH, true))) return rc;
+    if ((rc = make_tmap_2d_bf16(&p.tmDO1, d.d_o, uint64_t(d.B) * d.N, D, D, rows1, DH, true))) return rc;
   } else {
     p.tmDO = p.tmQKV;
   }
@@ -466,7 +642,8 @@ int attn_bwd_tc(const ngu_attn_desc& d, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e, "attn_bwd_tc attr");
     attr = true;
   }
-  attn_bwd_tc_kernel<<<d.B * d.H, kBwdThreads, kBwdSmem, st>>>(p);
+  const int items = d.B * d.H;
+  attn_bwd_tc_kernel<<<items < sm_count() ? items : sm_count(), kBwdThreads, kBwdSmem, st>>>(p);
   return check_launch("attn_bwd_tc");
 }
 

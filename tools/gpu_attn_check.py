@@ -9,7 +9,7 @@ def rel(a, b):
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).abs().max() / b.abs().max())
 
-for (B, N, H) in [(2, 197, 12), (3, 77, 12), (1, 128, 2), (2, 256, 3), (5, 130, 1)]:
+for (B, N, H) in [(2, 197, 12), (3, 77, 12), (1, 128, 2), (2, 256, 3), (5, 130, 1), (3, 64, 2), (2, 16, 1), (4, 65, 3), (2, 192, 2), (3, 193, 2), (30, 197, 12), (40, 77, 12), (70, 208, 5)]:
     torch.manual_seed(0)
     dh, D = 64, H * 64
     qkv = torch.randn(B * N, 3 * D).to(dev, torch.bfloat16)

@@ -58,16 +58,21 @@ NGU_DEVINL void st_row_bf16(bf16* dst, const float (&v)[64]) {
 // =====================================================================================================
 // forward
 // =====================================================================================================
-constexpr int kFwdThreads = 32 * 5;  // 4 softmax warps (one query row per thread) + 1 control warp
-constexpr int kFwdSmem = 5 * kTileBytes + 1024 + 1024;  // Q tile + K (2 tiles) + V (2 tiles)
+constexpr int kFwdSoftmaxWarps = 8;
+constexpr int kFwdThreads = 32 * (kFwdSoftmaxWarps + 1);  // 8 softmax warps (two threads per query row) + 1 control warp
+constexpr int kFwdSmem = 5 * kTileBytes + 2048 + 1024 + 1024;  // Q tile + K (2 tiles) + V (2 tiles) + pair-exchange floats
 
-// One CTA per (batch, head, 128-row query tile); 256 TMEM columns and ~82 KB smem so two CTAs share an SM and
-// overlap each other's load / MMA / softmax phases.
+// One CTA per (batch, head, 128-row query tile); 256 TMEM columns and ~83 KB smem so two CTAs share an SM and
+// overlap each other's load / MMA / softmax phases.  Softmax: warps w and w+4 share TMEM lane quarter w&3 and split
+// the kv columns of a row (32-column chunks [0, nc0) and [nc0, nch)); row max and row sum are exchanged through smem.
+// P (bf16) aliases the S columns, so every thread keeps its P values in registers until BOTH threads of the row have
+// finished reading S.
 __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = base + kTileBytes, sV = base + 3 * kTileBytes;
-  const uint32_t sBar = base + 5 * kTileBytes;
+  const uint32_t sRed = base + 5 * kTileBytes;       // max [2 halves][128 rows], sum [2][128] fp32
+  const uint32_t sBar = sRed + 2048;
   const uint32_t bar_kv = sBar, bar_q = sBar + 8, bar_s = sBar + 16, bar_p = sBar + 24, bar_o = sBar + 32;
   const uint32_t sTmem = sBar + 40;
 
@@ -85,11 +90,11 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
     mbar_init(bar_kv, 1);
     mbar_init(bar_q, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, 32 * kFwdSoftmaxWarps);
     mbar_init(bar_o, 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == kFwdSoftmaxWarps) {
     tmem_alloc(sTmem, 256);
     tmem_relinquish();
   }
@@ -99,8 +104,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(sTmem));
 
-  if (warp == 4) {
-    if (lane == 0) {
+  if (warp == kFwdSoftmaxWarps) {
+    // whole warp walks (warp-uniform values stay in uniform registers); one elected lane issues
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_q, kTileBytes);
       tma_load_2d(sQ, &p.tmQKV, bar_q, h * DH, row0 + t * TILE);
       mbar_arrive_expect_tx(bar_kv, 2 * ntiles * kTileBytes);
@@ -108,85 +114,127 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
         tma_load_2d(sK + u * kTileBytes, &p.tmQKV, bar_kv, D + h * DH, row0 + u * TILE);
         tma_load_2d(sV + u * kTileBytes, &p.tmQKV, bar_kv, 2 * D + h * DH, row0 + u * TILE);
       }
-      // ---- S = Q K^T
-      const uint32_t idesc_s = make_idesc_bf16(TILE, npad);
-      mbar_wait(bar_q, 0);
-      mbar_wait(bar_kv, 0);
-      tc_fence_after();
+    }
+    __syncwarp();
+    // ---- S = Q K^T
+    const uint32_t idesc_s = make_idesc_bf16(TILE, npad);
+    const uint64_t dq = desc_kmajor(sQ), dk = desc_kmajor(sK), dv = desc_mnmajor(sV, 0);
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_kv, 0);
+    tc_fence_after();
+    if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < DH / 16; ++k) umma_ss(tmem, desc_kmajor(sQ + k * 32), desc_kmajor(sK + k * 32), idesc_s, k != 0);
+      for (int k = 0; k < DH / 16; ++k) umma_ss(tmem, dq + uint64_t(k * 2), dk + uint64_t(k * 2), idesc_s, k != 0);
       umma_commit(bar_s);
-      // ---- O = P V   (A = P in TMEM at columns [0, npad/2), D = O at column 128)
-      constexpr uint32_t idesc_o = make_idesc_bf16(TILE, DH, 0, 1);
-      mbar_wait(bar_p, 0);
-      tc_fence_after();
-      for (int j = 0; j < npad / 16; ++j) umma_ts(tmem + 128, tmem + j * 8, desc_mnmajor(sV + j * 2048, 0), idesc_o, j != 0);
+    }
+    __syncwarp();
+    // ---- O = P V   (A = P in TMEM at columns [0, npad/2), D = O at column 128)
+    constexpr uint32_t idesc_o = make_idesc_bf16(TILE, DH, 0, 1);
+    const int nsl = npad / 16;
+    mbar_wait(bar_p, 0);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) umma_ts_if(j < nsl, tmem + 128, tmem + j * 8, dv + uint64_t(j * 128), idesc_o, j != 0);
       umma_commit(bar_o);
     }
+    __syncwarp();
   } else {
-    const int q = warp;
-    const int r = t * TILE + q * 32 + lane;  // query row within the sequence
+    const int q = warp & 3, hf = warp >> 2;
+    const int rt = q * 32 + lane;              // row within the tile (= TMEM lane)
+    const int r = t * TILE + rt;               // query row within the sequence
+    const bool live = t * TILE + q * 32 < N;   // warp-uniform: any valid query row in this warp (same for both halves)
     const uint32_t trow = tmem + (uint32_t(q * 32) << 16);
     const float c = p.scale * kLog2e;
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
-    const int nchunks = (npad + 31) / 32;
-    float mx = -INFINITY;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      uint32_t v[32];
-      tmem_ld32(trow + ch * 32, v);
-      tmem_ld_wait();
+    const int nch = (npad + 31) / 32;          // 32-column chunks of the kv axis (<= 8)
+    const int nc0 = (nch + 1) / 2;             // half 0: chunks [0, nc0), half 1: [nc0, nch)
+    const int cb = hf ? nc0 : 0, ce = hf ? nch : nc0;
+    const uint32_t my_red = sRed + 4u * uint32_t(hf * 128 + rt), other_red = sRed + 4u * uint32_t((hf ^ 1) * 128 + rt);
+    float sum = 0.f, mx = -INFINITY;
+    if (live) {
+      mbar_wait(bar_s, 0);
+      tc_fence_after();
+      // ---- pass 1: row max over this thread's columns
+      for (int ch = cb; ch < ce; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(trow + ch * 32, v);
+        tmem_ld_wait();
+        if (ch * 32 + 32 <= N) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (ch * 32 + i < N) mx = fmaxf(mx, __uint_as_float(v[i]));
-    }
-    float sum = 0.f;
-    const float mc = mx * c;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      uint32_t v[32];
-      tmem_ld32(trow + ch * 32, v);
-      tmem_ld_wait();
-      uint32_t pk[16];
+          for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+        } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int c0 = ch * 32 + 2 * i;
-        float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, -mc));
-        float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
-        p0 = (c0 < N) ? p0 : 0.f;
-        p1 = (c0 + 1 < N) ? p1 : 0.f;
-        // the PV MMA sees bf16 probabilities: accumulate the same rounded values into the row sum
-        const uint32_t w = pack_bf16x2(p0, p1);
-        const float2 rr = unpack_bf16x2(w);
-        sum += rr.x + rr.y;
-        pk[i] = w;
+          for (int i = 0; i < 32; ++i)
+            if (ch * 32 + i < N) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
       }
-      tmem_st16(trow + ch * 16, pk);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_red), "f"(mx) : "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      float omx;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(omx) : "r"(other_red));
+      mx = fmaxf(mx, omx);
+      const float mc = mx * c;
+      // ---- pass 2: P = exp2(S*c - max*c) kept in registers (bf16 pairs), row sum of this thread's columns
+      uint32_t pk[4][16];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ch = cb + k;
+        if (ch < ce) {
+          uint32_t v[32];
+          tmem_ld32(trow + ch * 32, v);
+          tmem_ld_wait();
+          const bool full = ch * 32 + 32 <= N;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, -mc));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
+            if (!full) {
+              p0 = (ch * 32 + 2 * i < N) ? p0 : 0.f;
+              p1 = (ch * 32 + 2 * i + 1 < N) ? p1 : 0.f;
+            }
+            sum += p0 + p1;
+            pk[k][i] = pack_bf16x2(p0, p1);
+          }
+        }
+      }
+      // both threads of the row are done reading S (and publish their partial sums) before P overwrites it
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_red + 1024u), "f"(sum) : "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      float osum;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(osum) : "r"(other_red + 1024u));
+      sum += osum;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (cb + k < ce) tmem_st16(trow + (cb + k) * 16, pk[k]);
+      tmem_st_wait();
     }
-    tmem_st_wait();
     tc_fence_before();
     mbar_arrive(bar_p);
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    uint32_t ov[64];
-    {
-      uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&ov[0]);
-      uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&ov[32]);
-      tmem_ld32(trow + 128, lo);
-      tmem_ld32(trow + 160, hi);
+    if (live) {
+      mbar_wait(bar_o, 0);
+      tc_fence_after();
+      uint32_t ov[32];
+      tmem_ld32(trow + 128 + hf * 32, ov);
       tmem_ld_wait();
-    }
-    if (r < N) {
-      const float inv = 1.f / sum;
-      float of[64];
+      if (r < N) {
+        const float inv = 1.f / sum;
+        bf16* dst = p.o + size_t(row0 + r) * D + h * DH + hf * 32;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) of[i] = __uint_as_float(ov[i]) * inv;
-      st_row_bf16(p.o + size_t(row0 + r) * D + h * DH, of);
-      if (p.lse) p.lse[(size_t(b) * p.H + h) * N + r] = mx * p.scale + logf(sum);
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(ov[8 * j + 0]) * inv, __uint_as_float(ov[8 * j + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(ov[8 * j + 2]) * inv, __uint_as_float(ov[8 * j + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(ov[8 * j + 4]) * inv, __uint_as_float(ov[8 * j + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(ov[8 * j + 6]) * inv, __uint_as_float(ov[8 * j + 7]) * inv);
+          reinterpret_cast<uint4*>(dst)[j] = u;
+        }
+        if (p.lse && hf == 0) p.lse[(size_t(b) * p.H + h) * N + r] = mx * p.scale + logf(sum);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kFwdSoftmaxWarps) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
@@ -226,6 +274,157 @@ NGU_DEVINL BwdStep bwd_step(int r, int par, int ntiles, int N) {
   return s;
 }
 
+#ifdef NGU_ATTN_TRACE
+__device__ unsigned long long g_attn_trace[3 * 4096 + 8];
+NGU_DEVINL void trace_ev(int code, unsigned a) {
+  if (blockIdx.x != 0) return;
+  const unsigned long long i = atomicAdd(&g_attn_trace[0], 1ull);
+  if (i < 4096) { g_attn_trace[8 + 3 * i] = code; g_attn_trace[9 + 3 * i] = a; g_attn_trace[10 + 3 * i] = clock64(); }
+}
+#define TRACE(code, a) do { if ((threadIdx.x & 31) == 0) trace_ev(code, a); } while (0)
+#else
+#define TRACE(code, a) do {} while (0)
+#endif
+
+// ---- MMA issuer of the backward kernel.  This single warp paces the whole CTA, so its per-step instruction count is
+// what matters: the step sequence of an item is unrolled at compile time (kv tile, query tile, half and all smem
+// descriptor offsets are constants; only the live query width of the last tile is a run-time value).
+template <int NT>
+struct BwdIssuer {
+  static constexpr int kRaw = 2 * NT * NT;
+  __host__ __device__ static constexpr int sj(int r) { return NT == 2 ? r >> 2 : 0; }
+  __host__ __device__ static constexpr int sii(int r) { return NT == 2 ? (r >> 1) & 1 : 0; }
+  __host__ __device__ static constexpr int si(int r, int par) { return NT == 2 ? (sii(r) ^ sj(r) ^ par) : 0; }
+  __host__ __device__ static constexpr int sh(int r) { return r & 1; }
+
+  uint32_t tmem, sBar;
+  int n_local;
+  int nq[2][2];     // [query tile][half]: live columns padded to 16 (0 = dead step)
+  int nkvs[2];      // [kv tile]: ceil16(live kv rows) / 16
+  uint64_t dQ0, dK0, dV0, dDO0, mQ0, mK0, mDO0, mDS0;
+  uint32_t sc_s = 0, sc_m = 0, pc = 0, jc = 0;
+
+  NGU_DEVINL uint32_t bar_full(int g) const { return sBar + 8u * g; }
+  NGU_DEVINL uint32_t bar_free(int g) const { return sBar + 32u + 8u * g; }
+  NGU_DEVINL uint32_t bar_s(uint32_t b) const { return sBar + 64u + 8u * b; }
+  NGU_DEVINL uint32_t bar_p(uint32_t b) const { return sBar + 80u + 8u * b; }
+  NGU_DEVINL uint32_t bar_dq(uint32_t b) const { return sBar + 96u + 8u * b; }
+  NGU_DEVINL uint32_t bar_acc() const { return sBar + 144u; }
+  NGU_DEVINL uint32_t bar_drained() const { return sBar + 152u; }
+
+  // S^T = K_j Q_{i,half}^T and dP^T = V_j dO_{i,half}^T into the next TMEM buffer
+  template <int R, int PAR>
+  NGU_DEVINL void issue_s(int n) {
+    constexpr int j = sj(R), i = si(R, PAR), half = sh(R);
+    const uint32_t ph = uint32_t(n) & 1u;
+    if constexpr (R == 0) { mbar_wait(bar_full(0), ph); mbar_wait(bar_full(2 + i), ph); }   // first use of K0/V0, Q_i/dO_i
+    if constexpr (NT == 2 && R == 2) mbar_wait(bar_full(2 + i), ph);                        // first use of the other Q/dO
+    if constexpr (NT == 2 && R == 4) mbar_wait(bar_full(1), ph);                            // first use of K1/V1
+    TRACE(10, sc_s);
+    tc_fence_after();
+    const uint32_t cb = tmem + (sc_s & 1u) * 128u;
+    const uint32_t idesc_st = make_idesc_bf16(TILE, nq[i][half]);
+    constexpr uint64_t qo = uint64_t((i * kTileBytes + half * 8192) >> 4), ko = uint64_t((j * kTileBytes) >> 4);
+    if (elect_one()) {
+      // the two accumulation chains are interleaved: consecutive MMAs into the same accumulator are latency-bound
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k) {
+        umma_ss(cb, dK0 + (ko + 2 * k), dQ0 + (qo + 2 * k), idesc_st, k != 0);
+        umma_ss(cb + 64, dV0 + (ko + 2 * k), dDO0 + (qo + 2 * k), idesc_st, k != 0);
+      }
+      umma_commit(bar_s(sc_s & 1u));
+    }
+    __syncwarp();
+    TRACE(11, sc_s);
+    ++sc_s;
+  }
+
+  // S^T / dP^T of the first live step at or after R.  Crossing into the next item happens BEFORE this step's P^T is
+  // awaited when NT == 2 (its tiles were released at least one pair ago) and AFTER this step's MMAs when NT == 1
+  // (its tiles are released by exactly those MMAs).
+  template <int R, int PAR>
+  NGU_DEVINL void lookahead(int n, bool before) {
+    if constexpr (R < kRaw) {
+      if (nq[si(R, PAR)][sh(R)] > 0) {
+        if (before) issue_s<R, PAR>(n);
+      } else {
+        lookahead<R + 1, PAR>(n, before);
+      }
+    } else {
+      if (((NT == 2) == before) && n + 1 < n_local) issue_s<0, PAR ^ 1>(n + 1);
+    }
+  }
+
+  // dV_j += P^T dO, dK_j += dS^T Q (A from TMEM), and after the pair's last half dQ_i += dS K_j (A = dS^T in smem)
+  template <int R, int PAR>
+  NGU_DEVINL void mma(int n) {
+    constexpr int j = sj(R), ii = sii(R), i = si(R, PAR), half = sh(R);
+    constexpr bool first_of_j = ii == 0 && half == 0;
+    constexpr uint32_t idesc_ts = make_idesc_bf16(TILE, DH, 0, 1);
+    constexpr uint32_t idesc_dq = make_idesc_bf16(TILE, DH, 1, 1);
+    constexpr uint64_t qo = uint64_t((i * kTileBytes + half * 8192) >> 4), ko = uint64_t((j * kTileBytes) >> 4);
+    const uint32_t cb = tmem + (sc_m & 1u) * 128u;
+    const int nks = nq[i][half] >> 4;
+    const bool last_half = half == 1 || nq[i][1] == 0;
+    TRACE(20, sc_m);
+    mbar_wait(bar_p(sc_m & 1u), (sc_m >> 1) & 1u);
+    TRACE(21, sc_m);
+    // the accumulators of the previous kv tile (and dQ of the previous item) must have been read out
+    if constexpr (first_of_j) { if (jc > 0) mbar_wait(bar_drained(), (jc - 1u) & 1u); }
+    tc_fence_after();
+    if (elect_one()) {
+      const uint64_t dsd = mDS0 + uint64_t(((pc & 1u) * 2 * kTileBytes) >> 4);
+      const int nk = last_half ? nkvs[j] : 0;
+      // three accumulation chains (dV, dK, dQ) interleaved: consecutive MMAs into one accumulator are latency-bound
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // P^T / dS^T (bf16) of query slice k sit in columns [16k, 16k + 8) of the S^T / dP^T block
+        umma_ts_if(k < nks, tmem + 256, cb + 16 * k, mDO0 + (qo + 128 * k), idesc_ts, (first_of_j && k == 0) ? 0u : 1u);
+        umma_ts_if(k < nks, tmem + 320, cb + 64 + 16 * k, mQ0 + (qo + 128 * k), idesc_ts, (first_of_j && k == 0) ? 0u : 1u);
+        umma_ss_if(2 * k < nk, tmem + 384 + i * 64, dsd + 128 * (2 * k), mK0 + (ko + 128 * (2 * k)), idesc_dq, (j | k) != 0 ? 1u : 0u);
+        umma_ss_if(2 * k + 1 < nk, tmem + 384 + i * 64, dsd + 128 * (2 * k + 1), mK0 + (ko + 128 * (2 * k + 1)), idesc_dq, 1u);
+      }
+      if (last_half) {
+        umma_commit(bar_dq(pc & 1u));
+        if constexpr (j == NT - 1) umma_commit(bar_free(2 + i));   // last kv tile: Q_i / dO_i are done
+        if constexpr (ii == NT - 1) {                              // last pair of this kv tile
+          umma_commit(bar_free(j));
+          umma_commit(bar_acc());
+        }
+      }
+    }
+    __syncwarp();
+    TRACE(22, sc_m);
+    ++sc_m;
+    if (last_half) {
+      ++pc;
+      if constexpr (ii == NT - 1) ++jc;
+    }
+  }
+
+  template <int R, int PAR>
+  NGU_DEVINL void steps(int n) {
+    if constexpr (R < kRaw) {
+      if (nq[si(R, PAR)][sh(R)] > 0) {
+        lookahead<R + 1, PAR>(n, true);
+        mma<R, PAR>(n);
+        lookahead<R + 1, PAR>(n, false);
+      }
+      steps<R + 1, PAR>(n);
+    }
+  }
+
+  NGU_DEVINL void run() {
+    if (n_local > 0) issue_s<0, 0>(0);
+    for (int n = 0; n < n_local; n += 2) {
+      steps<0, 0>(n);
+      if (n + 1 < n_local) steps<0, 1>(n + 1);
+    }
+  }
+};
+
+
+template <int NT>
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -247,8 +446,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.N, D = p.H * DH;
-  const int ntiles = (N + TILE - 1) / TILE;
-  const int nraw = ntiles * ntiles * 2;
+  constexpr int ntiles = NT;
+  constexpr int nraw = ntiles * ntiles * 2;
   const int items = p.B * p.H;
   const int n_local = (items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
   const int rows1 = ntiles == 2 ? ((N - TILE + 15) & ~15) : 0;   // rows of the second tile that are fetched
@@ -353,99 +552,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     }
   } else if (warp == kBwdComputeWarps) {
     // ================================ MMA issuer ================================
-    // The whole warp walks the loop so that every value is warp-uniform (uniform registers, no per-lane waterfall
-    // around the tcgen05 instructions); one elected lane issues.  This warp is the pacemaker of the kernel: keep
-    // its instruction count small.
-    constexpr uint32_t idesc_ts = make_idesc_bf16(TILE, DH, 0, 1);      // dV / dK: A in TMEM, B MN-major
-    constexpr uint32_t idesc_dq = make_idesc_bf16(TILE, DH, 1, 1);      // dQ: A MN-major (smem), B MN-major
-    const uint64_t dQ0 = desc_kmajor(sQ), dK0 = desc_kmajor(sK), dV0 = desc_kmajor(sV), dDO0 = desc_kmajor(sDO);
-    const uint64_t mQ0 = desc_mnmajor(sQ, 0), mK0 = desc_mnmajor(sK, 0), mDO0 = desc_mnmajor(sDO, 0);
-    const uint64_t mDS0 = desc_mnmajor(sDS, kTileBytes);
-    int w_item = -1;
-    uint32_t w_mask = 0;   // tile groups of item w_item whose full barrier has been observed
-    auto groups_of = [&](const BwdStep& s) { return (1u << s.j) | (1u << (2 + s.i)); };
-    auto issue_s = [&](int n, int r, uint32_t sc, bool blocking) -> bool {
-      const BwdStep s = bwd_step(r, n & 1, ntiles, N);
-      if (n != w_item) { w_item = n; w_mask = 0; }
-      uint32_t need = groups_of(s) & ~w_mask;
-      if (need) {
-        for (int g = 0; g < 4; ++g) {
-          if (!((need >> g) & 1u)) continue;
-          if (blocking) mbar_wait(bar_full(g), n & 1);
-          else if (!__all_sync(0xffffffffu, mbar_try_wait(bar_full(g), n & 1))) return false;
-          w_mask |= 1u << g;
-        }
+    BwdIssuer<NT> is;
+    is.tmem = tmem;
+    is.sBar = sBar;
+    is.n_local = n_local;
+    for (int i = 0; i < 2; ++i)
+      for (int hh = 0; hh < 2; ++hh) {
+        int live = N - (i * TILE + hh * 64);
+        live = live < 0 ? 0 : (live > 64 ? 64 : live);
+        is.nq[i][hh] = (live + 15) & ~15;
       }
-      tc_fence_after();
-      const uint32_t cb = tmem + (sc & 1u) * 128u;
-      const uint32_t idesc_st = make_idesc_bf16(TILE, s.nq);             // S^T / dP^T: K-major x K-major
-      const uint64_t qo = uint64_t((s.i * kTileBytes + s.half * 8192) >> 4), ko = uint64_t((s.j * kTileBytes) >> 4);
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_ss(cb, dK0 + ko + uint64_t(k * 2), dQ0 + qo + uint64_t(k * 2), idesc_st, k != 0);
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_ss(cb + 64, dV0 + ko + uint64_t(k * 2), dDO0 + qo + uint64_t(k * 2), idesc_st, k != 0);
-        umma_commit(bar_s(sc & 1u));
-      }
-      __syncwarp();
-      return true;
-    };
-    auto next_live = [&](int& n, int& r) {   // advance to the next live step, crossing item boundaries
-      for (;;) {
-        if (++r == nraw) { r = 0; ++n; }
-        if (n >= n_local || bwd_step(r, n & 1, ntiles, N).nq > 0) return;
-      }
-    };
-    int n = 0, r = 0;
-    uint32_t sc = 0, pc = 0, jc = 0;
-    if (n_local > 0) issue_s(0, 0, 0, true);
-    while (n < n_local) {
-      int nn = n, nr = r;
-      next_live(nn, nr);
-      // Look-ahead: S^T / dP^T of the next step go out before this step's P^T is awaited -- unless their tiles have
-      // not landed yet; then they are issued after this step's MMAs.
-      const bool ahead = nn < n_local && issue_s(nn, nr, sc + 1, false);
-      const BwdStep s = bwd_step(r, n & 1, ntiles, N);
-      const uint32_t cb = tmem + (sc & 1u) * 128u;
-      const uint64_t qo = uint64_t((s.i * kTileBytes + s.half * 8192) >> 4);
-      const bool first_of_j = s.ii == 0 && s.half == 0;
-      const bool last_half = s.half == 1 || N <= s.i * TILE + 64;
-      const int nks = s.nq >> 4;
-      int nkv = N - s.j * TILE;
-      nkv = nkv > TILE ? TILE : nkv;
-      const int nkvs = (nkv + 15) >> 4;
-      const uint64_t dsd = mDS0 + uint64_t(((pc & 1u) * 2 * kTileBytes) >> 4);
-      const uint64_t kjd = mK0 + uint64_t((s.j * kTileBytes) >> 4);
-      mbar_wait(bar_p(sc & 1u), (sc >> 1) & 1u);
-      // the accumulators of the previous kv tile (and dQ of the previous item) must have been read out
-      if (first_of_j && jc > 0) mbar_wait(bar_drained, (jc - 1u) & 1u);
-      tc_fence_after();
-      if (elect_one()) {
-        for (int k = 0; k < nks; ++k) {
-          // P^T / dS^T (bf16) of query slice k sit in columns [16k, 16k + 8) of the S^T / dP^T block
-          const uint32_t acc = (first_of_j && k == 0) ? 0u : 1u;
-          umma_ts(tmem + cDV, cb + 16 * k, mDO0 + qo + uint64_t(k * 128), idesc_ts, acc);
-          umma_ts(tmem + cDK, cb + 64 + 16 * k, mQ0 + qo + uint64_t(k * 128), idesc_ts, acc);
-        }
-        if (last_half) {
-          for (int k = 0; k < nkvs; ++k)
-            umma_ss(tmem + cDQ + s.i * 64, dsd + uint64_t(k * 128), kjd + uint64_t(k * 128), idesc_dq, (s.j | k) != 0);
-          umma_commit(bar_dq(pc & 1u));
-          if (s.j == ntiles - 1) umma_commit(bar_free(2 + s.i));   // last kv tile: Q_i / dO_i are done
-          if (s.ii == ntiles - 1) {                                 // last pair of this kv tile
-            umma_commit(bar_free(s.j));
-            umma_commit(bar_acc);
-          }
-        }
-      }
-      __syncwarp();
-      if (last_half) {
-        ++pc;
-        if (s.ii == ntiles - 1) ++jc;
-      }
-      if (nn < n_local && !ahead) issue_s(nn, nr, sc + 1, true);
-      n = nn; r = nr; ++sc;
+    for (int j = 0; j < 2; ++j) {
+      int nkv = N - j * TILE;
+      nkv = nkv < 0 ? 0 : (nkv > TILE ? TILE : nkv);
+      is.nkvs[j] = (nkv + 15) >> 4;
     }
+    is.dQ0 = desc_kmajor(sQ); is.dK0 = desc_kmajor(sK); is.dV0 = desc_kmajor(sV); is.dDO0 = desc_kmajor(sDO);
+    is.mQ0 = desc_mnmajor(sQ, 0); is.mK0 = desc_mnmajor(sK, 0); is.mDO0 = desc_mnmajor(sDO, 0);
+    is.mDS0 = desc_mnmajor(sDS, kTileBytes);
+    is.run();
   } else {
     // ================================ compute ================================
     const int qd = warp & 3, hq = warp >> 2;     // TMEM lane quarter, 16-column slice of the step's 64 query columns
@@ -507,7 +632,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
         const bool warp_live = kvb < N;                    // any valid kv row in this warp (warp-uniform)
         const bool partial = kvb + 32 > N;                 // some rows of the warp are past the end
         const uint32_t cb = trow + (sc & 1u) * 128u;
+        if (warp == 0) TRACE(30, sc);
         mbar_wait(bar_s(sc & 1u), (sc >> 1) & 1u);
+        if (warp == 0) TRACE(31, sc);
         tc_fence_after();
         // the dS smem buffer of this pair was last read by the dQ MMAs of pair pc-2
         if (s.half == 0 && pc >= 2) mbar_wait(bar_dq(pc & 1u), ((pc >> 1) - 1u) & 1u);
@@ -556,8 +683,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
         }
         tc_fence_before();
         mbar_arrive(bar_p(sc & 1u));
+        if (warp == 0) TRACE(32, sc);
         ++sc;
-        if (pend) drain();
+        if (pend) { drain(); if (warp == 0) TRACE(33, sc); }
         const bool last_half = s.half == 1 || N <= s.i * TILE + 64;
         if (last_half) {
           ++pc;
@@ -610,6 +738,13 @@ int fill_params(const ngu_attn_desc& d, AttnTcParams& p, bool bwd) {
 
 }  // namespace
 
+#ifdef NGU_ATTN_TRACE
+extern "C" int ngu_debug_attn_trace(void* out, int reset) {
+  if (reset) { unsigned long long z = 0; return cudaMemcpyToSymbol(g_attn_trace, &z, 8) != cudaSuccess; }
+  return cudaMemcpyFromSymbol(out, g_attn_trace, sizeof(g_attn_trace)) != cudaSuccess;
+}
+#endif
+
 bool attn_tc_supported(const ngu_attn_desc& d, bool bwd) {
   if (d.dtype != NGU_BF16 || d.dh != DH || d.N > 2 * TILE || !is_packed(d)) return false;
   if (bwd) {
@@ -638,12 +773,15 @@ int attn_bwd_tc(const ngu_attn_desc& d, cudaStream_t st) {
   if (int rc = fill_params(d, p, true)) return rc;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
     if (e != cudaSuccess) return cuda_status(e, "attn_bwd_tc attr");
     attr = true;
   }
   const int items = d.B * d.H;
-  attn_bwd_tc_kernel<<<items < sm_count() ? items : sm_count(), kBwdThreads, kBwdSmem, st>>>(p);
+  const int grid = items < sm_count() ? items : sm_count();
+  if (d.N > TILE) attn_bwd_tc_kernel<2><<<grid, kBwdThreads, kBwdSmem, st>>>(p);
+  else attn_bwd_tc_kernel<1><<<grid, kBwdThreads, kBwdSmem, st>>>(p);
   return check_launch("attn_bwd_tc");
 }
 

@@ -1,0 +1,30 @@
+"""Timeline of the attention-backward roles on block 0 (needs the library built with -DNGU_ATTN_TRACE)."""
+import sys, ctypes
+sys.path.insert(0, ".")
+import torch, numpy as np
+from nextgen_uia_b200 import ops, _lib as L
+lib = L.lib()
+dev = torch.device("cuda:0")
+B, N, H, dh = 256, 197, 12, 64
+D = H * dh
+qkv = torch.randn(B * N, 3 * D).to(dev, torch.bfloat16)
+do = torch.randn(B * N, D).to(dev, torch.bfloat16)
+o, lse = ops.attn_fwd_packed(qkv, B, N, H, dh)
+dq = ops.attn_bwd_packed(qkv, o, lse, do, B, N, H, dh)
+torch.cuda.synchronize()
+lib.ngu_debug_attn_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
+lib.ngu_debug_attn_trace(None, 1)
+dq = ops.attn_bwd_packed(qkv, o, lse, do, B, N, H, dh)
+torch.cuda.synchronize()
+buf = np.zeros(3 * 4096 + 8, dtype=np.uint64)
+lib.ngu_debug_attn_trace(buf.ctypes.data, 0)
+n = int(min(buf[0], 4096))
+ev = buf[8:8 + 3 * n].reshape(n, 3).astype(np.int64)
+t0 = ev[:, 2].min()
+names = {10: "S.issue.begin", 11: "S.issued", 20: "M.waitP", 21: "M.Pseen", 22: "M.issued", 30: "C.waitS", 31: "C.Sseen", 32: "C.Parrive", 33: "C.drained"}
+ev = ev[np.argsort(ev[:, 2])]
+lo, hi = int(sys.argv[1]) if len(sys.argv) > 1 else 16, int(sys.argv[2]) if len(sys.argv) > 2 else 34
+for c, a, t in ev:
+    if lo <= a < hi:
+        print(f"{t - t0:8d}  step {a:3d}  {names.get(int(c), c)}")
+print("events", n, "span cycles", int(ev[:, 2].max() - t0))

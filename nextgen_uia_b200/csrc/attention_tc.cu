@@ -15,6 +15,7 @@
 //     dV_j += PT dO_i, dK_j += dST Q_i    (TS, A = PT / dST bf16 in TMEM, B MN-major)
 //     dQ_i += dS K_j                      (SS, A = dST staged in smem as an MN-major operand, B = K_j MN-major)
 //     dV/dK/dQ accumulate in TMEM across the loop and are written once (no atomics).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -25,6 +26,23 @@ constexpr int DH = 64;
 constexpr int TILE = 128;
 constexpr int kTileBytes = TILE * DH * 2;  // 16 KB: 128 rows x 128 B
 constexpr float kLog2e = 1.4426950408889634f;
+
+#ifdef NGU_ATTN_TRACE
+// Per-warp private event slots (no atomics: a returning atomic would stall the traced warp for ~1 us per event).
+// Layout: [warp][256 events][code, arg, clock]
+__device__ unsigned long long g_attn_trace[32 * 256 * 3];
+NGU_DEVINL void trace_ev(uint32_t& n, int code, unsigned a) {
+  if (blockIdx.x != 0 || n >= 256) return;
+  unsigned long long* e = g_attn_trace + (size_t(threadIdx.x >> 5) * 256 + n) * 3;
+  e[0] = code; e[1] = a; e[2] = clock64();
+  ++n;
+}
+#define TRACE_DECL uint32_t tr_n = 0
+#define TRACE(code, a) do { if ((threadIdx.x & 31) == 0) trace_ev(tr_n, code, a); } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(code, a) do {} while (0)
+#endif
 
 struct AttnTcParams {
   CUtensorMap tmQKV;  // [B*N rows, 3*H*64 cols] bf16, box 64 cols x 128 rows, SWIZZLE_128B
@@ -77,6 +95,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
   const uint32_t sTmem = sBar + 40;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TRACE_DECL;
   const int N = p.N, D = p.H * DH;
   const int ntiles = (N + TILE - 1) / TILE;      // 1 or 2
   const int t = blockIdx.x % ntiles;             // query tile of this CTA
@@ -240,6 +259,292 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
   }
 }
 
+
+// ---- persistent forward ---------------------------------------------------------------------------------
+// One CTA per SM walks (batch, head) items; a "unit" is one 128-row query tile of an item.  Roles:
+//   warps 0-7   softmax group 0 (units 0, 2, 4, ...; TMEM slot 0)     warps 8-15  softmax group 1 (odd units; slot 1)
+//               two threads per query row (warps w and w+4 of a group share TMEM lane quarter w&3)
+//   warp 16     MMA issuer: event loop over both groups (S = Q K^T as soon as the slot is drained and the tiles have
+//               landed, O = P V as soon as the group has written P)
+//   warp 17     TMA loader: K/V of item n+1 (double-buffered) and the Q tiles of the next units (4-deep ring)
+// Each group runs its own serial chain (S -> softmax -> P -> O -> store) and the two chains interleave on the SM, as
+// two co-resident CTAs would, but K/V are fetched once per item and nothing is re-initialised between units.
+constexpr int kFwdGroupWarps = 8;
+constexpr int kFwdPThreads = 32 * (2 * kFwdGroupWarps + 2);
+constexpr int kFwdPSmem = 12 * kTileBytes + 2 * 2048 + 1024 + 1024;   // K/V 2 x 4 tiles, Q 4 tiles, exchange, barriers
+
+__global__ void __launch_bounds__(kFwdPThreads, 1) attn_fwd_persistent_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto sK = [&](int buf, int u) { return base + uint32_t(buf * 4 + u) * kTileBytes; };
+  auto sV = [&](int buf, int u) { return base + uint32_t(buf * 4 + 2 + u) * kTileBytes; };
+  auto sQ = [&](int slot) { return base + uint32_t(8 + slot) * kTileBytes; };
+  const uint32_t sRed = base + 12 * kTileBytes;       // per group: max [2 halves][128 rows], sum [2][128] fp32
+  const uint32_t sBar = sRed + 2 * 2048;
+  auto bar_kv = [&](int b) { return sBar + 8u * b; };            // 2: K/V of item parity b landed
+  auto bar_kvfree = [&](int b) { return sBar + 16u + 8u * b; };  // 2: all PV MMAs of that item complete
+  auto bar_q = [&](int s) { return sBar + 32u + 8u * s; };       // 4: Q tile of unit (k & 3) landed
+  auto bar_qfree = [&](int s) { return sBar + 64u + 8u * s; };   // 4: S MMAs of that unit complete
+  auto bar_s = [&](int g) { return sBar + 96u + 8u * g; };       // 2: S of group g's unit complete
+  auto bar_p = [&](int g) { return sBar + 112u + 8u * g; };      // 2: P written (256 arrivals)
+  auto bar_o = [&](int g) { return sBar + 128u + 8u * g; };      // 2: O complete
+  auto bar_drained = [&](int g) { return sBar + 144u + 8u * g; };  // 2: O read out (256 arrivals)
+  const uint32_t sTmem = sBar + 160u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TRACE_DECL;
+  const int N = p.N, D = p.H * DH;
+  const int ntiles = (N + TILE - 1) / TILE;      // 1 or 2
+  const int npad = (N + 15) & ~15;               // MMA N extent over the kv axis
+  const int rows1 = ntiles == 2 ? ((N - TILE + 15) & ~15) : 0;
+  const int items = p.B * p.H;
+  const int n_local = (items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int n_units = n_local * ntiles;
+  constexpr int kGroup = 32 * kFwdGroupWarps;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmQKV);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_kv(b), 1); mbar_init(bar_kvfree(b), 1);
+      mbar_init(bar_s(b), 1); mbar_init(bar_p(b), kGroup); mbar_init(bar_o(b), 1); mbar_init(bar_drained(b), kGroup);
+    }
+    for (int s = 0; s < 4; ++s) { mbar_init(bar_q(s), 1); mbar_init(bar_qfree(s), 1); }
+    fence_mbar_init();
+  }
+  if (warp == 2 * kFwdGroupWarps) {
+    tmem_alloc(sTmem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(sTmem));
+
+  if (warp == 2 * kFwdGroupWarps + 1) {
+    // ================================ TMA loader ================================
+    if (lane == 0) {
+      for (int k = 0; k < n_units; ++k) {
+        const int n = ntiles == 2 ? k >> 1 : k, t = ntiles == 2 ? k & 1 : 0;
+        const int item = int(blockIdx.x) + n * int(gridDim.x);
+        const int b = item / p.H, h = item - b * p.H;
+        const int row0 = b * N;
+        if (t == 0) {
+          const int kb = n & 1;
+          if (n >= 2) mbar_wait(bar_kvfree(kb), uint32_t((n >> 1) - 1) & 1u);
+          mbar_arrive_expect_tx(bar_kv(kb), 2 * kTileBytes + 2 * rows1 * 128);
+          tma_load_2d(sK(kb, 0), &p.tmQKV, bar_kv(kb), D + h * DH, row0);
+          tma_load_2d(sV(kb, 0), &p.tmQKV, bar_kv(kb), 2 * D + h * DH, row0);
+          if (ntiles == 2) {
+            tma_load_2d(sK(kb, 1), &p.tmQKV1, bar_kv(kb), D + h * DH, row0 + TILE);
+            tma_load_2d(sV(kb, 1), &p.tmQKV1, bar_kv(kb), 2 * D + h * DH, row0 + TILE);
+          }
+        }
+        const int qs = k & 3;
+        if (k >= 4) mbar_wait(bar_qfree(qs), uint32_t((k >> 2) - 1) & 1u);
+        mbar_arrive_expect_tx(bar_q(qs), t ? rows1 * 128 : kTileBytes);
+        tma_load_2d(sQ(qs), t ? &p.tmQKV1 : &p.tmQKV, bar_q(qs), h * DH, row0 + t * TILE);
+      }
+    }
+  } else if (warp == 2 * kFwdGroupWarps) {
+    // ================================ MMA issuer ================================
+    // Per group: state 0 = S part A of the next unit not issued, 1 = part B (and the commit) pending, 2 = waiting for P.
+    // TMEM slot layout: S in columns [0, npad), P (bf16) aliases [0, npad/2), O in [192, 256).  S therefore overlaps the
+    // previous unit's O only in columns >= 192: part A (kv columns < 192) is issued right after the previous PV, part B
+    // (kv columns 192..npad, at most 64) once the group has read O out.  Whole warp walks; one lane issues.
+    const int na = npad < 192 ? npad : 192, nb = npad - na;
+    const uint32_t idesc_a = make_idesc_bf16(TILE, na), idesc_b = make_idesc_bf16(TILE, nb > 0 ? nb : 16);
+    constexpr uint32_t idesc_o = make_idesc_bf16(TILE, DH, 0, 1);
+    const int nsl = npad / 16;
+    int unit[2] = {0, 1};
+    int state[2] = {0, 0};
+    int remaining = n_units;      // units whose PV has not been issued yet
+    int pv_issued[2] = {0, 0};    // per K/V buffer: PV MMAs issued for the item it holds (the groups run at their own pace)
+    while (remaining > 0) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int k = unit[g];
+        if (k >= n_units) continue;
+        const int n = ntiles == 2 ? k >> 1 : k;
+        const int kb = n & 1, qs = k & 3;
+        const uint32_t slot = tmem + uint32_t(g) * 256u;
+        if (state[g] == 0) {
+          const bool ready = mbar_try_wait(bar_kv(kb), (n >> 1) & 1) && mbar_try_wait(bar_q(qs), (k >> 2) & 1);
+          if (__all_sync(0xffffffffu, ready)) {
+            tc_fence_after();
+            const uint64_t dq = desc_kmajor(sQ(qs)), dk = desc_kmajor(sK(kb, 0));
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < DH / 16; ++kk) umma_ss(slot, dq + uint64_t(kk * 2), dk + uint64_t(kk * 2), idesc_a, kk != 0);
+              if (nb == 0) { umma_commit(bar_s(g)); umma_commit(bar_qfree(qs)); }
+            }
+            __syncwarp();
+            TRACE(60 + g, k);
+            state[g] = nb == 0 ? 2 : 1;
+          }
+        } else if (state[g] == 1) {
+          const bool ready = k < 2 || mbar_try_wait(bar_drained(g), uint32_t((k >> 1) - 1) & 1u);
+          if (__all_sync(0xffffffffu, ready)) {
+            tc_fence_after();
+            // kv rows 192.. : K tile 1, rows 64.. (8 KB in), S columns 192..
+            const uint64_t dq = desc_kmajor(sQ(qs)), dk = desc_kmajor(sK(kb, 1) + 8192);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < DH / 16; ++kk) umma_ss(slot + 192, dq + uint64_t(kk * 2), dk + uint64_t(kk * 2), idesc_b, kk != 0);
+              umma_commit(bar_s(g));
+              umma_commit(bar_qfree(qs));
+            }
+            __syncwarp();
+            TRACE(64 + g, k);
+            state[g] = 2;
+          }
+        } else {
+          if (__all_sync(0xffffffffu, mbar_try_wait(bar_p(g), (k >> 1) & 1))) {
+            tc_fence_after();
+            const uint64_t dv = desc_mnmajor(sV(kb, 0), 0);
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) umma_ts_if(j < nsl, slot + 192, slot + j * 8, dv + uint64_t(j * 128), idesc_o, j != 0);
+              umma_commit(bar_o(g));
+              if (pv_issued[kb] + 1 == ntiles) umma_commit(bar_kvfree(kb));   // the item's last PV (of either group)
+            }
+            __syncwarp();
+            TRACE(62 + g, k);
+            pv_issued[kb] = (pv_issued[kb] + 1 == ntiles) ? 0 : pv_issued[kb] + 1;
+            state[g] = 0;
+            unit[g] = k + 2;
+            --remaining;
+          }
+        }
+      }
+    }
+  } else {
+    // ================================ softmax groups ================================
+    const int g = warp / kFwdGroupWarps, w = warp % kFwdGroupWarps;
+    const int q = w & 3, hf = w >> 2;
+    const int rt = q * 32 + lane;              // row within the tile (= TMEM lane)
+    const uint32_t trow = tmem + uint32_t(g) * 256u + (uint32_t(q * 32) << 16);
+    const float c = p.scale * kLog2e;
+    const int nch = (npad + 31) / 32;          // 32-column chunks of the kv axis (<= 8)
+    const int nc0 = (nch + 1) / 2;             // half 0: chunks [0, nc0), half 1: [nc0, nch)
+    const int cb = hf ? nc0 : 0, ce = hf ? nch : nc0;
+    const uint32_t red = sRed + uint32_t(g) * 2048u;
+    const uint32_t my_red = red + 4u * uint32_t(hf * 128 + rt), other_red = red + 4u * uint32_t((hf ^ 1) * 128 + rt);
+    const int pair_bar = 1 + g * 4 + q;
+    uint32_t cnt = 0;
+    for (int k = g; k < n_units; k += 2, ++cnt) {
+      const int n = ntiles == 2 ? k >> 1 : k, t = ntiles == 2 ? k & 1 : 0;
+      const int item = int(blockIdx.x) + n * int(gridDim.x);
+      const int b = item / p.H, h = item - b * p.H;
+      const int row0 = b * N;
+      const int r = t * TILE + rt;               // query row within the sequence
+      const bool live = t * TILE + q * 32 < N;   // warp-uniform: any valid query row in this warp (same for both halves)
+      float sum = 0.f, mx = -INFINITY;
+      // dead warps (all rows past the sequence end) skip the math but keep in step with the barriers' phases
+      if (w == 0) TRACE(40 + g, k);
+      mbar_wait(bar_s(g), cnt & 1u);
+      if (w == 0) TRACE(42 + g, k);
+      tc_fence_after();
+      if (live) {
+        // ---- pass 1: row max over this thread's columns (four independent running maxima)
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int ch = cb; ch < ce; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(trow + ch * 32, v);
+          tmem_ld_wait();
+          if (ch * 32 + 32 <= N) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) m4[e] = fmaxf(m4[e], fmaxf(__uint_as_float(v[i + 2 * e]), __uint_as_float(v[i + 2 * e + 1])));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (ch * 32 + i < N) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+          }
+        }
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        if (w == 0) TRACE(44 + g, k);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_red), "f"(mx) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        float omx;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(omx) : "r"(other_red));
+        mx = fmaxf(mx, omx);
+        const float mc = mx * c;
+        // ---- pass 2: P = exp2(S*c - max*c) kept in registers (bf16 pairs), row sum of this thread's columns
+        uint32_t pk[4][16];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int ch = cb + kk;
+          if (ch < ce) {
+            uint32_t v[32];
+            tmem_ld32(trow + ch * 32, v);
+            tmem_ld_wait();
+            const bool full = ch * 32 + 32 <= N;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, -mc));
+              float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
+              if (!full) {
+                p0 = (ch * 32 + 2 * i < N) ? p0 : 0.f;
+                p1 = (ch * 32 + 2 * i + 1 < N) ? p1 : 0.f;
+              }
+              sum += p0 + p1;
+              pk[kk][i] = pack_bf16x2(p0, p1);
+            }
+          }
+        }
+        // both threads of the row are done reading S (and publish their partial sums) before P overwrites it
+        if (w == 0) TRACE(46 + g, k);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_red + 1024u), "f"(sum) : "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        float osum;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(osum) : "r"(other_red + 1024u));
+        sum += osum;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          if (cb + kk < ce) tmem_st16(trow + (cb + kk) * 16, pk[kk]);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(bar_p(g));
+      if (w == 0) TRACE(48 + g, k);
+      mbar_wait(bar_o(g), cnt & 1u);
+      if (w == 0) TRACE(50 + g, k);
+      tc_fence_after();
+      if (live) {
+        uint32_t ov[32];
+        tmem_ld32(trow + 192 + hf * 32, ov);
+        tmem_ld_wait();
+        if (r < N) {
+          const float inv = rcp_approx(sum);
+          bf16* dst = p.o + size_t(row0 + r) * D + h * DH + hf * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(ov[8 * j + 0]) * inv, __uint_as_float(ov[8 * j + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(ov[8 * j + 2]) * inv, __uint_as_float(ov[8 * j + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(ov[8 * j + 4]) * inv, __uint_as_float(ov[8 * j + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(ov[8 * j + 6]) * inv, __uint_as_float(ov[8 * j + 7]) * inv);
+            reinterpret_cast<uint4*>(dst)[j] = u;
+          }
+          if (p.lse && hf == 0) p.lse[(size_t(b) * p.H + h) * N + r] = fmaf(mx, p.scale, 0.6931471805599453f * lg2_approx(sum));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_drained(g));
+      if (w == 0) TRACE(52 + g, k);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2 * kFwdGroupWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // =====================================================================================================
 // backward
 // =====================================================================================================
@@ -274,18 +579,6 @@ NGU_DEVINL BwdStep bwd_step(int r, int par, int ntiles, int N) {
   return s;
 }
 
-#ifdef NGU_ATTN_TRACE
-__device__ unsigned long long g_attn_trace[3 * 4096 + 8];
-NGU_DEVINL void trace_ev(int code, unsigned a) {
-  if (blockIdx.x != 0) return;
-  const unsigned long long i = atomicAdd(&g_attn_trace[0], 1ull);
-  if (i < 4096) { g_attn_trace[8 + 3 * i] = code; g_attn_trace[9 + 3 * i] = a; g_attn_trace[10 + 3 * i] = clock64(); }
-}
-#define TRACE(code, a) do { if ((threadIdx.x & 31) == 0) trace_ev(code, a); } while (0)
-#else
-#define TRACE(code, a) do {} while (0)
-#endif
-
 // ---- MMA issuer of the backward kernel.  This single warp paces the whole CTA, so its per-step instruction count is
 // what matters: the step sequence of an item is unrolled at compile time (kv tile, query tile, half and all smem
 // descriptor offsets are constants; only the live query width of the last tile is a run-time value).
@@ -303,6 +596,7 @@ struct BwdIssuer {
   int nkvs[2];      // [kv tile]: ceil16(live kv rows) / 16
   uint64_t dQ0, dK0, dV0, dDO0, mQ0, mK0, mDO0, mDS0;
   uint32_t sc_s = 0, sc_m = 0, pc = 0, jc = 0;
+  TRACE_DECL;
 
   NGU_DEVINL uint32_t bar_full(int g) const { return sBar + 8u * g; }
   NGU_DEVINL uint32_t bar_free(int g) const { return sBar + 32u + 8u * g; }
@@ -445,6 +739,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
   const uint32_t sTmem = sBar + 160u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TRACE_DECL;
   const int N = p.N, D = p.H * DH;
   constexpr int ntiles = NT;
   constexpr int nraw = ntiles * ntiles * 2;
@@ -718,10 +1013,10 @@ int fill_params(const ngu_attn_desc& d, AttnTcParams& p, bool bwd) {
   const int D = d.H * d.dh;
   int rc;
   if ((rc = make_tmap_2d_bf16(&p.tmQKV, d.q, uint64_t(d.B) * d.N, 3 * D, 3 * D, TILE, DH, true))) return rc;
+  const int rows1 = d.N > TILE ? ((d.N - TILE + 15) & ~15) : TILE;
+  if ((rc = make_tmap_2d_bf16(&p.tmQKV1, d.q, uint64_t(d.B) * d.N, 3 * D, 3 * D, rows1, DH, true))) return rc;
   if (bwd) {
     if ((rc = make_tmap_2d_bf16(&p.tmDO, d.d_o, uint64_t(d.B) * d.N, D, D, TILE, DH, true))) return rc;
-    const int rows1 = d.N > TILE ? ((d.N - TILE + 15) & ~15) : TILE;
-    if ((rc = make_tmap_2d_bf16(&p.tmQKV1, d.q, uint64_t(d.B) * d.N, 3 * D, 3 * D, rows1, DH, true))) return rc;
     if ((rc = make_tmap_2d_bf16(&p.tmDO1, d.d_o, uint64_t(d.B) * d.N, D, D, rows1, DH, true))) return rc;
   } else {
     p.tmDO = p.tmQKV;
@@ -740,7 +1035,7 @@ int fill_params(const ngu_attn_desc& d, AttnTcParams& p, bool bwd) {
 
 #ifdef NGU_ATTN_TRACE
 extern "C" int ngu_debug_attn_trace(void* out, int reset) {
-  if (reset) { unsigned long long z = 0; return cudaMemcpyToSymbol(g_attn_trace, &z, 8) != cudaSuccess; }
+  if (reset) { void* sym; cudaGetSymbolAddress(&sym, g_attn_trace); return cudaMemset(sym, 0, sizeof(g_attn_trace)) != cudaSuccess; }
   return cudaMemcpyFromSymbol(out, g_attn_trace, sizeof(g_attn_trace)) != cudaSuccess;
 }
 #endif
@@ -764,8 +1059,23 @@ int attn_fwd_tc(const ngu_attn_desc& d, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e, "attn_fwd_tc attr");
     attr = true;
   }
-  attn_fwd_tc_kernel<<<d.B * d.H * ((d.N + TILE - 1) / TILE), kFwdThreads, kFwdSmem, st>>>(p);
-  return check_launch("attn_fwd_tc");
+  // Default: one CTA per (batch, head, query tile), two CTAs per SM (147 us at the ViT-B/16 shape).  NGU_ATTN_FWD=1
+  // selects the persistent two-group kernel (164 us: its two groups fall into lock-step on the MUFU pipe; kept as the
+  // starting point for a single-group four-threads-per-row variant).
+  static const int mode = [] { const char* e = getenv("NGU_ATTN_FWD"); return e ? atoi(e) : 0; }();
+  if (mode == 0) {
+    attn_fwd_tc_kernel<<<d.B * d.H * ((d.N + TILE - 1) / TILE), kFwdThreads, kFwdSmem, st>>>(p);
+    return check_launch("attn_fwd_tc");
+  }
+  static bool attr2 = false;
+  if (!attr2) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdPSmem);
+    if (e != cudaSuccess) return cuda_status(e, "attn_fwd_persistent attr");
+    attr2 = true;
+  }
+  const int items = d.B * d.H;
+  attn_fwd_persistent_kernel<<<items < sm_count() ? items : sm_count(), kFwdPThreads, kFwdPSmem, st>>>(p);
+  return check_launch("attn_fwd_persistent");
 }
 
 int attn_bwd_tc(const ngu_attn_desc& d, cudaStream_t st) {

@@ -418,9 +418,14 @@ NGU_DEVINL void gelu_and_grad(float x, float& y, float& dy) {
   const float x2 = x * x;
   const float t = tanh_approx(x * fmaf(fmaf(kGa2, x2, kGa1), x2, kGa0));
   const float cdf = fmaf(0.5f, t, 0.5f);
-  const float du = fmaf(fmaf(5.0f * kGa2, x2, 3.0f * kGa1), x2, kGa0);
+  const float hdu = fmaf(fmaf(2.5f * kGa2, x2, 1.5f * kGa1), x2, 0.5f * kGa0);   // u'(x) / 2
   y = x * cdf;
-  dy = fmaf(0.5f * x * fmaf(-t, t, 1.0f), du, cdf);
+  dy = fmaf(x * fmaf(-t, t, 1.0f), hdu, cdf);
+}
+NGU_DEVINL float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 NGU_DEVINL float rcp_approx(float x) {
   float y;

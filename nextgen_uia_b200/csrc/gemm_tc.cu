@@ -356,13 +356,22 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
             __syncwarp();
             const int piece = lane & 7, rsub = lane >> 3;
             bf16* pbase = const_cast<bf16*>(pre_out) + size_t(m0 + q * 32) * p.ldpre + nc + piece * 8;
+            // batches of four independent 16-byte loads before their stores: one register quad reused for every
+            // LDS/STG pair serialises on the store's operand read
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 4 + rsub;
-              uint4 val;
-              const uint32_t a = slab + r * 128 + (uint32_t(piece ^ (r & 7)) << 4);
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(a));
-              if (m0 + q * 32 + r < p.M && nc + piece * 8 < p.N) *reinterpret_cast<uint4*>(pbase + size_t(r) * p.ldpre) = val;
+            for (int bt = 0; bt < 2; ++bt) {
+              uint4 val[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int r = (bt * 4 + u) * 4 + rsub;
+                const uint32_t a = slab + r * 128 + (uint32_t(piece ^ (r & 7)) << 4);
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val[u].x), "=r"(val[u].y), "=r"(val[u].z), "=r"(val[u].w) : "r"(a));
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int r = (bt * 4 + u) * 4 + rsub;
+                if (m0 + q * 32 + r < p.M && nc + piece * 8 < p.N) *reinterpret_cast<uint4*>(pbase + size_t(r) * p.ldpre) = val[u];
+              }
             }
             __syncwarp();
           }

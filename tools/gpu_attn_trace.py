@@ -14,14 +14,18 @@ dq = ops.attn_bwd_packed(qkv, o, lse, do, B, N, H, dh)
 torch.cuda.synchronize()
 lib.ngu_debug_attn_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 lib.ngu_debug_attn_trace(None, 1)
-dq = ops.attn_bwd_packed(qkv, o, lse, do, B, N, H, dh)
+if "fwd" in sys.argv:
+    ops.attn_fwd_packed(qkv, B, N, H, dh)
+else:
+    dq = ops.attn_bwd_packed(qkv, o, lse, do, B, N, H, dh)
 torch.cuda.synchronize()
-buf = np.zeros(3 * 4096 + 8, dtype=np.uint64)
+buf = np.zeros(32 * 256 * 3, dtype=np.uint64)
 lib.ngu_debug_attn_trace(buf.ctypes.data, 0)
-n = int(min(buf[0], 4096))
-ev = buf[8:8 + 3 * n].reshape(n, 3).astype(np.int64)
+ev = buf.reshape(-1, 3).astype(np.int64)
+ev = ev[ev[:, 2] > 0]
+n = len(ev)
 t0 = ev[:, 2].min()
-names = {10: "S.issue.begin", 11: "S.issued", 20: "M.waitP", 21: "M.Pseen", 22: "M.issued", 30: "C.waitS", 31: "C.Sseen", 32: "C.Parrive", 33: "C.drained"}
+names = {40: "g0.waitS", 41: "g1.waitS", 42: "g0.Sseen", 43: "g1.Sseen", 44: "g0.pass1", 45: "g1.pass1", 46: "g0.pass2", 47: "g1.pass2", 48: "g0.Parr", 49: "g1.Parr", 50: "g0.Oseen", 51: "g1.Oseen", 52: "g0.drained", 53: "g1.drained", 60: "M.S(g0)", 61: "M.S(g1)", 62: "M.PV(g0)", 63: "M.PV(g1)", 10: "S.issue.begin", 11: "S.issued", 20: "M.waitP", 21: "M.Pseen", 22: "M.issued", 30: "C.waitS", 31: "C.Sseen", 32: "C.Parrive", 33: "C.drained"}
 ev = ev[np.argsort(ev[:, 2])]
 lo, hi = int(sys.argv[1]) if len(sys.argv) > 1 else 16, int(sys.argv[2]) if len(sys.argv) > 2 else 34
 for c, a, t in ev:

@@ -79,7 +79,7 @@ for (N, K, kw) in [(2304, 768, dict(bias=1)), (768, 768, dict(bias=1, aux_mode=1
     C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     P = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     line = f"perf N={N} K={K} {kw}:"
-    for bn in (1000, 2256):
+    for bn in (0, 1000, 2256):
         us = timeit(lambda: gemm(A, B, bias, kw.get("act", 0), aux, kw.get("aux_mode", 0), bool(kw.get("save_pre")), block_n=bn, C=C, Pre=P))
         line += f"  bn={bn}: {us:.1f} us {2.0*M*N*K/us/1e6:.0f} TF/s"
     print(line, flush=True)

@@ -472,9 +472,9 @@ template <> NGU_DEVINL bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn
 // host side: tensor map encode through the driver entry point (no link against libcuda)
 // ----------------------------------------------------------------------------------------
 // 2-D row-major tensor [rows, cols] of bf16 with row pitch `ld` elements; box = [box_rows, box_cols].
-// swizzle128: box_cols * 2 bytes must be <= 128.
+// swizzle: 0 none, 1 = SWIZZLE_128B (box_cols * 2 <= 128 bytes), 2 = SWIZZLE_64B (box_cols * 2 <= 64 bytes).
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows, uint32_t box_cols, bool swizzle128);
+                      uint32_t box_rows, uint32_t box_cols, int swizzle);
 int sm_count();
 
 }  // namespace ngu

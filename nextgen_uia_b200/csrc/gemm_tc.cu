@@ -26,16 +26,17 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kNumEpiWarps = 8;
+constexpr int kNumEpiWarps = 16;
 constexpr int kGemmThreads = 32 * (2 + kNumEpiWarps);
-constexpr int kSlabBytes = 32 * 128;  // 32 rows x 64 bf16
+constexpr int kChunkCols = 32;              // columns per epilogue work item
+constexpr int kSlabBytes = 32 * kChunkCols * 2;  // 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
 
 template <int BLOCK_N, bool kPair = false>
 struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = (kPair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // pair mode: each CTA holds half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytes = kNumEpiWarps * kSlabBytes;  // one 32x64 slab per epilogue warp
+  static constexpr int kEpiBytes = kNumEpiWarps * kSlabBytes;  // one 32x32 slab per epilogue warp
   static constexpr int kBarBytes = 1024;  // mbarriers + tmem ptr
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/;
   static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes - kBarBytes) / kStageBytes;
@@ -60,24 +61,22 @@ struct GemmKernelParams {
   int prefetch;  // L2 prefetch distance for A in k-blocks (0 = off)
 };
 
-// Epilogue math for one 64-column chunk of one row: v = raw fp32 accumulators, ax = aux row chunk
-// (bf16x2 words), bias_s = smem address of this warp's 64 staged bias floats.  Compile-time
-// ACT/AUX so the hot loop stays small (the runtime switch happens once per chunk, warp-uniform).
+// Epilogue math for one 32-column chunk of one row: v = raw fp32 accumulators, ax = aux row chunk (bf16x2 words),
+// bias_l = this lane's bias[chunk column `lane`].  Compile-time ACT/AUX so the hot loop stays small (the run-time
+// switch happens once per chunk, warp-uniform).
 template <int ACT, int AUX>
-NGU_DEVINL void epi_chunk(const uint32_t (&v)[64], const uint4 (&ax)[8], float2 bias2, float alpha, bool save,
-                          uint32_t (&outp)[32], uint32_t (&prep)[32]) {
-  // bias2 = this lane's (bias[2*lane], bias[2*lane+1]) of the chunk; element j of the row needs lane j/2's value
+NGU_DEVINL void epi_chunk(const uint32_t (&v)[32], const uint4 (&ax)[4], float bias_l, float alpha, bool save,
+                          uint32_t (&outp)[16], uint32_t (&prep)[16]) {
+  const uint32_t* axw = reinterpret_cast<const uint32_t*>(ax);
 #pragma unroll
-  for (int j4 = 0; j4 < 16; ++j4) {
-    float b[4];
-    b[0] = __shfl_sync(0xffffffffu, bias2.x, 2 * j4);
-    b[1] = __shfl_sync(0xffffffffu, bias2.y, 2 * j4);
-    b[2] = __shfl_sync(0xffffffffu, bias2.x, 2 * j4 + 1);
-    b[3] = __shfl_sync(0xffffffffu, bias2.y, 2 * j4 + 1);
+  for (int j4 = 0; j4 < 8; ++j4) {
     float x[4], d[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { x[i] = fmaf(__uint_as_float(v[4 * j4 + i]), alpha, b[i]); d[i] = x[i]; }
-    const uint32_t* axw = reinterpret_cast<const uint32_t*>(ax);
+    for (int i = 0; i < 4; ++i) {
+      const float b = __shfl_sync(0xffffffffu, bias_l, 4 * j4 + i);   // element j of the row needs lane j's bias
+      x[i] = fmaf(__uint_as_float(v[4 * j4 + i]), alpha, b);
+      d[i] = x[i];
+    }
     const float2 a01 = unpack_bf16x2(axw[2 * j4]);
     const float2 a23 = unpack_bf16x2(axw[2 * j4 + 1]);
     const float a[4] = {a01.x, a01.y, a23.x, a23.y};
@@ -148,7 +147,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), ((BLOCK_N / 64 >= 2) ? kNumEpiWarps : 4) * (kPair ? 2 : 1));  // pair: both CTAs' epilogues
+      mbar_init(tempty_bar(a), ((BLOCK_N / kChunkCols >= 4) ? kNumEpiWarps : 4 * (BLOCK_N / kChunkCols)) * (kPair ? 2 : 1));  // pair: both CTAs' epilogues
     }
     fence_mbar_init();
   }
@@ -257,61 +256,54 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     }
   } else {
     // ================================ epilogue ================================
-    // 8 warps: warp w owns TMEM lane quarter (w & 3) and one half of the tile's 64-column chunks, so two warps
-    // share each SM sub-partition and overlap each other's TMEM / global-load / MUFU latencies.
+    // 16 warps: warp w owns TMEM lane quarter (w & 3) and BLOCK_N/128 of the tile's 32-column chunks, so four warps
+    // share each SM sub-partition and hide each other's TMEM / global-load / MUFU / dependent-issue latencies (the
+    // GELU + saved-derivative epilogue needs ~23 issue slots per element; with two warps per scheduler it, not the
+    // tensor pipe, set the pace).
     const int ew = warp - 2;
     const int q = warp & 3;
-    constexpr int kChunks = BLOCK_N / 64;
-    constexpr int kPerWarp = kChunks >= 2 ? kChunks / 2 : 1;
-    const int c_begin = (kChunks >= 2 ? (ew >> 2) : 0) * kPerWarp;
-    const bool active = (kChunks >= 2) || (ew < 4);
+    const int g = ew >> 2;
+    constexpr int kChunks = BLOCK_N / kChunkCols;
+    constexpr int kPerWarp = kChunks >= 4 ? kChunks / 4 : 1;
+    const int c_begin = g * kPerWarp;
+    const bool active = g < kChunks;
     const uint32_t slab = sEpi + ew * kSlabBytes;
     const bool use_aux = p.aux_mode != NGU_AUX_NONE;
     const bf16* pre_out = reinterpret_cast<const bf16*>(p.pre);
 
-    auto load_aux = [&](int t, int c, uint4 (&dst)[8]) {
-      const int m0 = tile_m0(t), nc = tile_n0(t) + c * 64;
+    auto load_aux = [&](int t, int c, uint4 (&dst)[4]) {
+      const int m0 = tile_m0(t), nc = tile_n0(t) + c * kChunkCols;
       const int row = m0 + q * 32 + lane;
       const bool ok = use_aux && t < num_tiles && nc < p.N && row < p.M;
       const uint4* ap = reinterpret_cast<const uint4*>(p.aux + size_t(ok ? row : 0) * p.ldaux + (ok ? nc : 0));
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dst[j] = (ok && nc + j * 8 < p.N) ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
+      for (int j = 0; j < 4; ++j) dst[j] = (ok && nc + j * 8 < p.N) ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
     };
 
     if (active) {
       int acc = 0;
       uint32_t acc_ph = 0;
-      uint4 axn[8];
+      uint4 axn[4];
       load_aux(tile_first, c_begin, axn);
       for (int t = tile_first; t < num_tiles; t += tile_stride) {
         const int m0 = tile_m0(t);
         const int n0 = tile_n0(t);
-        const int row = m0 + q * 32 + lane;
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
 #pragma unroll 1
         for (int ci = 0; ci < kPerWarp; ++ci) {
           const int c = c_begin + ci;
-          const int nc = n0 + c * 64;
+          const int nc = n0 + c * kChunkCols;
           const bool live = nc < p.N;  // warp-uniform
-          uint32_t v[64];
-          {
-            uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-            uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-            tmem_ld32(t_addr + c * 64, lo);
-            tmem_ld32(t_addr + c * 64 + 32, hi);
-          }
-          float2 bias2 = make_float2(0.f, 0.f);
-          if (p.bias != nullptr && live) {
-            const int n = nc + 2 * lane;
-            bias2.x = (n < p.N) ? __ldg(p.bias + n) : 0.f;
-            bias2.y = (n + 1 < p.N) ? __ldg(p.bias + n + 1) : 0.f;
-          }
+          uint32_t v[32];
+          tmem_ld32(t_addr + c * kChunkCols, v);
+          float bias_l = 0.f;
+          if (p.bias != nullptr && live) bias_l = (nc + lane < p.N) ? __ldg(p.bias + nc + lane) : 0.f;
           // aux chunk was prefetched one work item ago; start fetching the next one now
-          uint4 ax[8];
+          uint4 ax[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ax[j] = axn[j];
+          for (int j = 0; j < 4; ++j) ax[j] = axn[j];
           if (use_aux) {
             if (ci + 1 < kPerWarp) load_aux(t, c + 1, axn);
             else load_aux(t + tile_stride, c_begin, axn);
@@ -327,58 +319,55 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
           }
           if (!live) continue;
 
-          uint32_t outp[32];
-          uint32_t prep[32];
+          uint32_t outp[16];
+          uint32_t prep[16];
           {
             const bool sv = p.save_pre != 0;
             const int mode = (p.aux_mode == NGU_AUX_DACT) ? 100 : p.act * 3 + p.aux_mode;  // warp-uniform
             switch (mode) {
-              case 100: epi_chunk<NGU_ACT_NONE, NGU_AUX_DACT>(v, ax, bias2, p.alpha, false, outp, prep); break;
-              case NGU_ACT_NONE * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_NONE, NGU_AUX_RESIDUAL>(v, ax, bias2, p.alpha, sv, outp, prep); break;
-              case NGU_ACT_GELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_GELU, NGU_AUX_NONE>(v, ax, bias2, p.alpha, sv, outp, prep); break;
-              case NGU_ACT_GELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_GELU, NGU_AUX_RESIDUAL>(v, ax, bias2, p.alpha, sv, outp, prep); break;
-              case NGU_ACT_QUICKGELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_NONE>(v, ax, bias2, p.alpha, sv, outp, prep); break;
-              case NGU_ACT_QUICKGELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_RESIDUAL>(v, ax, bias2, p.alpha, sv, outp, prep); break;
-              default: epi_chunk<NGU_ACT_NONE, NGU_AUX_NONE>(v, ax, bias2, p.alpha, sv, outp, prep); break;
+              case 100: epi_chunk<NGU_ACT_NONE, NGU_AUX_DACT>(v, ax, bias_l, p.alpha, false, outp, prep); break;
+              case NGU_ACT_NONE * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_NONE, NGU_AUX_RESIDUAL>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
+              case NGU_ACT_GELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_GELU, NGU_AUX_NONE>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
+              case NGU_ACT_GELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_GELU, NGU_AUX_RESIDUAL>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
+              case NGU_ACT_QUICKGELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_NONE>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
+              case NGU_ACT_QUICKGELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_RESIDUAL>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
+              default: epi_chunk<NGU_ACT_NONE, NGU_AUX_NONE>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
             }
           }
           if (lane == 0) tma_store_wait_read<0>();   // previous TMA store has finished reading this warp's slab
           __syncwarp();
-          const uint32_t rbase = slab + lane * 128;
+          // slab rows are 64 bytes; SWIZZLE_64B: 16-byte piece index ^= (row >> 1) & 3
+          const uint32_t rbase = slab + lane * 64;
+          const uint32_t rsw = uint32_t(lane >> 1) & 3u;
           if (p.save_pre) {
-            // activation derivative (saved for backward): transpose through the slab, then coalesced 512-byte row groups
+            // activation derivative (saved for backward): transpose through the slab, then coalesced 64-byte row pieces
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t a = rbase + (uint32_t(j ^ (lane & 7)) << 4);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t a = rbase + ((uint32_t(j) ^ rsw) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(prep[4 * j]), "r"(prep[4 * j + 1]),
                            "r"(prep[4 * j + 2]), "r"(prep[4 * j + 3]) : "memory");
             }
             __syncwarp();
-            const int piece = lane & 7, rsub = lane >> 3;
+            const int piece = lane & 3, rsub = lane >> 2;
             bf16* pbase = const_cast<bf16*>(pre_out) + size_t(m0 + q * 32) * p.ldpre + nc + piece * 8;
-            // batches of four independent 16-byte loads before their stores: one register quad reused for every
-            // LDS/STG pair serialises on the store's operand read
+            uint4 val[4];
 #pragma unroll
-            for (int bt = 0; bt < 2; ++bt) {
-              uint4 val[4];
+            for (int u = 0; u < 4; ++u) {
+              const int r = u * 8 + rsub;
+              const uint32_t a = slab + r * 64 + ((uint32_t(piece) ^ (uint32_t(r >> 1) & 3u)) << 4);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val[u].x), "=r"(val[u].y), "=r"(val[u].z), "=r"(val[u].w) : "r"(a));
+            }
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int r = (bt * 4 + u) * 4 + rsub;
-                const uint32_t a = slab + r * 128 + (uint32_t(piece ^ (r & 7)) << 4);
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val[u].x), "=r"(val[u].y), "=r"(val[u].z), "=r"(val[u].w) : "r"(a));
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int r = (bt * 4 + u) * 4 + rsub;
-                if (m0 + q * 32 + r < p.M && nc + piece * 8 < p.N) *reinterpret_cast<uint4*>(pbase + size_t(r) * p.ldpre) = val[u];
-              }
+            for (int u = 0; u < 4; ++u) {
+              const int r = u * 8 + rsub;
+              if (m0 + q * 32 + r < p.M && nc + piece * 8 < p.N) *reinterpret_cast<uint4*>(pbase + size_t(r) * p.ldpre) = val[u];
             }
             __syncwarp();
           }
-          // registers -> swizzled slab -> TMA store (per-warp 32 x 64 box)
+          // registers -> swizzled slab -> TMA store (per-warp 32 x 32 box)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t a = rbase + (uint32_t(j ^ (lane & 7)) << 4);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t a = rbase + ((uint32_t(j) ^ rsw) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(outp[4 * j]),
                          "r"(outp[4 * j + 1]), "r"(outp[4 * j + 2]), "r"(outp[4 * j + 3])
                          : "memory");
@@ -423,7 +412,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     p.tmB2 = p.tmB;
     p.tmB2h = p.tmBh;
   }
-  if ((rc = make_tmap_2d_bf16(&p.tmC, a.C, a.M, a.N, a.ldc, 32, 64, true))) return rc;
+  if ((rc = make_tmap_2d_bf16(&p.tmC, a.C, a.M, a.N, a.ldc, 32, kChunkCols, 2))) return rc;
   p.pre = a.Pre;
   p.ldpre = a.ldpre;
   p.bias = a.bias;

@@ -51,13 +51,16 @@ static EncodeTiledFn get_encode() {
 }
 
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows, uint32_t box_cols, bool swizzle128) {
+                      uint32_t box_rows, uint32_t box_cols, int swizzle) {
+  // swizzle: 0 none, 1 (true) 128-byte, 2 64-byte
+  const bool swizzle128 = swizzle == 1;
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error("cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU?)"); return NGU_ERR_CUDA; }
   if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * 2) & 15u)) {
     set_last_error("tensor map: base %p / pitch %llu B not 16-byte aligned", base, (unsigned long long)(ld * 2));
     return NGU_ERR_ALIGN;
   }
+  if (swizzle == 2 && box_cols * 2 > 64) { set_last_error("tensor map: 64B-swizzled box wider than 64 B"); return NGU_ERR_ARG; }
   if (swizzle128 && box_cols * 2 > 128) { set_last_error("tensor map: swizzled box wider than 128 B"); return NGU_ERR_ARG; }
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld * 2};
@@ -65,7 +68,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", int(r),

@@ -31,14 +31,31 @@ __global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ o
 template <typename T>
 __global__ void assemble_kernel(const T* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
                                 T* __restrict__ out, int B, int np, int D) {
-  const size_t total = size_t(B) * (np + 1) * D;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int c = int(i % D);
-    const int n = int((i / D) % (np + 1));
-    const int b = int(i / (size_t(D) * (np + 1)));
-    float v = pos[size_t(n) * D + c];
-    v += (n == 0) ? cls[c] : to_f32<T>(patch[(size_t(b) * np + (n - 1)) * D + c]);
-    out[i] = from_f32<T>(v);
+  // one 16-byte vector of a token row per thread; 32-bit index math (the scalar 64-bit div/mod version ran 8x off the
+  // HBM roofline)
+  constexpr int V = Vec<T>::N;
+  const int vpr = D / V;                                 // vectors per row
+  const unsigned total = unsigned(B) * unsigned(np + 1) * unsigned(vpr);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned row = i / unsigned(vpr);
+    const int c = int(i - row * unsigned(vpr)) * V;
+    const int b = int(row / unsigned(np + 1));
+    const int n = int(row - unsigned(b) * unsigned(np + 1));
+    float v[V], a[V];
+#pragma unroll
+    for (int e = 0; e < V; e += 4) {
+      const float4 q = *reinterpret_cast<const float4*>(pos + size_t(n) * D + c + e);
+      v[e] = q.x; v[e + 1] = q.y; v[e + 2] = q.z; v[e + 3] = q.w;
+    }
+    if (n == 0) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) a[e] = cls[c + e];
+    } else {
+      Vec<T>::load(patch + (size_t(b) * np + (n - 1)) * D + c, a);
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] += a[e];
+    Vec<T>::store(out + size_t(row) * D + c, v);
   }
 }
 
@@ -46,14 +63,24 @@ __global__ void assemble_kernel(const T* __restrict__ patch, const float* __rest
 template <typename T>
 __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
                              const float* __restrict__ type0, T* __restrict__ out, int B, int S, int D, int vocab) {
-  const size_t total = size_t(B) * S * D;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int c = int(i % D);
-    const size_t tok = i / D;
-    const int s = int(tok % S);
+  constexpr int V = Vec<T>::N;
+  const int vpr = D / V;
+  const unsigned total = unsigned(B) * unsigned(S) * unsigned(vpr);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned tok = i / unsigned(vpr);
+    const int c = int(i - tok * unsigned(vpr)) * V;
+    const int sidx = int(tok % unsigned(S));
     int64_t id = ids[tok];
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-    out[i] = from_f32<T>(word[size_t(id) * D + c] + pos[size_t(s) * D + c] + type0[c]);
+    float v[V];
+#pragma unroll
+    for (int e = 0; e < V; e += 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(word + size_t(id) * D + c + e);
+      const float4 p4 = *reinterpret_cast<const float4*>(pos + size_t(sidx) * D + c + e);
+      const float4 t4 = *reinterpret_cast<const float4*>(type0 + c + e);
+      v[e] = w4.x + p4.x + t4.x; v[e + 1] = w4.y + p4.y + t4.y; v[e + 2] = w4.z + p4.z + t4.z; v[e + 3] = w4.w + p4.w + t4.w;
+    }
+    Vec<T>::store(out + size_t(tok) * D + c, v);
   }
 }
 
@@ -175,7 +202,8 @@ int patchify(const float* img, void* out, int B, int R, int P, int dtype, cudaSt
 }
 int assemble_tokens(const void* patch, const float* cls, const float* pos, void* out, int B, int np, int D, int dtype, cudaStream_t st) {
   if (B <= 0 || np <= 0 || D <= 0) { set_last_error("assemble_tokens: empty"); return NGU_ERR_SHAPE; }
-  const size_t total = size_t(B) * (np + 1) * D;
+  if (D % 8) { set_last_error("assemble_tokens: D must be a multiple of 8"); return NGU_ERR_SHAPE; }
+  const size_t total = size_t(B) * (np + 1) * D / (dtype == NGU_F32 ? 4 : 8);
   if (dtype == NGU_F32) assemble_kernel<float><<<grid_for(total), 256, 0, st>>>(reinterpret_cast<const float*>(patch), cls, pos, reinterpret_cast<float*>(out), B, np, D);
   else assemble_kernel<bf16><<<grid_for(total), 256, 0, st>>>(reinterpret_cast<const bf16*>(patch), cls, pos, reinterpret_cast<bf16*>(out), B, np, D);
   return check_launch("assemble_tokens");
@@ -183,7 +211,8 @@ int assemble_tokens(const void* patch, const float* cls, const float* pos, void*
 int embed_tokens(const int64_t* ids, const float* word, const float* pos, const float* type0, void* out, int B, int S, int D,
                  int vocab, int dtype, cudaStream_t st) {
   if (B <= 0 || S <= 0 || D <= 0 || vocab <= 0) { set_last_error("embed_tokens: empty"); return NGU_ERR_SHAPE; }
-  const size_t total = size_t(B) * S * D;
+  if (D % 8) { set_last_error("embed_tokens: D must be a multiple of 8"); return NGU_ERR_SHAPE; }
+  const size_t total = size_t(B) * S * D / (dtype == NGU_F32 ? 4 : 8);
   if (dtype == NGU_F32) embed_kernel<float><<<grid_for(total), 256, 0, st>>>(ids, word, pos, type0, reinterpret_cast<float*>(out), B, S, D, vocab);
   else embed_kernel<bf16><<<grid_for(total), 256, 0, st>>>(ids, word, pos, type0, reinterpret_cast<bf16*>(out), B, S, D, vocab);
   return check_launch("embed_tokens");

@@ -177,7 +177,8 @@ typedef struct ngu_attn_desc {
   int B, H, N, S, dh;
   float scale; int causal;
   int dtype;
-  int impl;                   /* 0 = default for dtype (bf16: tcgen05, fp32: CUDA cores); 1 = force CUDA cores */
+  int impl;                   /* 0 = default for dtype (bf16: tcgen05, fp32: CUDA cores); 1 = force CUDA cores;
+                                 2 = tcgen05 with the persistent two-group forward kernel (forward only; tuning) */
 } ngu_attn_desc;
 int ngu_attn_fwd(const ngu_attn_desc* d, void* stream);
 int ngu_attn_bwd(const ngu_attn_desc* d, void* stream);

@@ -1059,11 +1059,11 @@ int attn_fwd_tc(const ngu_attn_desc& d, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e, "attn_fwd_tc attr");
     attr = true;
   }
-  // Default: one CTA per (batch, head, query tile), two CTAs per SM (147 us at the ViT-B/16 shape).  NGU_ATTN_FWD=1
-  // selects the persistent two-group kernel (164 us: its two groups fall into lock-step on the MUFU pipe; kept as the
+  // Default: one CTA per (batch, head, query tile), two CTAs per SM (147 us at the ViT-B/16 shape).  NGU_ATTN_FWD=1 or
+  // desc.impl = 2 selects the persistent two-group kernel (164 us: its two groups fall into lock-step on the MUFU pipe; kept as the
   // starting point for a single-group four-threads-per-row variant).
   static const int mode = [] { const char* e = getenv("NGU_ATTN_FWD"); return e ? atoi(e) : 0; }();
-  if (mode == 0) {
+  if (mode == 0 && d.impl != 2) {
     attn_fwd_tc_kernel<<<d.B * d.H * ((d.N + TILE - 1) / TILE), kFwdThreads, kFwdSmem, st>>>(p);
     return check_launch("attn_fwd_tc");
   }

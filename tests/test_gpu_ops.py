@@ -120,6 +120,30 @@ def test_attention(dtype, B, N, H, causal):
     assert relerr(dqkv, dref) < GTOL[dtype]
 
 
+@pytest.mark.parametrize("B,N,H", [(30, 197, 12), (40, 77, 12), (70, 208, 5), (3, 193, 2), (2, 16, 1), (4, 65, 3), (2, 256, 3),
+                                   (37, 128, 4)])
+def test_attention_tc_persistent_paths(B, N, H):
+    """tcgen05 attention against the CUDA-core kernels on shapes that exercise the persistent backward: several
+    (batch, head) items per CTA (B*H > 148), one and two query tiles, trimmed second tiles, dead half-steps, both
+    item parities of the alternating tile order.  Also the persistent two-group forward (desc.impl = 2)."""
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(11)
+    dh = 64
+    D = H * dh
+    qkv = torch.randn(B * N, 3 * D).to(dev(), torch.bfloat16)
+    do = torch.randn(B * N, D).to(dev(), torch.bfloat16)
+    o, lse = ops.attn_fwd_packed(qkv, B, N, H, dh, impl=0)
+    o1, lse1 = ops.attn_fwd_packed(qkv, B, N, H, dh, impl=1)
+    assert relerr(o, o1) < 1e-2 and relerr(lse, lse1) < 1e-4
+    o2, lse2 = ops.attn_fwd_packed(qkv, B, N, H, dh, impl=2)
+    assert relerr(o2, o1) < 1e-2 and relerr(lse2, lse1) < 1e-4
+    g = ops.attn_bwd_packed(qkv, o1, lse1, do, B, N, H, dh, impl=0)
+    g1 = ops.attn_bwd_packed(qkv, o1, lse1, do, B, N, H, dh, impl=1)
+    for sl in (slice(0, D), slice(D, 2 * D), slice(2 * D, 3 * D)):      # dq, dk, dv separately (different magnitudes)
+        assert relerr(g[:, sl], g1[:, sl]) < 1e-2
+    assert torch.isfinite(g.float()).all()
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_wgrad_colsum(dtype):
     from nextgen_uia_b200 import ops

@@ -244,6 +244,18 @@ int ngu_embed_tokens(const int64_t* ids, const float* word, const float* pos, co
 /* out (dtype) = scale * in (fp32 [rows, cols]), optionally transposed to [cols, rows] */
 int ngu_cast_f32(const float* in, void* out, int rows, int cols, int transpose, float scale, int dtype, void* stream);
 
+/* The same conversion for a table of tensors in ONE launch: the per-step refresh of the bf16 shadows (and transposes)
+ * of the trainable adapter projections after the optimizer update (mona.py:127,148 weights; lora.py:48-51 factors).
+ * `items` is a DEVICE array of n entries; pointers in it are device pointers. */
+typedef struct ngu_cast_item {
+  const float* in;            /* fp32 [rows, cols] */
+  void* out;                  /* dtype [rows, cols], or [cols, rows] when transpose */
+  int rows, cols;
+  int transpose;
+  float scale;
+} ngu_cast_item;
+int ngu_cast_f32_batch(const ngu_cast_item* items, int n, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,11 @@ AUX_NONE, AUX_RESIDUAL, AUX_DACT = 0, 1, 2
 _c_void_p, _c_int, _c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 
 
+class CastItem(ctypes.Structure):   # ngu_cast_item
+    _fields_ = [("inp", _c_void_p), ("out", _c_void_p), ("rows", _c_int), ("cols", _c_int), ("transpose", _c_int),
+                ("scale", _c_float)]
+
+
 class GemmDesc(ctypes.Structure):
     _fields_ = [
         ("A", _c_void_p), ("lda", _c_int),
@@ -128,6 +133,7 @@ PROTOTYPES = {
     "ngu_assemble_tokens": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "ngu_embed_tokens": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "ngu_cast_f32": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_int, _c_void_p]),
+    "ngu_cast_f32_batch": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p]),
 }
 
 

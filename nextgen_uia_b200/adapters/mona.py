@@ -29,6 +29,18 @@ def _next_seed():
     return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 
+def _shadow(owner, w, dt, transpose):
+    """Low-precision (optionally transposed) copy of a projection weight: taken from the trainer's one-launch
+    `ops.CastPlan` when it is fresh for this parameter, converted on the spot otherwise."""
+    plan = getattr(owner, "_ngu_castplan", None) if owner is not None else None
+    if plan is not None and plan.fresh and plan.dtype == dt:
+        t = plan.get(owner.project1.weight if w is owner.project1.weight or w.data_ptr() == owner.project1.weight.data_ptr()
+                     else owner.project2.weight, transpose)
+        if t is not None:
+            return t
+    return ops.cast(w, dt, transpose=transpose)
+
+
 class MonaFunction(torch.autograd.Function):
     """y = x + project2(dropout(gelu(convstage(project1(LN(x)*gamma + x*gammax)))))  on [B,N,D].
     Variant tensors (freq_filter, noise-estimator weights) are None for the baseline adapter."""
@@ -41,10 +53,10 @@ class MonaFunction(torch.autograd.Function):
         x2 = x.contiguous().view(B * N, D)
         dt = x2.dtype
         u, mean, rstd = ops.ln_fwd(x2, norm_w, norm_b, _LN_EPS, gamma=gamma, gammax=gammax)
-        h = ops.gemm(u, ops.cast(w1, dt), bias=b1)                                   # [M, C]
+        h = ops.gemm(u, _shadow(owner, w1, dt, False), bias=b1)                      # [M, C]
         conv_w = (k3, b3, k5, b5, k7, b7, pw, pb, freq, ne_w1, ne_b1, ne_w2, ne_b2)
         g = ops.mona_conv_fwd(h.view(B, N, C), conv_w, hw, has_cls, drop_p, seed)     # [B, N, C]
-        y = ops.gemm(g.view(B * N, C), ops.cast(w2, dt), bias=b2, aux=x2, aux_mode=L.AUX_RESIDUAL)
+        y = ops.gemm(g.view(B * N, C), _shadow(owner, w2, dt, False), bias=b2, aux=x2, aux_mode=L.AUX_RESIDUAL)
         ctx.save_for_backward(x2, mean, rstd, u, h, g, norm_w, norm_b, gamma, gammax, w1, k3, b3, k5, b5, k7, b7, pw, pb, w2,
                               *[t for t in (freq, ne_w1, ne_b1, ne_w2, ne_b2) if t is not None])
         ctx.variant = (freq is not None, ne_w1 is not None)
@@ -80,7 +92,7 @@ class MonaFunction(torch.autograd.Function):
             return torch.zeros(*shape, device=dev, dtype=torch.float32)
 
         # project2:  y = x + g W2^T + b2
-        dg = ops.gemm(dy2, ops.cast(w2, dt, transpose=True))                          # [M, C] = dy W2
+        dg = ops.gemm(dy2, _shadow(owner, w2, dt, True))                              # [M, C] = dy W2
         g2 = g.view(B * N, C)
         dw2 = buf(owner.project2.weight if sink else None, (D, C))
         ops.wgrad(dy2, g2, out=dw2)                                                   # [D, C]
@@ -103,7 +115,7 @@ class MonaFunction(torch.autograd.Function):
         dh2 = dh.view(B * N, C)
         # project1:  h = u W1^T + b1
         dw1t = ops.wgrad(u, dh2)                                                      # [D, C] = dW1^T
-        du = ops.gemm(dh2, ops.cast(w1, dt, transpose=True))                          # [M, D] = dh W1
+        du = ops.gemm(dh2, _shadow(owner, w1, dt, True))                              # [M, D] = dh W1
         # LN mix + residual
         if sink is not None:
             dnw, dnb, dgam, dgamx, db2 = owner.norm.weight.grad, owner.norm.bias.grad, owner.gamma.grad, owner.gammax.grad, owner.project2.bias.grad

@@ -95,5 +95,8 @@ int ngu_embed_tokens(const int64_t* ids, const float* word, const float* pos, co
 int ngu_cast_f32(const float* in, void* out, int rows, int cols, int transpose, float scale, int dtype, void* stream) {
   return cast_f32(in, out, rows, cols, transpose, scale, dtype, NGU_STREAM);
 }
+int ngu_cast_f32_batch(const ngu_cast_item* items, int n, int dtype, void* stream) {
+  return cast_f32_batch(items, n, dtype, NGU_STREAM);
+}
 
 }  // extern "C"

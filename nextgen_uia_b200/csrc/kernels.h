@@ -30,6 +30,7 @@ int patchify(const float* img, void* out, int B, int R, int P, int dtype, cudaSt
 int assemble_tokens(const void* patch, const float* cls, const float* pos, void* out, int B, int np, int D, int dtype, cudaStream_t s);
 int embed_tokens(const int64_t* ids, const float* word, const float* pos, const float* type0, void* out, int B, int S, int D, int vocab, int dtype, cudaStream_t s);
 int cast_f32(const float* in, void* out, int rows, int cols, int transpose, float scale, int dtype, cudaStream_t s);
+int cast_f32_batch(const ngu_cast_item* items, int n, int dtype, cudaStream_t s);
 int wgrad_simt(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int Tn, int Mo, int No, int dtype, cudaStream_t s);
 int dropout(const void* x, void* out, size_t n, float p, uint64_t seed, int accumulate, int dtype, cudaStream_t s);
 bool wgrad_tc_supported(int ldx, int ldy, int ldd, int Mo, int No, int dtype, const void* X, const void* Y, const float* D);

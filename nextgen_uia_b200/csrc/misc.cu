@@ -96,6 +96,20 @@ __global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, i
   }
 }
 
+// table of casts in one launch: blockIdx.y = item, blockIdx.x strides over its elements
+template <typename T>
+__global__ void cast_batch_kernel(const ngu_cast_item* __restrict__ items) {
+  const ngu_cast_item it = items[blockIdx.y];
+  const unsigned total = unsigned(it.rows) * unsigned(it.cols);
+  T* out = reinterpret_cast<T*>(it.out);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / unsigned(it.cols), c = i - r * unsigned(it.cols);
+    const float v = it.in[i] * it.scale;
+    if (it.transpose) out[size_t(c) * it.rows + r] = from_f32<T>(v);
+    else out[i] = from_f32<T>(v);
+  }
+}
+
 // D[Mo,No] += X^T Y,  X [T,Mo], Y [T,No] row-major, reduction over tokens split across blockIdx.z
 constexpr int WT = 64, WK = 16;
 template <typename T>
@@ -223,6 +237,14 @@ int cast_f32(const float* in, void* out, int rows, int cols, int transpose, floa
   if (dtype == NGU_F32) cast_kernel<float><<<grid_for(total), 256, 0, st>>>(in, reinterpret_cast<float*>(out), rows, cols, transpose, scale);
   else cast_kernel<bf16><<<grid_for(total), 256, 0, st>>>(in, reinterpret_cast<bf16*>(out), rows, cols, transpose, scale);
   return check_launch("cast");
+}
+int cast_f32_batch(const ngu_cast_item* items, int n, int dtype, cudaStream_t st) {
+  if (n <= 0 || items == nullptr) { set_last_error("cast_batch: empty table"); return NGU_ERR_SHAPE; }
+  if (n > 65535) { set_last_error("cast_batch: at most 65535 items per launch"); return NGU_ERR_ARG; }
+  const dim3 grid(48, n);
+  if (dtype == NGU_F32) cast_batch_kernel<float><<<grid, 256, 0, st>>>(items);
+  else cast_batch_kernel<bf16><<<grid, 256, 0, st>>>(items);
+  return check_launch("cast_batch");
 }
 int dropout(const void* x, void* out, size_t n, float p, uint64_t seed, int accumulate, int dtype, cudaStream_t st) {
   if (n == 0 || p < 0.f || p >= 1.f) { set_last_error("dropout: bad n/p"); return NGU_ERR_ARG; }

@@ -213,6 +213,20 @@ class Trainer:
                     for p in mod.parameters():
                         p._ngu_owner = mod
         self.buckets = GradBuckets(self.params, bucket_of, flatten_params=self.fused)
+        # One-launch refresh of the bf16 shadows (and transposes) of every Mona projection weight after each update,
+        # instead of four small cast launches per layer per step.
+        self.castplan = None
+        dt = next((getattr(m, "compute_dtype") for m in model.modules() if hasattr(m, "compute_dtype")), None)
+        if on_gpu and self.fused and dt == torch.bfloat16:
+            from .adapters.mona import BaselineMona
+            from . import ops
+            monas = [m for m in model.modules() if isinstance(m, BaselineMona) and all(p.requires_grad for p in m.parameters())]
+            entries = [(w, tr) for m in monas for w in (m.project1.weight, m.project2.weight) for tr in (False, True)]
+            if entries:
+                self.castplan = ops.CastPlan(entries, dt)
+                self.castplan.fresh = False
+                for m in monas:
+                    m._ngu_castplan = self.castplan
         self.grad_clip = grad_clip
         self.accum = accumulation_steps
         self.micro = 0
@@ -229,6 +243,10 @@ class Trainer:
         m = self.model
         last = (self.micro + 1) % self.accum == 0
         self.buckets.enabled = last  # all-reduce only on the micro-step that completes an update
+        if self.castplan is not None and not self.castplan.fresh:
+            if self.castplan.valid():
+                self.castplan.run()
+                self.castplan.fresh = True
         fi = m.encode_image(images)
         ft = m.encode_text(ids)
         loss = self.criterion(fi, ft)
@@ -240,6 +258,8 @@ class Trainer:
                 # global-norm clip + AdamW + cosine LR + zero_grad on device; a non-finite loss skips the update
                 # (the reference's `if not torch.isfinite(loss): continue`, finetune.py:281-285, without the host sync)
                 self.optimizer.step(loss=loss.detach().float().view(1))
+                if self.castplan is not None:
+                    self.castplan.fresh = False   # parameters changed: shadows are re-made at the next micro-step
             else:
                 if self.grad_clip and self.grad_clip > 0:
                     torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip)

@@ -292,6 +292,45 @@ def embed_tokens(ids, word, pos, type0, dtype):
     return out
 
 
+class CastPlan:
+    """One-launch refresh of the low-precision shadows of a set of fp32 parameters (`ngu_cast_f32_batch`).
+
+    `entries`: list of (param, transpose).  Output tensors and the device-side item table are allocated once; `run()`
+    re-converts everything (call it after the parameters changed), `get(param, transpose)` returns the shadow.
+    Valid as long as the parameters keep their storage (they do: the optimizer updates in place)."""
+
+    def __init__(self, entries, dtype):
+        import numpy as np
+        self.dtype = dtype
+        self.outs = {}
+        items = (L.CastItem * len(entries))()
+        self._keep = []
+        for i, (p, tr) in enumerate(entries):
+            w = p.detach()
+            _need_cuda(w)
+            if w.dtype != torch.float32 or w.dim() != 2 or not w.is_contiguous():
+                raise ValueError("CastPlan: parameters must be contiguous 2-D fp32 tensors")
+            rows, cols = w.shape
+            out = torch.empty((cols, rows) if tr else (rows, cols), device=w.device, dtype=dtype)
+            items[i] = L.CastItem(w.data_ptr(), out.data_ptr(), rows, cols, int(tr), 1.0)
+            self.outs[(id(p), bool(tr))] = out
+            self._keep.append(p)
+        raw = np.frombuffer(bytes(items), dtype=np.uint8).copy()
+        self.table = torch.from_numpy(raw).to(self._keep[0].device)
+        self.n = len(entries)
+        self.ptrs = [p.data_ptr() for p in self._keep]
+
+    def valid(self):
+        return all(p.data_ptr() == q for p, q in zip(self._keep, self.ptrs))
+
+    def run(self):
+        code = L.NGU_BF16 if self.dtype == torch.bfloat16 else L.NGU_F32
+        L.check(L.lib().ngu_cast_f32_batch(self.table.data_ptr(), self.n, code, _stream()), "ngu_cast_f32_batch")
+
+    def get(self, p, transpose=False):
+        return self.outs.get((id(p), bool(transpose)))
+
+
 def cast(w, dtype, transpose=False, scale=1.0):
     """fp32 [rows, cols] parameter -> dtype copy (optionally transposed, scaled)."""
     _need_cuda(w)

@@ -217,3 +217,20 @@ def test_fused_adamw_matches_torch():
         p.grad.fill_(1.0)
     fo.step(loss=torch.full((1,), float("nan"), device=dev()))
     assert all(torch.equal(a, b) for a, b in zip(mine, before)) and float(gb.flat_grad.abs().sum()) == 0.0
+
+
+def test_cast_batch_matches_single_casts():
+    """ngu_cast_f32_batch (ops.CastPlan) == the per-tensor ngu_cast_f32 results, plain and transposed."""
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(12)
+    ps = [torch.nn.Parameter(torch.randn(r, c, device=dev())) for r, c in ((64, 768), (768, 64), (8, 768), (2304, 8))]
+    plan = ops.CastPlan([(p, tr) for p in ps for tr in (False, True)], torch.bfloat16)
+    plan.run()
+    for p in ps:
+        for tr in (False, True):
+            assert torch.equal(plan.get(p, tr), ops.cast(p, torch.bfloat16, transpose=tr))
+    with torch.no_grad():
+        ps[0].mul_(2.0)
+    plan.run()
+    assert torch.equal(plan.get(ps[0], True), ops.cast(ps[0], torch.bfloat16, transpose=True))
+    assert plan.valid()

@@ -48,6 +48,7 @@ struct AttnTcParams {
   CUtensorMap tmQKV;  // [B*N rows, 3*H*64 cols] bf16, box 64 cols x 128 rows, SWIZZLE_128B
   CUtensorMap tmDO;   // [B*N rows, H*64 cols]   bf16, same box (backward)
   CUtensorMap tmQKV1, tmDO1;  // backward, N > 128: boxes of ceil16(N - 128) rows for the second tile
+  CUtensorMap tmO3;           // forward output as [B, N, H*64], box 1 x 128 x 64: rows past N are clipped by the TMA store
   bf16* o;            // [B*N, H*64]
   const bf16* o_in;   // backward: forward output
   const bf16* d_o;    // backward
@@ -235,20 +236,30 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
       uint32_t ov[32];
       tmem_ld32(trow + 128 + hf * 32, ov);
       tmem_ld_wait();
-      if (r < N) {
-        const float inv = 1.f / sum;
-        bf16* dst = p.o + size_t(row0 + r) * D + h * DH + hf * 32;
+      // O tile staged in the (now dead) Q tile, 128B-swizzled rows of 64 head-dim values, and written with ONE TMA store:
+      // per-lane row stores (32 distinct lines per instruction) made the LSU the bottleneck of this phase.
+      {
+        const float inv = rcp_approx(sum);
+        const uint32_t rb = sQ + uint32_t(rt) * 128u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(ov[8 * j + 0]) * inv, __uint_as_float(ov[8 * j + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(ov[8 * j + 2]) * inv, __uint_as_float(ov[8 * j + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(ov[8 * j + 4]) * inv, __uint_as_float(ov[8 * j + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(ov[8 * j + 6]) * inv, __uint_as_float(ov[8 * j + 7]) * inv);
-          reinterpret_cast<uint4*>(dst)[j] = u;
+          const uint32_t a = rb + ((uint32_t(hf * 4 + j) ^ uint32_t(rt & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                       "r"(pack_bf16x2(__uint_as_float(ov[8 * j + 0]) * inv, __uint_as_float(ov[8 * j + 1]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(ov[8 * j + 2]) * inv, __uint_as_float(ov[8 * j + 3]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(ov[8 * j + 4]) * inv, __uint_as_float(ov[8 * j + 5]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(ov[8 * j + 6]) * inv, __uint_as_float(ov[8 * j + 7]) * inv))
+                       : "memory");
         }
-        if (p.lse && hf == 0) p.lse[(size_t(b) * p.H + h) * N + r] = mx * p.scale + logf(sum);
+        if (r < N && p.lse && hf == 0) p.lse[(size_t(b) * p.H + h) * N + r] = fmaf(mx, p.scale, 0.6931471805599453f * lg2_approx(sum));
       }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 9, %0;" ::"r"(32 * kFwdSoftmaxWarps) : "memory");   // all softmax warps (dead ones included)
+    if (warp == 0 && lane == 0) {
+      tma_store_3d(&p.tmO3, sQ, h * DH, t * TILE, b);
+      tma_store_commit();
+      tma_store_wait_read<0>();   // smem must outlive the store's read; global visibility comes with kernel completion
     }
   }
   tc_fence_before();
@@ -1020,6 +1031,9 @@ int fill_params(const ngu_attn_desc& d, AttnTcParams& p, bool bwd) {
     if ((rc = make_tmap_2d_bf16(&p.tmDO1, d.d_o, uint64_t(d.B) * d.N, D, D, rows1, DH, true))) return rc;
   } else {
     p.tmDO = p.tmQKV;
+  }
+  if (!bwd) {
+    if ((rc = make_tmap_3d_bf16(&p.tmO3, d.o, d.B, d.N, D, D, uint64_t(d.N) * D, TILE, DH, 1))) return rc;
   }
   p.o = reinterpret_cast<bf16*>(d.o);
   p.o_in = reinterpret_cast<const bf16*>(d.o);

@@ -159,6 +159,11 @@ NGU_DEVINL void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, in
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+NGU_DEVINL void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 NGU_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 NGU_DEVINL void tma_store_wait_read() {
@@ -474,6 +479,10 @@ template <> NGU_DEVINL bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn
 // 2-D row-major tensor [rows, cols] of bf16 with row pitch `ld` elements; box = [box_rows, box_cols].
 // swizzle: 0 none, 1 = SWIZZLE_128B (box_cols * 2 <= 128 bytes), 2 = SWIZZLE_64B (box_cols * 2 <= 64 bytes).
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols, int swizzle);
+// 3-D row-major tensor [batch, rows, cols] of bf16 (row pitch ld, batch pitch ldb elements), box = [1, box_rows, box_cols];
+// rows past `rows` inside a batch element are clipped on store / zero-filled on load.
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld, uint64_t ldb,
                       uint32_t box_rows, uint32_t box_cols, int swizzle);
 int sm_count();
 

@@ -78,6 +78,31 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return NGU_OK;
 }
 
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld, uint64_t ldb,
+                      uint32_t box_rows, uint32_t box_cols, int swizzle) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error("cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU?)"); return NGU_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * 2) & 15u) || ((ldb * 2) & 15u)) {
+    set_last_error("tensor map: base %p / pitches %llu, %llu B not 16-byte aligned", base, (unsigned long long)(ld * 2),
+                   (unsigned long long)(ldb * 2));
+    return NGU_ERR_ALIGN;
+  }
+  cuuint64_t gdim[3] = {cols, rows, batch};
+  cuuint64_t gstride[2] = {ld * 2, ldb * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(3d) failed (%d) batch=%llu rows=%llu cols=%llu", int(r), (unsigned long long)batch,
+                   (unsigned long long)rows, (unsigned long long)cols);
+    return NGU_ERR_CUDA;
+  }
+  return NGU_OK;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -246,7 +246,6 @@ class Trainer:
         if self.castplan is not None and not self.castplan.fresh:
             if self.castplan.valid():
                 self.castplan.run()
-                self.castplan.fresh = True
         fi = m.encode_image(images)
         ft = m.encode_text(ids)
         loss = self.criterion(fi, ft)

@@ -319,6 +319,8 @@ class CastPlan:
         self.table = torch.from_numpy(raw).to(self._keep[0].device)
         self.n = len(entries)
         self.ptrs = [p.data_ptr() for p in self._keep]
+        self._fresh = False
+        self._versions = None
 
     def valid(self):
         return all(p.data_ptr() == q for p, q in zip(self._keep, self.ptrs))
@@ -326,6 +328,18 @@ class CastPlan:
     def run(self):
         code = L.NGU_BF16 if self.dtype == torch.bfloat16 else L.NGU_F32
         L.check(L.lib().ngu_cast_f32_batch(self.table.data_ptr(), self.n, code, _stream()), "ngu_cast_f32_batch")
+        self._versions = [p._version for p in self._keep]
+        self._fresh = True
+
+    @property
+    def fresh(self):
+        """True while the shadows match the parameters: set by run(), cleared by the optimizer (whose fused kernel writes
+        the parameters through raw pointers) and by any in-place torch update (version counters) or re-allocation."""
+        return (self._fresh and self.valid() and self._versions == [p._version for p in self._keep])
+
+    @fresh.setter
+    def fresh(self, v):
+        self._fresh = bool(v)
 
     def get(self, p, transpose=False):
         return self.outs.get((id(p), bool(transpose)))

@@ -233,4 +233,9 @@ def test_cast_batch_matches_single_casts():
         ps[0].mul_(2.0)
     plan.run()
     assert torch.equal(plan.get(ps[0], True), ops.cast(ps[0], torch.bfloat16, transpose=True))
-    assert plan.valid()
+    assert plan.valid() and plan.fresh
+    with torch.no_grad():
+        ps[1].add_(1.0)          # an in-place torch update makes the shadows stale until the next run()
+    assert not plan.fresh
+    plan.run()
+    assert plan.fresh

@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(kFwdPThreads, 1) attn_fwd_persistent_kernel(co
 // query tile costs 64 + 16 columns instead of 128) and the kv extent of dQ to ceil16(live kv rows).
 constexpr int kBwdComputeWarps = 16;
 constexpr int kBwdThreads = 32 * (kBwdComputeWarps + 4);
-constexpr int kBwdSmem = 12 * kTileBytes + 2 * 2048 + 1024 + 1024;
+constexpr int kBwdSmem = 13 * kTileBytes + 2 * 2048 + 1024 + 1024;   // + one tile to transpose the accumulator read-out
 
 struct BwdStep {
   int j, i, ii, half, nq;  // ii: position of the pair within its kv tile; nq: live query columns padded to 16 (0 = dead)
@@ -735,7 +735,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = base + 2 * kTileBytes, sV = base + 4 * kTileBytes, sDO = base + 6 * kTileBytes;
   const uint32_t sDS = base + 8 * kTileBytes;   // 2 buffers x [2 q-chunks of 64][128 kv rows][128 B]
-  const uint32_t sStat = base + 12 * kTileBytes;  // [2 buffers][lse2[256], delta[256]] fp32
+  const uint32_t sOut = base + 12 * kTileBytes;   // [128 rows][128 B] staging tile of the coalesced accumulator stores
+  const uint32_t sStat = base + 13 * kTileBytes;  // [2 buffers][lse2[256], delta[256]] fp32
   const uint32_t sBar = sStat + 2 * 2048;
   // tile groups: 0 = {K0,V0}  1 = {K1,V1}  2 = {Q0,dO0}  3 = {Q1,dO1}
   auto bar_full = [&](int g) { return sBar + 8u * g; };           // 4: tile group landed
@@ -887,8 +888,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     // deferred read-out of dV_j / dK_j (/ dQ): done after the NEXT step's P^T so the issuer never waits for it
     bool pend = false;
     int pend_row0 = 0, pend_h = 0, pend_j = 0;
-    auto store16 = [&](bf16* dst, const uint32_t (&v)[16]) {
-      uint4 u0, u1;
+    // Accumulator read-out.  Each thread holds 16 columns of one row; storing them directly costs 32 LSU wavefronts per
+    // instruction (one 16/32-byte piece of 32 different rows).  The pieces are transposed through a 128B-swizzled smem
+    // tile instead and written as whole 128-byte rows (4 rows per instruction).
+    auto pack16 = [&](const uint32_t (&v)[16], uint4& u0, uint4& u1) {
       u0.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
       u0.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
       u0.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]));
@@ -897,32 +900,60 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       u1.y = pack_bf16x2(__uint_as_float(v[10]), __uint_as_float(v[11]));
       u1.z = pack_bf16x2(__uint_as_float(v[12]), __uint_as_float(v[13]));
       u1.w = pack_bf16x2(__uint_as_float(v[14]), __uint_as_float(v[15]));
-      reinterpret_cast<uint4*>(dst)[0] = u0;
-      reinterpret_cast<uint4*>(dst)[1] = u1;
+    };
+    const int ctid = threadIdx.x;                 // compute threads are 0 .. kCompute-1
+    // tile [128 x 64] (this thread's 2 pieces at row t) -> global rows `grow0 + r` (r < nrows), columns gcol .. gcol+63
+    auto flush_tile = [&](const uint4& u0, const uint4& u1, int grow0, int nrows, int gcol) {
+      asm volatile("bar.sync 10, %0;" ::"r"(kCompute) : "memory");          // previous tile fully copied out
+      const uint32_t rb = sOut + uint32_t(t) * 128u;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rb + ((uint32_t(hq * 2) ^ uint32_t(t & 7)) << 4)),
+                   "r"(u0.x), "r"(u0.y), "r"(u0.z), "r"(u0.w) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rb + ((uint32_t(hq * 2 + 1) ^ uint32_t(t & 7)) << 4)),
+                   "r"(u1.x), "r"(u1.y), "r"(u1.z), "r"(u1.w) : "memory");
+      asm volatile("bar.sync 10, %0;" ::"r"(kCompute) : "memory");
+#pragma unroll
+      for (int k = 0; k < (TILE * 8) / kCompute; ++k) {
+        const int idx = k * kCompute + ctid;
+        const int r = idx >> 3, pc8 = idx & 7;
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(sOut + uint32_t(r) * 128u + ((uint32_t(pc8) ^ uint32_t(r & 7)) << 4)));
+        if (r < nrows) *reinterpret_cast<uint4*>(p.dqkv + size_t(grow0 + r) * 3 * D + gcol + pc8 * 8) = v;
+      }
     };
     auto drain = [&]() {
       mbar_wait(bar_acc, accn & 1u);
       ++accn;
       tc_fence_after();
-      const int kv = pend_j * TILE + t;
-      uint32_t a[16], bq[16];
-      tmem_ld16(trow + cDV + hq * 16, a);
-      tmem_ld16(trow + cDK + hq * 16, bq);
-      tmem_ld_wait();
-      if (kv < N) {
-        bf16* dst = p.dqkv + size_t(pend_row0 + kv) * 3 * D + pend_h * DH + hq * 16;
-        store16(dst + 2 * D, a);
-        store16(dst + D, bq);
-      }
-      if (pend_j == ntiles - 1) {
-        tmem_ld16(trow + cDQ + hq * 16, a);
-        if (ntiles == 2) tmem_ld16(trow + cDQ + 64 + hq * 16, bq);
+      const bool with_dq = pend_j == ntiles - 1;
+      uint4 v0, v1, k0, k1, q0, q1, q2, q3;
+      {
+        uint32_t a[16], bq[16];
+        tmem_ld16(trow + cDV + hq * 16, a);
+        tmem_ld16(trow + cDK + hq * 16, bq);
         tmem_ld_wait();
-        if (t < N) store16(p.dqkv + size_t(pend_row0 + t) * 3 * D + pend_h * DH + hq * 16, a);
-        if (ntiles == 2 && TILE + t < N) store16(p.dqkv + size_t(pend_row0 + TILE + t) * 3 * D + pend_h * DH + hq * 16, bq);
+        pack16(a, v0, v1);
+        pack16(bq, k0, k1);
+        if (with_dq) {
+          tmem_ld16(trow + cDQ + hq * 16, a);
+          if (ntiles == 2) tmem_ld16(trow + cDQ + 64 + hq * 16, bq);
+          tmem_ld_wait();
+          pack16(a, q0, q1);
+          if (ntiles == 2) pack16(bq, q2, q3);
+        }
       }
+      // TMEM is free again: let the issuer go on before the (slower) global stores
       tc_fence_before();
       mbar_arrive(bar_drained);
+      int nkv = N - pend_j * TILE;
+      nkv = nkv > TILE ? TILE : nkv;
+      const int grow = pend_row0 + pend_j * TILE;
+      flush_tile(v0, v1, grow, nkv, 2 * D + pend_h * DH);
+      flush_tile(k0, k1, grow, nkv, D + pend_h * DH);
+      if (with_dq) {
+        flush_tile(q0, q1, pend_row0, N > TILE ? TILE : N, pend_h * DH);
+        if (ntiles == 2) flush_tile(q2, q3, pend_row0 + TILE, N - TILE, pend_h * DH);
+      }
       pend = false;
     };
     for (int n = 0; n < n_local; ++n) {

@@ -98,6 +98,19 @@ int infonce_normalize_bwd(const float* dxhat, const float* xhat, const float* no
 }
 
 // ws: fp32 workspace of 2*Bg*Bg + 2*Bg floats.  loss must be zeroed by this call.
+// Lt = L^T for the [n, n] fp32 logits (32 x 32 smem tiles, conflict-free): the text->image logits are the transpose of the
+// image->text logits, so a second n x n x E GEMM is not needed.
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (by + r < n && bx + tx < n) tile[r][tx] = in[size_t(by + r) * n + bx + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (bx + r < n && by + tx < n) out[size_t(bx + r) * n + by + tx] = tile[tx][r];
+}
+
 int infonce_core(const ngu_infonce_desc& d, cudaStream_t st) {
   const int n = d.Bg, E = d.E;
   if (n <= 0 || E <= 0 || d.Bl <= 0 || d.r0 < 0 || d.r0 + d.Bl > n) { set_last_error("infonce: bad shape Bg=%d Bl=%d r0=%d", n, d.Bl, d.r0); return NGU_ERR_SHAPE; }
@@ -113,8 +126,11 @@ int infonce_core(const ngu_infonce_desc& d, cudaStream_t st) {
   g.M = n; g.N = n; g.K = E; g.lda = E; g.ldb = E; g.ldc = n; g.alpha = 1.f / d.temperature; g.dtype = NGU_F32;
   g.A = d.ihat; g.B = d.that; g.C = L;
   if (int rc = gemm_simt(g, st)) return rc;
-  g.A = d.that; g.B = d.ihat; g.C = Lt;
-  if (int rc = gemm_simt(g, st)) return rc;
+  {
+    const dim3 tg((n + 31) / 32, (n + 31) / 32);
+    transpose_kernel<<<tg, 256, 0, st>>>(L, Lt, n);
+    if (int rc = check_launch("infonce transpose")) return rc;
+  }
   const int wpb = 4;
   const int grid = (n + wpb - 1) / wpb;
   row_lse_kernel<<<grid, wpb * 32, 0, st>>>(L, rlse, d.loss, n, 0.5f / float(n));

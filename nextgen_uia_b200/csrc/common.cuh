@@ -552,14 +552,20 @@ NGU_DEVINL uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) 
   return make_uint4(c[0], c[1], c[2], c[3]);
 }
 // keep-mask for element `idx` of a tensor under dropout probability p: returns 1/(1-p) or 0.
-// Counter-based (stateless, regenerated in backward from seed + element index): splitmix64 finaliser of
-// (seed, idx) — ~12 integer instructions per element instead of a 10-round Philox.
-NGU_DEVINL float dropout_scale(uint64_t seed, uint64_t idx, float p) {
-  uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
+// Counter-based (stateless, regenerated in backward from seed + element index): one splitmix64 finaliser of
+// (seed, idx / 4) yields the 16-bit uniforms of four consecutive elements, so vectorised kernels hash once per
+// four elements; every user (LoRA dropout kernel, Mona conv stage forward / backward) goes through these two functions.
+NGU_DEVINL uint64_t dropout_bits(uint64_t seed, uint64_t group) {
+  uint64_t z = group * 0x9E3779B97F4A7C15ull + seed;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = float(uint32_t(z >> 40)) * (1.0f / 16777216.0f);
-  return u >= p ? 1.0f / (1.0f - p) : 0.0f;
+  return z ^ (z >> 31);
+}
+NGU_DEVINL uint32_t dropout_threshold(float p) { return uint32_t(p * 65536.0f); }
+NGU_DEVINL float dropout_pick(uint64_t bits, int lane4, uint32_t thr, float keep_scale) {
+  return (uint32_t(bits >> (16 * lane4)) & 0xFFFFu) >= thr ? keep_scale : 0.0f;
+}
+NGU_DEVINL float dropout_scale(uint64_t seed, uint64_t idx, float p) {
+  return dropout_pick(dropout_bits(seed, idx >> 2), int(idx & 3), dropout_threshold(p), 1.0f / (1.0f - p));
 }
 }  // namespace ngu

@@ -191,7 +191,27 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, in
 // out = (accumulate ? out : 0) + x * mask(seed, i) / (1-p)   (LoRA input dropout, src/adapters/lora.py:82-83)
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ out, size_t n, float p, uint64_t seed, int accumulate) {
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+  // one 16-byte vector per thread and iteration, one hash per four elements
+  constexpr int V = Vec<T>::N;
+  const uint32_t thr = dropout_threshold(p);
+  const float ks = 1.0f / (1.0f - p);
+  const size_t nv = n / V;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += size_t(gridDim.x) * blockDim.x) {
+    float v[V], o[V];
+    Vec<T>::load(x + i * V, v);
+    if (accumulate) Vec<T>::load(out + i * V, o);
+#pragma unroll
+    for (int g = 0; g < V / 4; ++g) {
+      const uint64_t bits = dropout_bits(seed, (i * V) / 4 + g);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float r = v[4 * g + e] * dropout_pick(bits, e, thr, ks);
+        v[4 * g + e] = accumulate ? r + o[4 * g + e] : r;
+      }
+    }
+    Vec<T>::store(out + i * V, v);
+  }
+  for (size_t i = nv * V + size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
     float v = to_f32<T>(x[i]) * dropout_scale(seed, i, p);
     if (accumulate) v += to_f32<T>(out[i]);
     out[i] = from_f32<T>(v);
@@ -248,8 +268,9 @@ int cast_f32_batch(const ngu_cast_item* items, int n, int dtype, cudaStream_t st
 }
 int dropout(const void* x, void* out, size_t n, float p, uint64_t seed, int accumulate, int dtype, cudaStream_t st) {
   if (n == 0 || p < 0.f || p >= 1.f) { set_last_error("dropout: bad n/p"); return NGU_ERR_ARG; }
-  if (dtype == NGU_F32) dropout_kernel<float><<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(out), n, p, seed, accumulate);
-  else dropout_kernel<bf16><<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out), n, p, seed, accumulate);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15u) { set_last_error("dropout: pointers must be 16-byte aligned"); return NGU_ERR_ALIGN; }
+  if (dtype == NGU_F32) dropout_kernel<float><<<grid_for(n / 4 + 1), 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(out), n, p, seed, accumulate);
+  else dropout_kernel<bf16><<<grid_for(n / 8 + 1), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out), n, p, seed, accumulate);
   return check_launch("dropout");
 }
 int wgrad_simt(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int Tn, int Mo, int No, int dtype, cudaStream_t st) {

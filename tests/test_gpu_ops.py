@@ -239,3 +239,28 @@ def test_cast_batch_matches_single_casts():
     assert not plan.fresh
     plan.run()
     assert plan.fresh
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dropout_kernel_mask_statistics_and_regeneration(dtype):
+    """ngu_dropout: keep rate ~ 1-p, kept values scaled by 1/(1-p), the same (seed, index) mask on every call (the
+    backward regenerates it), a different mask for another seed, and `accumulate` adds into the output."""
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(13)
+    n, p = 1_000_003 - 3, 0.25            # multiple of 8, so every element goes through the vector path
+    x = torch.ones(n, device=dev(), dtype=dtype)
+    a = ops.dropout(x, p, 1234)
+    b = ops.dropout(x, p, 1234)
+    c = ops.dropout(x, p, 99)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    keep = (a != 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 3e-3
+    kept = a[a != 0].float()
+    assert torch.allclose(kept, torch.full_like(kept, 1 / (1 - p)), rtol=1e-2)
+    # no structure across the four elements that share one hash
+    m = (a != 0).float().view(-1, 4)
+    assert (m.mean(0) - (1 - p)).abs().max().item() < 5e-3
+    assert abs(torch.corrcoef(m.t())[0, 1].item()) < 1e-2
+    out = torch.full_like(x, 2.0)
+    ops.dropout(x, p, 1234, out=out, accumulate=True)
+    assert torch.allclose(out.float(), a.float() + 2.0, rtol=1e-2)

@@ -257,6 +257,8 @@ class Trainer:
                 # global-norm clip + AdamW + cosine LR + zero_grad on device; a non-finite loss skips the update
                 # (the reference's `if not torch.isfinite(loss): continue`, finetune.py:281-285, without the host sync)
                 self.optimizer.step(loss=loss.detach().float().view(1))
+                from . import ops as _ops
+                _ops.bump_param_epoch()           # raw-pointer parameter update: invalidate low-precision shadows
                 if self.castplan is not None:
                     self.castplan.fresh = False   # parameters changed: shadows are re-made at the next micro-step
             else:

@@ -50,12 +50,29 @@ class Proj:
             self.p = float(drop.p) if (drop is not None and linear.training) else 0.0
 
 
-def _lora_operands(pj, dtype):
-    A, B = pj.A.detach(), pj.B.detach()
-    if pj.rp != pj.r:  # zero-pad the tiny fp32 factors to the padded rank
-        A = F.pad(A, (0, 0, 0, pj.rp - pj.r))
-        B = F.pad(B, (0, pj.rp - pj.r))
-    return A.contiguous(), B.contiguous()
+def _lora_shadows(pj, dtype):
+    """(A [rp,K], B [N,rp], A^T [K,rp], B^T [rp,N]) in `dtype`, rank zero-padded to pj.rp.  Made once per parameter
+    update (keyed on the tensors' version counters and ops.PARAM_EPOCH) and shared by forward and backward, instead of
+    padding and casting the factors four times per projection per step."""
+    A, B = pj.A, pj.B
+    key = (A._version, B._version, ops.PARAM_EPOCH[0], A.data_ptr(), B.data_ptr(), dtype, pj.rp)
+    cache = getattr(A, "_ngu_shadow", None)
+    if cache is None or cache[0] != key:
+        r, K = A.shape
+        N = B.shape[0]
+        bufs = cache[1] if (cache is not None and cache[1][0].dtype == dtype and cache[1][0].shape == (pj.rp, K)
+                            and cache[1][1].shape == (N, pj.rp)) else None
+        if bufs is None:   # zero padding is written once; updates only touch the live rank
+            bufs = (torch.zeros(pj.rp, K, device=A.device, dtype=dtype), torch.zeros(N, pj.rp, device=A.device, dtype=dtype),
+                    torch.zeros(K, pj.rp, device=A.device, dtype=dtype), torch.zeros(pj.rp, N, device=A.device, dtype=dtype))
+        with torch.no_grad():
+            bufs[0][:r].copy_(A)
+            bufs[1][:, :r].copy_(B)
+            bufs[2][:, :r].copy_(A.t())
+            bufs[3][:r].copy_(B.t())
+        cache = (key, bufs)
+        A._ngu_shadow = cache
+    return cache[1]
 
 
 def _k2(pj):
@@ -69,12 +86,12 @@ def proj_fwd(x2, pj, *, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save_pre=
     if pj.A is None:
         return ops.gemm(x2, pj.W, bias=bias, act=act, aux=aux, aux_mode=aux_mode, save_pre=save_pre), None
     dt = x2.dtype
-    A32, B32 = _lora_operands(pj, dt)
+    A16, B16, _, _ = _lora_shadows(pj, dt)
     xd = ops.dropout(x2, pj.p, seed) if pj.p > 0 else x2
-    t = ops.gemm(xd, ops.cast(A32, dt), alpha=pj.scaling)                       # [M, rp] = s * drop(x) A^T
+    t = ops.gemm(xd, A16, alpha=pj.scaling)                                     # [M, rp] = s * drop(x) A^T
     k2 = _k2(pj)
     out = ops.gemm(x2, pj.W, bias=bias, act=act, aux=aux, aux_mode=aux_mode, save_pre=save_pre,
-                   A2=t[:, :k2], B2=ops.cast(B32, dt)[:, :k2])
+                   A2=t[:, :k2], B2=B16[:, :k2])
     return out, (xd, t, seed)
 
 
@@ -85,13 +102,12 @@ def proj_bwd(dy2, pj, saved, *, need_dx=True, need_bias=False):
         return (ops.gemm(dy2, pj.WT) if need_dx else None), dbias, None, None
     dt = dy2.dtype
     xd, t, seed = saved
-    A32, B32 = _lora_operands(pj, dt)
-    dts = ops.gemm(dy2, ops.cast(B32, dt, transpose=True), alpha=pj.scaling)    # [M, rp] = s * dy B
+    _, _, At, Bt = _lora_shadows(pj, dt)
+    dts = ops.gemm(dy2, Bt, alpha=pj.scaling)                                   # [M, rp] = s * dy B
     dB = ops.wgrad(dy2, t)[:, :pj.r].contiguous()                               # [N, r]
     dA = ops.wgrad(xd, dts)[:, :pj.r].t().contiguous()                          # [r, K]
     dx = None
     if need_dx:
-        At = ops.cast(A32, dt, transpose=True)                                  # [K, rp]
         if pj.p > 0:
             dx = ops.gemm(dy2, pj.WT)
             ops.dropout(ops.gemm(dts, At), pj.p, seed, out=dx, accumulate=True)

@@ -292,6 +292,15 @@ def embed_tokens(ids, word, pos, type0, dtype):
     return out
 
 
+# Bumped whenever parameters are rewritten behind autograd's back (the fused optimizer updates the flat parameter buffer
+# through raw pointers, so tensor version counters do not move).  Low-precision shadows are keyed on it.
+PARAM_EPOCH = [0]
+
+
+def bump_param_epoch():
+    PARAM_EPOCH[0] += 1
+
+
 class CastPlan:
     """One-launch refresh of the low-precision shadows of a set of fp32 parameters (`ngu_cast_f32_batch`).
 

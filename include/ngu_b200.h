@@ -233,7 +233,9 @@ typedef struct ngu_adamw_desc {
 int ngu_adamw_step(const ngu_adamw_desc* d, void* stream);
 
 /* Patch-embed im2col (stride == kernel, timm PatchEmbed / CLIP conv1): images fp32 NCHW [B,3,R,R]
- * -> [B*(R/P)^2, 3*P*P]; and token assembly x0[b,0]=cls+pos[0], x0[b,1+p]=patch[b,p]+pos[1+p]. */
+ * -> [B*(R/P)^2, Kp] with row pitch Kp = 3*P*P rounded up to a multiple of 8 (P = 14: 588 -> 592; the caller zero-fills
+ * the buffer once, the kernel writes the 3*P*P live columns; pixels past the last whole patch are dropped like the conv);
+ * and token assembly x0[b,0]=cls+pos[0], x0[b,1+p]=patch[b,p]+pos[1+p]. */
 int ngu_patchify(const float* img, void* out, int B, int R, int P, int dtype, void* stream);
 int ngu_assemble_tokens(const void* patch, const float* cls, const float* pos, void* out, int B, int np, int D,
                         int dtype, void* stream);

@@ -9,21 +9,46 @@ namespace ngu {
 namespace {
 
 // images [B,3,R,R] fp32 (NCHW) -> patches [B*G*G, 3*P*P] (T), column order (c, py, px) = conv weight flattening.
-// Thread per 4 consecutive pixels of one image row: one 16-byte load, one contiguous store (P % 4 == 0).
+// Thread per 8 consecutive pixels of one image row: two 16-byte loads, one contiguous 16/32-byte store (P % 8 == 0);
+// 32-bit index math.
 template <typename T>
 __global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int R, int P) {
-  const int G = R / P, K = 3 * P * P;
-  const size_t total4 = size_t(B) * 3 * R * R / 4;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total4; i += size_t(gridDim.x) * blockDim.x) {
-    const size_t e = i * 4;
-    const int xx = int(e % R);
-    const int yy = int((e / R) % R);
-    const int c = int((e / (size_t(R) * R)) % 3);
-    const int b = int(e / (size_t(3) * R * R));
-    const float4 v = *reinterpret_cast<const float4*>(img + e);
-    const int gx = xx / P, px = xx % P, gy = yy / P, py = yy % P;
+  const unsigned G = R / P, K = 3 * P * P, R8 = R / 8;
+  const unsigned total8 = unsigned(B) * 3u * unsigned(R) * R8;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += gridDim.x * blockDim.x) {
+    const unsigned x8 = i % R8, rowi = i / R8;            // rowi = (b*3 + c)*R + yy
+    const unsigned yy = rowi % unsigned(R), bc = rowi / unsigned(R);
+    const unsigned c = bc % 3u, b = bc / 3u;
+    const unsigned xx = x8 * 8;
+    const float4 v0 = *reinterpret_cast<const float4*>(img + size_t(i) * 8);
+    const float4 v1 = *reinterpret_cast<const float4*>(img + size_t(i) * 8 + 4);
+    const unsigned gx = xx / unsigned(P), px = xx % unsigned(P), gy = yy / unsigned(P), py = yy % unsigned(P);
     T* dst = out + (size_t(b) * G * G + size_t(gy) * G + gx) * K + c * P * P + py * P + px;
-    dst[0] = from_f32<T>(v.x); dst[1] = from_f32<T>(v.y); dst[2] = from_f32<T>(v.z); dst[3] = from_f32<T>(v.w);
+    const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    if (sizeof(T) == 2) {
+      uint4 u;
+      u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(dst) = u;
+    } else {
+      reinterpret_cast<float4*>(dst)[0] = v0;
+      reinterpret_cast<float4*>(dst)[1] = v1;
+    }
+  }
+}
+
+// Any patch size (ViT-L/14): thread per pixel; output rows have pitch Kp = ceil8(3*P*P), the tail stays as the caller
+// initialised it (zero) so the row is a legal K operand of the GEMM.
+template <typename T>
+__global__ void patchify_generic_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int R, int P, int Kp) {
+  const unsigned G = R / P;
+  const unsigned total = unsigned(B) * 3u * unsigned(R) * unsigned(R);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned xx = i % unsigned(R), rowi = i / unsigned(R);
+    const unsigned yy = rowi % unsigned(R), bc = rowi / unsigned(R);
+    const unsigned c = bc % 3u, b = bc / 3u;
+    const unsigned gx = xx / unsigned(P), px = xx % unsigned(P), gy = yy / unsigned(P), py = yy % unsigned(P);
+    if (gx >= G || gy >= G) continue;                      // pixels beyond the last whole patch are dropped (conv stride = P)
+    out[(size_t(b) * G * G + size_t(gy) * G + gx) * Kp + c * P * P + py * P + px] = from_f32<T>(img[i]);
   }
 }
 
@@ -228,8 +253,16 @@ int grid_for(size_t total) {
 
 int patchify(const float* img, void* out, int B, int R, int P, int dtype, cudaStream_t st) {
   if (B <= 0 || R <= 0 || P <= 0 || R % P) { set_last_error("patchify: bad shape B=%d R=%d P=%d", B, R, P); return NGU_ERR_SHAPE; }
-  if (P % 4) { set_last_error("patchify: patch size must be a multiple of 4"); return NGU_ERR_SHAPE; }
-  const size_t total = size_t(B) * (R / P) * (R / P) * 3 * P * P / 4;
+  if (B <= 0 || P <= 0 || R < P) { set_last_error("patchify: bad shape B=%d R=%d P=%d", B, R, P); return NGU_ERR_SHAPE; }
+  if (size_t(B) * 3 * R * R >= (size_t(1) << 32)) { set_last_error("patchify: more than 2^32 pixels"); return NGU_ERR_SHAPE; }
+  if (P % 8 || R % P) {
+    const int Kp = (3 * P * P + 7) & ~7;
+    const size_t tot = size_t(B) * 3 * R * R;
+    if (dtype == NGU_F32) patchify_generic_kernel<float><<<grid_for(tot), 256, 0, st>>>(img, reinterpret_cast<float*>(out), B, R, P, Kp);
+    else patchify_generic_kernel<bf16><<<grid_for(tot), 256, 0, st>>>(img, reinterpret_cast<bf16*>(out), B, R, P, Kp);
+    return check_launch("patchify");
+  }
+  const size_t total = size_t(B) * 3 * R * R / 8;
   if (dtype == NGU_F32) patchify_kernel<float><<<grid_for(total), 256, 0, st>>>(img, reinterpret_cast<float*>(out), B, R, P);
   else patchify_kernel<bf16><<<grid_for(total), 256, 0, st>>>(img, reinterpret_cast<bf16*>(out), B, R, P);
   return check_launch("patchify");

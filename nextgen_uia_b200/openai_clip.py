@@ -18,6 +18,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib as L
 from . import ops
@@ -195,8 +196,10 @@ class VisionTransformer(nn.Module):
             B = images.shape[0]
             P = self.conv1.kernel_size[0]
             patches = ops.patchify(images.float().contiguous(), P, dt)
-            W = _cached_cast(self.conv1.weight, ("2d", dt),
-                             lambda: ops.cast(self.conv1.weight.detach().float().view(self.conv1.weight.shape[0], -1).contiguous(), dt))
+            def _w2d():   # [width, 3*P*P], K zero-padded to the patch rows' pitch (ViT-L/14: 588 -> 592)
+                w = self.conv1.weight.detach().float().view(self.conv1.weight.shape[0], -1)
+                return ops.cast(F.pad(w, (0, patches.shape[1] - w.shape[1])).contiguous(), dt)
+            W = _cached_cast(self.conv1.weight, ("2d", dt), _w2d)
             tok = ops.gemm(patches, W)
             x = ops.assemble_tokens(tok, self.class_embedding.detach().contiguous(), self.positional_embedding.detach().contiguous(), B)
             x, _, _ = ops.ln_fwd(x, self.ln_pre.weight.detach(), self.ln_pre.bias.detach(), self.ln_pre.eps, save_stats=False)

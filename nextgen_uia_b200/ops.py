@@ -267,7 +267,9 @@ def patchify(img, P, dtype):
     B, _, R, R2 = img.shape
     assert R == R2
     G = R // P
-    out = torch.empty(B * G * G, 3 * P * P, device=img.device, dtype=dtype)
+    K = 3 * P * P
+    Kp = (K + 7) // 8 * 8                     # row pitch the GEMM can consume (P = 14: 588 -> 592, tail stays zero)
+    out = torch.empty(B * G * G, K, device=img.device, dtype=dtype) if Kp == K else torch.zeros(B * G * G, Kp, device=img.device, dtype=dtype)
     L.check(L.lib().ngu_patchify(img.data_ptr(), out.data_ptr(), B, R, P, _dt(out), _stream()), "ngu_patchify")
     return out
 

@@ -345,3 +345,43 @@ def test_device_feeder_overlapped_copies_are_intact():
     assert len(sums) == 7 and feeder.h2d_bytes == sum(a.numel() * 4 + b.numel() * 8 for a, b in host)
     for s, r in zip(sums, ref):
         assert abs(s - r) <= 1e-3 * max(1.0, abs(r))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_openai_clip_patch14_vision_tower_vs_oracle(dtype):
+    """Config-4 geometry in miniature: 14-pixel patches (ViT-L/14) -> 3*14*14 = 588 is not a multiple of 8, so the patch
+    rows and the conv1 weight are zero-padded to 592 for the GEMM.  Image features and Mona gradients vs the oracle."""
+    from nextgen_uia_b200.openai_clip import CLIP
+    from src.adapters import inject_mona_variant_to_clip
+    import oracle.functional as OF
+    torch.manual_seed(21)
+    m = CLIP(64, 56, 2, 256, 14, 8, 50, 64, 1, 1)
+    for p in m.parameters():
+        p.requires_grad = False
+    inject_mona_variant_to_clip(m, variant="baseline", bottleneck_dim=64)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "mona" in n and ("project2" in n or "gamma" in n):
+                p.add_(torch.randn_like(p) * 0.05)
+    trainable = [n for n, p in m.named_parameters() if "mona" in n]
+    for n, p in m.named_parameters():
+        p.requires_grad = n in trainable
+    images = torch.rand(3, 3, 56, 56)
+    gi = torch.randn(3, 64)
+    p64 = {k: (v.detach().double().clone().requires_grad_(k in trainable) if v.is_floating_point() else v) for k, v in m.state_dict().items()}
+    ocfg = dict(patch=14, depth=2, heads=4, text_layers=1, text_heads=1)
+    fo = OF.clip_encode_image(p64, images.double(), ocfg)
+    go = torch.autograd.grad((fo * gi.double()).sum(), [p64[n] for n in trainable])
+    m = m.to(dev()).eval().set_compute_dtype(dtype)
+    fi = m.encode_image(images.to(dev()))
+    (fi.float() * gi.to(dev())).sum().backward()
+    assert relerr(fi, fo) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
+    num = den = 0.0
+    params = dict(m.named_parameters())
+    for n, b in zip(trainable, go):
+        a = params[n].grad
+        assert a is not None, n
+        d = a.double().cpu() - b
+        num += float((d * d).sum()); den += float((b * b).sum())
+    assert (num / den) ** 0.5 < (5e-2 if dtype == torch.bfloat16 else 1e-3)

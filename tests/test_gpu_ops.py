@@ -264,3 +264,20 @@ def test_dropout_kernel_mask_statistics_and_regeneration(dtype):
     out = torch.full_like(x, 2.0)
     ops.dropout(x, p, 1234, out=out, accumulate=True)
     assert torch.allclose(out.float(), a.float() + 2.0, rtol=1e-2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("R,P", [(224, 16), (56, 14), (70, 14), (64, 8)])
+def test_patchify_matches_unfold(dtype, R, P):
+    """ngu_patchify == F.unfold(kernel = stride = P): the im2col of timm PatchEmbed / CLIP conv1, for the 16-pixel patches
+    of ViT-B/16 (vector path) and the 14-pixel patches of ViT-L/14 (generic path, rows zero-padded to a multiple of 8)."""
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(14)
+    B = 3
+    img = torch.rand(B, 3, R, R, device=dev())
+    out = ops.patchify(img, P, dtype)
+    G, K = R // P, 3 * P * P
+    ref = F.unfold(img[:, :, :G * P, :G * P], kernel_size=P, stride=P).transpose(1, 2).reshape(B * G * G, K)
+    assert out.shape == (B * G * G, (K + 7) // 8 * 8)
+    assert relerr(out[:, :K], ref) < (1e-6 if dtype == torch.float32 else 4e-3)
+    assert float(out[:, K:].float().abs().max()) == 0.0 if out.shape[1] > K else True

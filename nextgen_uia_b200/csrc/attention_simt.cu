@@ -85,19 +85,22 @@ attn_fwd_simt_kernel(ngu_attn_desc d) {
 }
 
 // Backward: pass A (warp per query row) -> dq; pass B (warp per key row) -> dk, dv.  Probabilities
-// are recomputed from the saved log-sum-exp.
+// are recomputed from the saved log-sum-exp.  When Q, dO, K and V do not fit in shared memory together (N = 577 of
+// ViT-L/14@336, N = 485 of ViT-B/16@352) the kernel runs in two phases that share one pair of tiles: K/V resident for pass A
+// (the warp's q / dO row comes from global memory), then Q/dO resident for pass B (k / v row from global memory).
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32)
-attn_bwd_simt_kernel(ngu_attn_desc d) {
+attn_bwd_simt_kernel(ngu_attn_desc d, int two_phase) {
   constexpr int LD = Pad<T>::LD;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int b = blockIdx.x / d.H, hd = blockIdx.x % d.H;
   const int N = d.N, S = d.S;
+  const int Lr = N > S ? N : S;
   T* Qs = reinterpret_cast<T*>(smem_dyn);
-  T* dOs = Qs + N * LD;
-  T* Ks = dOs + N * LD;
-  T* Vs = Ks + S * LD;
-  float* delta = reinterpret_cast<float*>(Vs + S * LD);  // [N]
+  T* dOs = Qs + (two_phase ? Lr : N) * LD;
+  T* Ks = two_phase ? Qs : dOs + N * LD;
+  T* Vs = two_phase ? dOs : Ks + S * LD;
+  float* delta = reinterpret_cast<float*>((two_phase ? dOs + Lr * LD : Vs + S * LD));  // [N]
   float* lse_s = delta + N;                              // [N]
   const int L = N > S ? N : S;
   float* buf0 = lse_s + N;                               // [kWarps][L]
@@ -111,8 +114,10 @@ attn_bwd_simt_kernel(ngu_attn_desc d) {
   T* dq = reinterpret_cast<T*>(d.dq) + int64_t(b) * d.q_bs + hd * DH;
   T* dk = reinterpret_cast<T*>(d.dk) + int64_t(b) * d.k_bs + hd * DH;
   T* dv = reinterpret_cast<T*>(d.dv) + int64_t(b) * d.v_bs + hd * DH;
-  load_tile<T>(Qs, q, N, d.q_ts);
-  load_tile<T>(dOs, dO, N, d.o_ts);
+  if (!two_phase) {
+    load_tile<T>(Qs, q, N, d.q_ts);
+    load_tile<T>(dOs, dO, N, d.o_ts);
+  }
   load_tile<T>(Ks, k, S, d.k_ts);
   load_tile<T>(Vs, v, S, d.v_ts);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,8 +133,13 @@ attn_bwd_simt_kernel(ngu_attn_desc d) {
   float* rw = rowb + warp * 2 * DH;
   // pass A: dq_i = scale * sum_j ds_ij k_j
   for (int i = warp; i < N; i += kWarps) {
-    rw[lane] = to_f32<T>(Qs[i * LD + lane]); rw[lane + 32] = to_f32<T>(Qs[i * LD + lane + 32]);
-    rw[DH + lane] = to_f32<T>(dOs[i * LD + lane]); rw[DH + lane + 32] = to_f32<T>(dOs[i * LD + lane + 32]);
+    if (two_phase) {
+      rw[lane] = to_f32<T>(q[int64_t(i) * d.q_ts + lane]); rw[lane + 32] = to_f32<T>(q[int64_t(i) * d.q_ts + lane + 32]);
+      rw[DH + lane] = to_f32<T>(dO[int64_t(i) * d.o_ts + lane]); rw[DH + lane + 32] = to_f32<T>(dO[int64_t(i) * d.o_ts + lane + 32]);
+    } else {
+      rw[lane] = to_f32<T>(Qs[i * LD + lane]); rw[lane + 32] = to_f32<T>(Qs[i * LD + lane + 32]);
+      rw[DH + lane] = to_f32<T>(dOs[i * LD + lane]); rw[DH + lane + 32] = to_f32<T>(dOs[i * LD + lane + 32]);
+    }
     __syncwarp();
     const float li = lse_s[i], di = delta[i];
     for (int j = lane; j < S; j += 32) {
@@ -155,9 +165,20 @@ attn_bwd_simt_kernel(ngu_attn_desc d) {
     __syncwarp();
   }
   // pass B: dv_j = sum_i p_ij dO_i ; dk_j = scale * sum_i ds_ij q_i
+  if (two_phase) {   // the K/V tiles make room for Q/dO
+    __syncthreads();
+    load_tile<T>(Qs, q, N, d.q_ts);
+    load_tile<T>(dOs, dO, N, d.o_ts);
+    __syncthreads();
+  }
   for (int j = warp; j < S; j += kWarps) {
-    rw[lane] = to_f32<T>(Ks[j * LD + lane]); rw[lane + 32] = to_f32<T>(Ks[j * LD + lane + 32]);
-    rw[DH + lane] = to_f32<T>(Vs[j * LD + lane]); rw[DH + lane + 32] = to_f32<T>(Vs[j * LD + lane + 32]);
+    if (two_phase) {
+      rw[lane] = to_f32<T>(k[int64_t(j) * d.k_ts + lane]); rw[lane + 32] = to_f32<T>(k[int64_t(j) * d.k_ts + lane + 32]);
+      rw[DH + lane] = to_f32<T>(v[int64_t(j) * d.v_ts + lane]); rw[DH + lane + 32] = to_f32<T>(v[int64_t(j) * d.v_ts + lane + 32]);
+    } else {
+      rw[lane] = to_f32<T>(Ks[j * LD + lane]); rw[lane + 32] = to_f32<T>(Ks[j * LD + lane + 32]);
+      rw[DH + lane] = to_f32<T>(Vs[j * LD + lane]); rw[DH + lane + 32] = to_f32<T>(Vs[j * LD + lane + 32]);
+    }
     __syncwarp();
     for (int i = lane; i < N; i += 32) {
       float s = 0.f, dp = 0.f;
@@ -202,11 +223,17 @@ template <typename T>
 int launch_bwd(const ngu_attn_desc& d, cudaStream_t st) {
   constexpr int LD = Pad<T>::LD;
   const int L = d.N > d.S ? d.N : d.S;
-  const int smem = (2 * d.N + 2 * d.S) * LD * int(sizeof(T)) + 2 * d.N * 4 + 2 * kWarps * L * 4 + kWarps * 2 * DH * 4;
+  const int rest = 2 * d.N * 4 + 2 * kWarps * L * 4 + kWarps * 2 * DH * 4;
+  int smem = (2 * d.N + 2 * d.S) * LD * int(sizeof(T)) + rest;
+  int two_phase = 0;
+  if (smem > 227 * 1024) {   // Q/dO and K/V take turns in one pair of tiles
+    two_phase = 1;
+    smem = 2 * L * LD * int(sizeof(T)) + rest;
+  }
   if (smem > 227 * 1024) { set_last_error("attn_bwd(simt): N=%d S=%d needs %d B smem", d.N, d.S, smem); return NGU_ERR_SHAPE; }
   cudaError_t e = cudaFuncSetAttribute(attn_bwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return cuda_status(e, "attn_bwd attr");
-  attn_bwd_simt_kernel<T><<<d.B * d.H, kWarps * 32, smem, st>>>(d);
+  attn_bwd_simt_kernel<T><<<d.B * d.H, kWarps * 32, smem, st>>>(d, two_phase);
   return check_launch("attn_bwd_simt");
 }
 

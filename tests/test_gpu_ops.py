@@ -281,3 +281,24 @@ def test_patchify_matches_unfold(dtype, R, P):
     assert out.shape == (B * G * G, (K + 7) // 8 * 8)
     assert relerr(out[:, :K], ref) < (1e-6 if dtype == torch.float32 else 4e-3)
     assert float(out[:, K:].float().abs().max()) == 0.0 if out.shape[1] > K else True
+
+
+@pytest.mark.parametrize("N", [485, 577])
+def test_attention_long_sequences_bf16(N):
+    """Sequence lengths of configs 4 / 5 (ViT-L/14@336: 577 tokens, ViT-B/16@352: 485): beyond the tcgen05 kernels' 256,
+    served by the CUDA-core kernels; the backward runs in its two-phase shared-memory mode."""
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(15)
+    B, H, dh = 2, 3, 64
+    D = H * dh
+    qkv = torch.randn(B * N, 3 * D).to(dev(), torch.bfloat16)
+    do = torch.randn(B * N, D).to(dev(), torch.bfloat16)
+    o, lse = ops.attn_fwd_packed(qkv, B, N, H, dh)
+    dqkv = ops.attn_bwd_packed(qkv, o, lse, do, B, N, H, dh)
+    t = qkv.double().cpu().requires_grad_(True)
+    q, k, v = t.view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, D)
+    (dref,) = torch.autograd.grad((ref * do.double().cpu()).sum(), t)
+    assert relerr(o, ref) < 1e-2
+    for sl in (slice(0, D), slice(D, 2 * D), slice(2 * D, 3 * D)):
+        assert relerr(dqkv[:, sl], dref[:, sl]) < 1.5e-2

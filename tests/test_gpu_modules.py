@@ -385,3 +385,45 @@ def test_openai_clip_patch14_vision_tower_vs_oracle(dtype):
         d = a.double().cpu() - b
         num += float((d * d).sum()); den += float((b * b).sum())
     assert (num / den) ** 0.5 < (5e-2 if dtype == torch.bfloat16 else 1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res,patch,width,heads", [(336, 14, 1024, 16), (352, 16, 768, 12)])
+def test_openai_clip_config4_config5_geometry_bf16(res, patch, width, heads):
+    """Config-4 / config-5 vision geometry at full width and resolution, two layers: ViT-L/14@336 -> 24 x 24 patches + CLS
+    = 577 tokens, width 1024, 16 heads; ViT-B/16@352 -> 22 x 22 + CLS = 485 tokens, width 768.  Mona (baseline) on the
+    24 x 24 / 22 x 22 grid.  Exercises the generic patchify path (K 588 -> 592), the D = 1024 LayerNorm kernels, the
+    long-sequence attention kernels and the large-grid Mona conv kernels together."""
+    from nextgen_uia_b200.openai_clip import CLIP
+    from src.adapters import inject_mona_variant_to_clip
+    import oracle.functional as OF
+    torch.manual_seed(22)
+    m = CLIP(64, res, 2, width, patch, 8, 50, 64, 1, 1)
+    for p in m.parameters():
+        p.requires_grad = False
+    inject_mona_variant_to_clip(m, variant="baseline", bottleneck_dim=64)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "mona" in n and ("project2" in n or "gamma" in n):
+                p.add_(torch.randn_like(p) * 0.05)
+    trainable = [n for n, p in m.named_parameters() if "mona" in n]
+    for n, p in m.named_parameters():
+        p.requires_grad = n in trainable
+    images = torch.rand(2, 3, res, res)
+    gi = torch.randn(2, 64)
+    p64 = {k: (v.detach().double().clone().requires_grad_(k in trainable) if v.is_floating_point() else v) for k, v in m.state_dict().items()}
+    ocfg = dict(patch=patch, depth=2, heads=heads, text_layers=1, text_heads=1)
+    fo = OF.clip_encode_image(p64, images.double(), ocfg)
+    go = torch.autograd.grad((fo * gi.double()).sum(), [p64[n] for n in trainable])
+    m = m.to(dev()).eval().set_compute_dtype(torch.bfloat16)
+    fi = m.encode_image(images.to(dev()))
+    (fi.float() * gi.to(dev())).sum().backward()
+    assert fi.shape == (2, 64) and relerr(fi, fo) < 3e-2
+    num = den = 0.0
+    params = dict(m.named_parameters())
+    for n, b in zip(trainable, go):
+        a = params[n].grad
+        assert a is not None and torch.isfinite(a).all(), n
+        d = a.double().cpu() - b
+        num += float((d * d).sum()); den += float((b * b).sum())
+    assert (num / den) ** 0.5 < 8e-2

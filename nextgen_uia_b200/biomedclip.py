@@ -132,8 +132,17 @@ class HFTextEncoder(nn.Module):
         (src/models/biomedclip/finetune.py:166-167 freezes it; no parameter requires grad)."""
         if any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError("ngu B200 path: the text tower is forward-only (frozen); tune_text_encoder is not on this path")
-        if bool((ids == self.pad_token_id).any()):
-            raise NotImplementedError("padded token batches need the key-padding mask path (not built yet)")
+        # Key-padding mask (open_clip HFTextEncoder.forward: attn_mask = (x != pad_token_id)): tokenizers pad on the right,
+        # so the mask is a per-sequence valid length; padded keys are masked in every layer, padded query rows compute
+        # values nobody reads (CLS pooling).  Any other mask shape is refused loudly.
+        kv_len = None
+        valid = ids != self.pad_token_id
+        if not bool(valid.all()):
+            lens = valid.sum(1)
+            prefix = torch.arange(ids.shape[1], device=ids.device)[None, :] < lens[:, None]
+            if not bool((prefix == valid).all()) or bool((lens < 1).any()):
+                raise NotImplementedError("ngu B200 path: only right-padded token batches (a suffix of pad ids) are supported")
+            kv_len = lens.to(torch.int32).contiguous()
         tr = self.transformer
         dt = self.compute_dtype
         B, S = ids.shape
@@ -147,7 +156,7 @@ class HFTextEncoder(nn.Module):
             H = sa.num_attention_heads
             Wqkv, bqkv = self._qkv_weights(sa, dt)
             qkv = ops.gemm(x, Wqkv, bias=bqkv)
-            ao, _ = ops.attn_fwd_packed(qkv, B, S, H, d // H)
+            ao, _ = ops.attn_fwd_packed(qkv, B, S, H, d // H, kv_len=kv_len)
             so = lyr.attention.output
             y = ops.gemm(ao, frozen_copies(so.dense.weight, dt)[0], bias=so.dense.bias.detach(), aux=x, aux_mode=L.AUX_RESIDUAL)
             x, _, _ = ops.ln_fwd(y, so.LayerNorm.weight.detach(), so.LayerNorm.bias.detach(), so.LayerNorm.eps, save_stats=False)

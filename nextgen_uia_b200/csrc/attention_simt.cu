@@ -32,11 +32,17 @@ attn_fwd_simt_kernel(ngu_attn_desc d) {
   constexpr int LD = Pad<T>::LD;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int b = blockIdx.x / d.H, hd = blockIdx.x % d.H;
-  const int N = d.N, S = d.S;
+  const int N = d.N;
+  int S = d.S;
+  const int Sfull = d.S;
+  if (d.kv_len) {   // key-padding mask: only the first kv_len[b] keys take part
+    const int l = d.kv_len[b];
+    S = l < 1 ? 1 : (l > Sfull ? Sfull : l);
+  }
   T* Ks = reinterpret_cast<T*>(smem_dyn);
-  T* Vs = Ks + S * LD;
-  float* pbuf = reinterpret_cast<float*>(Vs + S * LD);  // [kWarps][S]
-  float* qbuf = pbuf + kWarps * S;                      // [kWarps][DH]
+  T* Vs = Ks + Sfull * LD;
+  float* pbuf = reinterpret_cast<float*>(Vs + Sfull * LD);  // [kWarps][S]
+  float* qbuf = pbuf + kWarps * Sfull;                      // [kWarps][DH]
   const T* q = reinterpret_cast<const T*>(d.q) + int64_t(b) * d.q_bs + hd * DH;
   const T* k = reinterpret_cast<const T*>(d.k) + int64_t(b) * d.k_bs + hd * DH;
   const T* v = reinterpret_cast<const T*>(d.v) + int64_t(b) * d.v_bs + hd * DH;
@@ -45,7 +51,7 @@ attn_fwd_simt_kernel(ngu_attn_desc d) {
   load_tile<T>(Vs, v, S, d.v_ts);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* pw = pbuf + warp * S;
+  float* pw = pbuf + warp * Sfull;
   float* qw = qbuf + warp * DH;
   for (int i = warp; i < N; i += kWarps) {
     qw[lane] = to_f32<T>(q[int64_t(i) * d.q_ts + lane]);

@@ -56,6 +56,7 @@ struct AttnTcParams {
   bf16* dqkv;         // [B*N, 3*H*64]
   int B, H, N;
   float scale;
+  const int* kv_len;  // forward: per-batch number of valid keys (NULL = N)
 };
 
 NGU_DEVINL uint64_t desc_kmajor(uint32_t addr) { return make_smem_desc_sw128(addr, 16, 1024); }
@@ -104,6 +105,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
   const int b = bh / p.H, h = bh % p.H;
   const int npad = (N + 15) & ~15;               // MMA N extent over the kv axis
   const int row0 = b * N;
+  int Lk = p.kv_len ? __ldg(p.kv_len + b) : N;   // valid keys of this sequence (key-padding mask = suffix of the row)
+  Lk = Lk < 1 ? 1 : (Lk > N ? N : Lk);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmQKV);
@@ -179,13 +182,13 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
         uint32_t v[32];
         tmem_ld32(trow + ch * 32, v);
         tmem_ld_wait();
-        if (ch * 32 + 32 <= N) {
+        if (ch * 32 + 32 <= Lk) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (ch * 32 + i < N) mx = fmaxf(mx, __uint_as_float(v[i]));
+            if (ch * 32 + i < Lk) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
       }
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_red), "f"(mx) : "memory");
@@ -203,14 +206,14 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
           uint32_t v[32];
           tmem_ld32(trow + ch * 32, v);
           tmem_ld_wait();
-          const bool full = ch * 32 + 32 <= N;
+          const bool full = ch * 32 + 32 <= Lk;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, -mc));
             float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
             if (!full) {
-              p0 = (ch * 32 + 2 * i < N) ? p0 : 0.f;
-              p1 = (ch * 32 + 2 * i + 1 < N) ? p1 : 0.f;
+              p0 = (ch * 32 + 2 * i < Lk) ? p0 : 0.f;
+              p1 = (ch * 32 + 2 * i + 1 < Lk) ? p1 : 0.f;
             }
             sum += p0 + p1;
             pk[k][i] = pack_bf16x2(p0, p1);
@@ -1073,6 +1076,7 @@ int fill_params(const ngu_attn_desc& d, AttnTcParams& p, bool bwd) {
   p.dqkv = reinterpret_cast<bf16*>(d.dq);
   p.B = d.B; p.H = d.H; p.N = d.N;
   p.scale = d.scale;
+  p.kv_len = d.kv_len;
   return NGU_OK;
 }
 
@@ -1108,7 +1112,7 @@ int attn_fwd_tc(const ngu_attn_desc& d, cudaStream_t st) {
   // desc.impl = 2 selects the persistent two-group kernel (164 us: its two groups fall into lock-step on the MUFU pipe; kept as the
   // starting point for a single-group four-threads-per-row variant).
   static const int mode = [] { const char* e = getenv("NGU_ATTN_FWD"); return e ? atoi(e) : 0; }();
-  if (mode == 0 && d.impl != 2) {
+  if ((mode == 0 && d.impl != 2) || d.kv_len != nullptr) {   // key padding: only the per-tile kernel masks by kv_len
     attn_fwd_tc_kernel<<<d.B * d.H * ((d.N + TILE - 1) / TILE), kFwdThreads, kFwdSmem, st>>>(p);
     return check_launch("attn_fwd_tc");
   }

@@ -172,23 +172,26 @@ def mona_conv_bwd(h, dg, weights, grads, hw, has_cls, drop_p=0.0, seed=0):
     return dh
 
 
-def _attn_desc(q, k, v, o, B, H, N, S, dh, strides, scale, causal, impl):
+def _attn_desc(q, k, v, o, B, H, N, S, dh, strides, scale, causal, impl, kv_len=None):
     d = L.AttnDesc()
     (d.q_bs, d.q_ts), (d.k_bs, d.k_ts), (d.v_bs, d.v_ts), (d.o_bs, d.o_ts) = strides
     d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
     d.B, d.H, d.N, d.S, d.dh = B, H, N, S, dh
     d.scale, d.causal, d.dtype, d.impl = scale, int(causal), _dt(q), impl
+    if kv_len is not None:
+        assert kv_len.dtype == torch.int32 and kv_len.is_cuda and kv_len.numel() == B and kv_len.is_contiguous()
+        d.kv_len = kv_len.data_ptr()
     return d
 
 
-def attn_fwd_packed(qkv, B, N, H, dh, *, causal=False, impl=0):
+def attn_fwd_packed(qkv, B, N, H, dh, *, causal=False, impl=0, kv_len=None):
     """timm layout: qkv [B*N, 3*H*dh] (= [B,N,3,H,dh]); returns (o [B*N, H*dh], lse [B,H,N])."""
     _need_cuda(qkv)
     D = H * dh
     o = torch.empty(B * N, D, device=qkv.device, dtype=qkv.dtype)
     lse = torch.empty(B, H, N, device=qkv.device, dtype=torch.float32)
     st = ((N * 3 * D, 3 * D),) * 3 + ((N * D, D),)
-    d = _attn_desc(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B, H, N, N, dh, st, dh ** -0.5, causal, impl)
+    d = _attn_desc(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B, H, N, N, dh, st, dh ** -0.5, causal, impl, kv_len)
     d.lse = lse.data_ptr()
     L.check(L.lib().ngu_attn_fwd(_byref(d), _stream()), "ngu_attn_fwd")
     return o, lse

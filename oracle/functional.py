@@ -170,10 +170,11 @@ def clip_encode_text(p, text, cfg):
 # ---------------------------------------------------------------------------------------------------
 # BERT text tower (pinned deps transformers 4.57.1 BertModel + open_clip HFTextEncoder; restated)
 # ---------------------------------------------------------------------------------------------------
-def encode_text(p, ids, cfg):
-    """BertModel (post-LN, eps 1e-12, exact GELU, absolute positions, token_type 0, no padding in the
-    synthetic batch) -> CLS last-hidden-state pooler -> MLP proj (768->640->GELU->512, no bias).  Eval mode.
-    [pinned-dep knowledge]"""
+def encode_text(p, ids, cfg, pad_token_id=0):
+    """BertModel (post-LN, eps 1e-12, exact GELU, absolute positions, token_type 0; keys at pad positions are masked,
+    open_clip HFTextEncoder.forward `attn_mask = (x != pad_token_id)`) -> CLS last-hidden-state pooler -> MLP proj
+    (768->640->GELU->512, no bias).  Eval mode.  [pinned-dep knowledge; the encoder stack incl. the mask is checked against
+    transformers.BertModel in tests/test_cpu_oracle.py]"""
     t = "text.transformer."
     B, S = ids.shape
     heads = cfg["text_heads"]
@@ -187,7 +188,9 @@ def encode_text(p, ids, cfg):
         def heads_(name):
             return F.linear(x, p[f"{l}attention.self.{name}.weight"], p[f"{l}attention.self.{name}.bias"]).reshape(B, S, heads, dh).transpose(1, 2)
         q, k, v = heads_("query"), heads_("key"), heads_("value")
-        a = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), -1) @ v).transpose(1, 2).reshape(B, S, D)
+        sc = q @ k.transpose(-1, -2) / math.sqrt(dh)
+        sc = sc.masked_fill((ids == pad_token_id)[:, None, None, :], float("-inf"))
+        a = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B, S, D)
         a = F.linear(a, p[f"{l}attention.output.dense.weight"], p[f"{l}attention.output.dense.bias"])
         x = F.layer_norm(x + a, (D,), p[f"{l}attention.output.LayerNorm.weight"], p[f"{l}attention.output.LayerNorm.bias"], 1e-12)
         h = F.gelu(F.linear(x, p[f"{l}intermediate.dense.weight"], p[f"{l}intermediate.dense.bias"]))

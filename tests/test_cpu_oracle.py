@@ -88,3 +88,31 @@ def test_oracle_clip_matches_vendored_reference_golden(golden, tag):
     grads = torch.autograd.grad((fi * g["gi"].double()).sum(), [p[n] for n in g["trainable"]])
     for n, gr in zip(g["trainable"], grads):
         assert relerr(gr, g["grads"][n]) < 1e-4, n
+
+
+def test_oracle_bert_stack_with_padding_matches_transformers():
+    """The oracle's BERT restatement (encode_text: embeddings, post-LN encoder, exact GELU, key-padding mask, CLS pooling)
+    against transformers.BertModel with random weights on a right-padded batch -- pins the [pinned-dep knowledge] part
+    of the text tower, including the attention mask open_clip's HFTextEncoder builds from pad_token_id."""
+    transformers = pytest.importorskip("transformers")
+    import oracle.functional as OF
+    import torch.nn.functional as F
+    torch.manual_seed(31)
+    cfg = transformers.BertConfig(vocab_size=100, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                                  max_position_embeddings=32, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, pad_token_id=0)
+    bert = transformers.BertModel(cfg, add_pooling_layer=False).eval().double()
+    ids = torch.randint(5, 100, (4, 12))
+    ids[1, 7:] = 0
+    ids[2, 3:] = 0
+    ids[3, 11:] = 0
+    with torch.no_grad():
+        hid = bert(input_ids=ids, attention_mask=(ids != 0).long()).last_hidden_state
+    W0, W2 = torch.randn(40, 64, dtype=torch.float64) * 0.1, torch.randn(16, 40, dtype=torch.float64) * 0.1
+    ref = F.linear(F.gelu(F.linear(hid[:, 0], W0)), W2)
+    p = {"text.transformer." + k: v for k, v in bert.state_dict().items()}
+    p["text.proj.0.weight"], p["text.proj.2.weight"] = W0, W2
+    got = OF.encode_text(p, ids, dict(text_layers=2, text_heads=4))
+    assert float((got - ref).abs().max()) < 1e-10
+    # without the mask the padded rows differ (the check above is not vacuous)
+    nomask = OF.encode_text(p, ids, dict(text_layers=2, text_heads=4), pad_token_id=-1)
+    assert float((nomask[1] - ref[1]).abs().max()) > 1e-6

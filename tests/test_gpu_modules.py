@@ -427,3 +427,31 @@ def test_openai_clip_config4_config5_geometry_bf16(res, patch, width, heads):
         d = a.double().cpu() - b
         num += float((d * d).sum()); den += float((b * b).sum())
     assert (num / den) ** 0.5 < 8e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_text_tower_right_padded_batch_vs_oracle(dtype):
+    """BiomedCLIP text tower on a right-padded token batch (pad id 0): the key-padding mask travels to the attention
+    kernels as per-sequence valid lengths; features vs the oracle (whose masked BERT stack is pinned to
+    transformers.BertModel on CPU).  A mask that is not a suffix is refused."""
+    from oracle import functional as OF
+    model = _tiny_model("mona")
+    sd = {k: v.detach().double().clone() if v.is_floating_point() else v.clone() for k, v in model.state_dict().items()}
+    torch.manual_seed(33)
+    ids = torch.randint(5, 1000, (6, 77))
+    ids[:, 0] = 2
+    for b, l in enumerate((77, 40, 33, 12, 64, 5)):
+        ids[b, l - 1] = 3
+        ids[b, l:] = 0
+    cfg = dict(patch=16, depth=2, heads=12, text_layers=2, text_heads=12)
+    ref = OF.encode_text(sd, ids, cfg)
+    model = model.to(dev()).eval().set_compute_dtype(dtype)
+    ft = model.encode_text(ids.to(dev()))
+    assert relerr(ft, ref) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
+    unmasked = OF.encode_text(sd, ids, cfg, pad_token_id=-1)
+    assert relerr(ft[3:4], unmasked[3:4]) > 5 * relerr(ft[3:4], ref[3:4])     # the mask matters for the short rows
+    bad = ids.clone()
+    bad[1, 10] = 0                                                             # a hole, not a suffix
+    with pytest.raises(NotImplementedError):
+        model.encode_text(bad.to(dev()))

@@ -302,3 +302,32 @@ def test_attention_long_sequences_bf16(N):
     assert relerr(o, ref) < 1e-2
     for sl in (slice(0, D), slice(D, 2 * D), slice(2 * D, 3 * D)):
         assert relerr(dqkv[:, sl], dref[:, sl]) < 1.5e-2
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,N,H", [(5, 77, 12), (3, 197, 2), (4, 256, 1)])
+def test_attention_forward_key_padding_lengths(dtype, B, N, H):
+    """ngu_attn_fwd with kv_len: keys at positions >= kv_len[b] are masked (right-padded batches).  Valid query rows
+    match SDPA with the boolean key mask; the backward entry point refuses kv_len."""
+    from nextgen_uia_b200 import ops, _lib as L
+    torch.manual_seed(16)
+    dh = 64
+    D = H * dh
+    qkv = torch.randn(B * N, 3 * D).to(dev(), dtype)
+    lens = torch.randint(1, N + 1, (B,))
+    lens[0] = N
+    lens[-1] = 1
+    o, lse = ops.attn_fwd_packed(qkv, B, N, H, dh, kv_len=lens.to(dev(), torch.int32))
+    t = qkv.double().cpu()
+    q, k, v = t.view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
+    mask = (torch.arange(N)[None, :] < lens[:, None])[:, None, None, :]
+    ref = F.scaled_dot_product_attention(q, k, v, attn_mask=mask).transpose(1, 2).reshape(B, N, D)
+    got = o.view(B, N, D)
+    for b in range(B):
+        assert relerr(got[b, :lens[b]], ref[b, :lens[b]]) < TOL[dtype]
+    with pytest.raises(L.NguError):
+        d = ops._attn_desc(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B, H, N, N, dh, ((N * 3 * D, 3 * D),) * 3 + ((N * D, D),), dh ** -0.5,
+                           False, 0, lens.to(dev(), torch.int32))
+        d.lse, d.d_o = lse.data_ptr(), o.data_ptr()
+        d.dq = d.dk = d.dv = qkv.data_ptr()
+        L.check(L.lib().ngu_attn_bwd(ops._byref(d), ops._stream()), "ngu_attn_bwd")

@@ -179,7 +179,7 @@ typedef struct ngu_attn_desc {
   int dtype;
   int impl;                   /* 0 = default for dtype (bf16: tcgen05, fp32: CUDA cores); 1 = force CUDA cores;
                                  2 = tcgen05 with the persistent two-group forward kernel (forward only; tuning) */
-  const int* kv_len;          /* forward only, NULL = every key valid: [B] device ints, keys j >= kv_len[b] are masked
+  const int* kv_len;          /* NULL = every key valid: [B] device ints, keys j >= kv_len[b] are masked
                                  (right-padded token batches: the HF attention_mask of BiomedCLIP's text tower,
                                  open_clip HFTextEncoder.forward `attn_mask = (x != pad_token_id)`); 1 <= kv_len[b] <= S */
 } ngu_attn_desc;

@@ -55,7 +55,6 @@ int ngu_attn_fwd(const ngu_attn_desc* d, void* stream) {
 int ngu_attn_bwd(const ngu_attn_desc* d, void* stream) {
   NGU_NONNULL(d, "ngu_attn_bwd");
   if (int rc = attn_validate(*d, "ngu_attn_bwd", true)) return rc;
-  if (d->kv_len != nullptr) { set_last_error("attn_bwd: kv_len (key padding) is forward-only"); return NGU_ERR_ARG; }
   if (d->impl == 0 && attn_tc_supported(*d, true)) return attn_bwd_tc(*d, NGU_STREAM);
   return attn_bwd_simt(*d, NGU_STREAM);
 }

@@ -101,6 +101,9 @@ attn_bwd_simt_kernel(ngu_attn_desc d, int two_phase) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int b = blockIdx.x / d.H, hd = blockIdx.x % d.H;
   const int N = d.N, S = d.S;
+  // key-padding mask: keys >= kv_len[b] get probability 0 (pass A stops there, pass B writes zero dk / dv rows)
+  int Sk = S;
+  if (d.kv_len) { const int l = d.kv_len[b]; Sk = l < 1 ? 1 : (l > S ? S : l); }
   const int Lr = N > S ? N : S;
   T* Qs = reinterpret_cast<T*>(smem_dyn);
   T* dOs = Qs + (two_phase ? Lr : N) * LD;
@@ -148,7 +151,7 @@ attn_bwd_simt_kernel(ngu_attn_desc d, int two_phase) {
     }
     __syncwarp();
     const float li = lse_s[i], di = delta[i];
-    for (int j = lane; j < S; j += 32) {
+    for (int j = lane; j < Sk; j += 32) {
       float s = 0.f, dp = 0.f;
 #pragma unroll 16
       for (int c = 0; c < DH; ++c) {
@@ -161,7 +164,7 @@ attn_bwd_simt_kernel(ngu_attn_desc d, int two_phase) {
     }
     __syncwarp();
     float a0 = 0.f, a1 = 0.f;
-    for (int j = 0; j < S; ++j) {
+    for (int j = 0; j < Sk; ++j) {
       const float ds = b0[j];
       a0 = fmaf(ds, to_f32<T>(Ks[j * LD + lane]), a0);
       a1 = fmaf(ds, to_f32<T>(Ks[j * LD + lane + 32]), a1);
@@ -178,6 +181,11 @@ attn_bwd_simt_kernel(ngu_attn_desc d, int two_phase) {
     __syncthreads();
   }
   for (int j = warp; j < S; j += kWarps) {
+    if (j >= Sk) {   // masked key: no query attends to it
+      dv[int64_t(j) * d.v_ts + lane] = from_f32<T>(0.f); dv[int64_t(j) * d.v_ts + lane + 32] = from_f32<T>(0.f);
+      dk[int64_t(j) * d.k_ts + lane] = from_f32<T>(0.f); dk[int64_t(j) * d.k_ts + lane + 32] = from_f32<T>(0.f);
+      continue;
+    }
     if (two_phase) {
       rw[lane] = to_f32<T>(k[int64_t(j) * d.k_ts + lane]); rw[lane + 32] = to_f32<T>(k[int64_t(j) * d.k_ts + lane + 32]);
       rw[DH + lane] = to_f32<T>(v[int64_t(j) * d.v_ts + lane]); rw[DH + lane + 32] = to_f32<T>(v[int64_t(j) * d.v_ts + lane + 32]);

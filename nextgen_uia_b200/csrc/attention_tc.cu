@@ -964,13 +964,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       const int b = item / p.H, h = item - b * p.H;
       const int row0 = b * N;
       const uint32_t tab = sStat + (n & 1) * 2048;
+      int Lk = p.kv_len ? __ldg(p.kv_len + b) : N;       // key-padding mask: kv rows >= Lk get P = dS = 0 (dK = dV = 0 there)
+      Lk = Lk < 1 ? 1 : (Lk > N ? N : Lk);
       mbar_wait(bar_stat(n & 1), (n >> 1) & 1);
       for (int r = 0; r < nraw; ++r) {
         const BwdStep s = bwd_step(r, n & 1, ntiles, N);
         if (s.nq == 0) continue;
         const int kvb = s.j * TILE + qd * 32;              // first kv row of this warp
         const bool warp_live = kvb < N;                    // any valid kv row in this warp (warp-uniform)
-        const bool partial = kvb + 32 > N;                 // some rows of the warp are past the end
+        const bool partial = kvb + 32 > Lk;                // some rows of the warp are past the (valid) end
         const uint32_t cb = trow + (sc & 1u) * 128u;
         if (warp == 0) TRACE(30, sc);
         mbar_wait(bar_s(sc & 1u), (sc >> 1) & 1u);
@@ -990,7 +992,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dl[4 * e]), "=f"(dl[4 * e + 1]), "=f"(dl[4 * e + 2]), "=f"(dl[4 * e + 3]) : "r"(qa + 1024u + 16u * e));
           }
           tmem_ld_wait();
-          const bool row_ok = !partial || (kvb + lane < N);
+          const bool row_ok = !partial || (kvb + lane < Lk);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             // query columns past the end have lse = +inf -> p = 0 exactly; kv rows past the end are zeroed below

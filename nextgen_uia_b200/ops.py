@@ -197,14 +197,14 @@ def attn_fwd_packed(qkv, B, N, H, dh, *, causal=False, impl=0, kv_len=None):
     return o, lse
 
 
-def attn_bwd_packed(qkv, o, lse, do, B, N, H, dh, *, causal=False, impl=0):
+def attn_bwd_packed(qkv, o, lse, do, B, N, H, dh, *, causal=False, impl=0, kv_len=None):
     """Returns dqkv [B*N, 3*H*dh]."""
     _need_cuda(qkv, o, do)
     D = H * dh
     assert do.is_contiguous() and o.is_contiguous()
     dqkv = torch.empty_like(qkv)
     st = ((N * 3 * D, 3 * D),) * 3 + ((N * D, D),)
-    d = _attn_desc(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B, H, N, N, dh, st, dh ** -0.5, causal, impl)
+    d = _attn_desc(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B, H, N, N, dh, st, dh ** -0.5, causal, impl, kv_len)
     d.lse, d.d_o = lse.data_ptr(), do.data_ptr()
     d.dq, d.dk, d.dv = dqkv.data_ptr(), dqkv[:, D:].data_ptr(), dqkv[:, 2 * D:].data_ptr()
     L.check(L.lib().ngu_attn_bwd(_byref(d), _stream()), "ngu_attn_bwd")

@@ -17,6 +17,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import ops
 from .linear import frozen_copies
+from .linear import Proj, proj_fwd
 from .vit import VisionTransformer, HeadFunction
 
 
@@ -104,6 +105,46 @@ class BertModel(nn.Module):
         self.encoder = _BertEncoder(layers, d, heads, dm, eps)
 
 
+class _PackedAttnFunction(torch.autograd.Function):
+    """softmax(q k^T / sqrt(dh)) v on a packed [B*S, 3*D] projection with the key-padding lengths of the batch."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, S, H, kv_len):
+        qkv = qkv.contiguous()
+        dh = qkv.shape[1] // (3 * H)
+        o, lse = ops.attn_fwd_packed(qkv, B, S, H, dh, kv_len=kv_len)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.meta = (B, S, H, dh, kv_len)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        B, S, H, dh, kv_len = ctx.meta
+        return ops.attn_bwd_packed(qkv, o, lse, do.contiguous(), B, S, H, dh, kv_len=kv_len), None, None, None, None
+
+
+class _TextProjFunction(torch.autograd.Function):
+    """proj[2](gelu(proj[0](cls))) with frozen, bias-free weights (open_clip `mlp` text projection)."""
+
+    @staticmethod
+    def forward(ctx, cls, fc, out):
+        c2 = cls.contiguous()
+        p1, p2 = Proj(fc, c2.dtype), Proj(out, c2.dtype)
+        (a, der), _ = proj_fwd(c2, p1, act=L.ACT_GELU, save_pre=True)
+        y, _ = proj_fwd(a, p2)
+        ctx.save_for_backward(der)
+        ctx.p = (p1, p2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (der,) = ctx.saved_tensors
+        p1, p2 = ctx.p
+        dpre = ops.gemm(dy.contiguous(), p2.WT, aux=der, aux_mode=L.AUX_DACT)
+        return ops.gemm(dpre, p1.WT), None, None
+
+
 class HFTextEncoder(nn.Module):
     """open_clip HFTextEncoder with `cls_last_hidden_state_pooler` and `mlp` projection (BiomedCLIP config)."""
 
@@ -126,12 +167,10 @@ class HFTextEncoder(nn.Module):
             sa._ngu_qkv = c
         return c[1], c[2]
 
-    @torch.no_grad()
     def forward(self, ids):
-        """ids int64 [B,S] -> [B, embed_dim].  Frozen tower: forward only, no autograd graph
-        (src/models/biomedclip/finetune.py:166-167 freezes it; no parameter requires grad)."""
-        if any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("ngu B200 path: the text tower is forward-only (frozen); tune_text_encoder is not on this path")
+        """ids int64 [B,S] -> [B, embed_dim].  Frozen tower (src/models/biomedclip/finetune.py:166-167, the default): one
+        fused forward-only pipeline without an autograd graph.  With LoRA on the BERT projections
+        (inject_lora_to_biomedclip(tune_text_encoder=True), reference lora.py:317-367) the layers run as autograd nodes."""
         # Key-padding mask (open_clip HFTextEncoder.forward: attn_mask = (x != pad_token_id)): tokenizers pad on the right,
         # so the mask is a per-sequence valid length; padded keys are masked in every layer, padded query rows compute
         # values nobody reads (CLS pooling).  Any other mask shape is refused loudly.
@@ -143,14 +182,53 @@ class HFTextEncoder(nn.Module):
             if not bool((prefix == valid).all()) or bool((lens < 1).any()):
                 raise NotImplementedError("ngu B200 path: only right-padded token batches (a suffix of pad ids) are supported")
             kv_len = lens.to(torch.int32).contiguous()
+        has_lora = any(getattr(m, "r", 0) and hasattr(m, "w_lora_A") for m in self.modules())
+        if has_lora or any(p.requires_grad for p in self.parameters()):
+            return self._forward_trainable(ids, kv_len)
+        with torch.no_grad():
+            return self._forward_frozen(ids, kv_len)
+
+    def _embed(self, ids, dt):
+        emb = self.transformer.embeddings
+        for p in emb.parameters():
+            if p.requires_grad:
+                raise NotImplementedError("ngu B200 path: BERT embeddings must stay frozen")
+        with torch.no_grad():
+            x = ops.embed_tokens(ids.contiguous(), emb.word_embeddings.weight.detach(), emb.position_embeddings.weight.detach(),
+                                 emb.token_type_embeddings.weight.detach()[0].contiguous(), dt)
+            x, _, _ = ops.ln_fwd(x, emb.LayerNorm.weight.detach(), emb.LayerNorm.bias.detach(), emb.LayerNorm.eps, save_stats=False)
+        return x
+
+    def _forward_trainable(self, ids, kv_len):
+        """Post-LN BERT layers as autograd nodes over the same kernels: LinearLoRA / frozen projections, packed attention
+        with the key-padding lengths, LayerNorm, GELU MLP with the residual in the GEMM epilogue."""
+        from .adapters.lora import _apply_linear
+        from .openai_clip import _LnFunction, _MlpResidualFunction
+        for n, p in self.named_parameters():
+            if p.requires_grad and "lora" not in n:
+                raise NotImplementedError(f"ngu B200 path: only LoRA factors of the text tower may be trainable (got {n})")
         tr = self.transformer
         dt = self.compute_dtype
         B, S = ids.shape
-        emb = tr.embeddings
-        d = emb.word_embeddings.weight.shape[1]
-        x = ops.embed_tokens(ids.contiguous(), emb.word_embeddings.weight.detach(), emb.position_embeddings.weight.detach(),
-                             emb.token_type_embeddings.weight.detach()[0].contiguous(), dt)
-        x, _, _ = ops.ln_fwd(x, emb.LayerNorm.weight.detach(), emb.LayerNorm.bias.detach(), emb.LayerNorm.eps, save_stats=False)
+        x = self._embed(ids, dt).view(B, S, -1)
+        d = x.shape[-1]
+        for lyr in tr.encoder.layer:
+            sa, so = lyr.attention.self, lyr.attention.output
+            H = sa.num_attention_heads
+            qkv = torch.cat([_apply_linear(sa.query, x), _apply_linear(sa.key, x), _apply_linear(sa.value, x)], -1)
+            ao = _PackedAttnFunction.apply(qkv.view(B * S, 3 * d), B, S, H, kv_len)
+            s1 = x + _apply_linear(so.dense, ao.view(B, S, d))
+            x1 = _LnFunction.apply(s1, so.LayerNorm)
+            s2 = _MlpResidualFunction.apply(x1, x1, lyr.intermediate.dense, lyr.output.dense, L.ACT_GELU)
+            x = _LnFunction.apply(s2, lyr.output.LayerNorm)
+        return _TextProjFunction.apply(x[:, 0, :], self.proj[0], self.proj[2])
+
+    def _forward_frozen(self, ids, kv_len):
+        tr = self.transformer
+        dt = self.compute_dtype
+        B, S = ids.shape
+        x = self._embed(ids, dt)
+        d = x.shape[-1]
         for lyr in tr.encoder.layer:
             sa = lyr.attention.self
             H = sa.num_attention_heads

@@ -185,13 +185,14 @@ def encode_text(p, ids, cfg, pad_token_id=0):
     x = F.layer_norm(x, (D,), p[f"{t}embeddings.LayerNorm.weight"], p[f"{t}embeddings.LayerNorm.bias"], 1e-12)
     for i in range(cfg["text_layers"]):
         l = f"{t}encoder.layer.{i}."
+        tr_, ta_ = cfg.get("text_lora") or (0, 1)      # LoRA on the BERT projections (lora.py:317-367, tune_text_encoder)
         def heads_(name):
-            return F.linear(x, p[f"{l}attention.self.{name}.weight"], p[f"{l}attention.self.{name}.bias"]).reshape(B, S, heads, dh).transpose(1, 2)
+            return lora_linear(x, p, f"{l}attention.self.{name}.", tr_, ta_).reshape(B, S, heads, dh).transpose(1, 2)
         q, k, v = heads_("query"), heads_("key"), heads_("value")
         sc = q @ k.transpose(-1, -2) / math.sqrt(dh)
         sc = sc.masked_fill((ids == pad_token_id)[:, None, None, :], float("-inf"))
         a = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B, S, D)
-        a = F.linear(a, p[f"{l}attention.output.dense.weight"], p[f"{l}attention.output.dense.bias"])
+        a = lora_linear(a, p, f"{l}attention.output.dense.", tr_, ta_)
         x = F.layer_norm(x + a, (D,), p[f"{l}attention.output.LayerNorm.weight"], p[f"{l}attention.output.LayerNorm.bias"], 1e-12)
         h = F.gelu(F.linear(x, p[f"{l}intermediate.dense.weight"], p[f"{l}intermediate.dense.bias"]))
         h = F.linear(h, p[f"{l}output.dense.weight"], p[f"{l}output.dense.bias"])

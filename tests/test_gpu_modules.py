@@ -455,3 +455,51 @@ def test_text_tower_right_padded_batch_vs_oracle(dtype):
     bad[1, 10] = 0                                                             # a hole, not a suffix
     with pytest.raises(NotImplementedError):
         model.encode_text(bad.to(dev()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_text_tower_lora_tune_text_encoder_vs_oracle(dtype):
+    """inject_lora_to_biomedclip(tune_text_encoder=True) (reference lora.py:317-367): LoRA on the BERT q/k/v/o projections,
+    right-padded batch.  Text features and every LoRA gradient of the text tower vs the oracle."""
+    from oracle import functional as OF
+    from nextgen_uia_b200.biomedclip import BiomedCLIP, init_synthetic_
+    from src.adapters import inject_lora_to_biomedclip
+    torch.manual_seed(41)
+    model = BiomedCLIP(vision=dict(depth=1), text=dict(layers=2, vocab=1000, max_pos=128))
+    init_synthetic_(model, seed=41, std=0.02)
+    for p in model.parameters():
+        p.requires_grad = False
+    inject_lora_to_biomedclip(model, lora_r=8, lora_alpha=32, lora_dropout=0.0, tune_text_encoder=True)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("w_lora_B"):
+                p.copy_(torch.randn(p.shape) * 0.02)
+    trainable = [n for n, p in model.named_parameters() if "lora" in n and n.startswith("text.")]
+    assert len(trainable) == 2 * 4 * 2
+    for n, p in model.named_parameters():
+        p.requires_grad = n in trainable
+    ids = torch.randint(5, 1000, (5, 40))
+    ids[:, 0] = 2
+    for b, l in enumerate((40, 17, 33, 9, 25)):
+        ids[b, l - 1] = 3
+        ids[b, l:] = 0
+    gt = torch.randn(5, 512)
+    p64 = {k: (v.detach().double().clone().requires_grad_(k in trainable) if v.is_floating_point() else v) for k, v in model.state_dict().items()}
+    cfg = dict(patch=16, depth=1, heads=12, text_layers=2, text_heads=12, text_lora=(8, 32))
+    fo = OF.encode_text(p64, ids, cfg)
+    go = torch.autograd.grad((fo * gt.double()).sum(), [p64[n] for n in trainable])
+    model = model.to(dev()).eval().set_compute_dtype(dtype)
+    ft = model.encode_text(ids.to(dev()))
+    (ft.float() * gt.to(dev())).sum().backward()
+    assert relerr(ft, fo) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
+    num = den = 0.0
+    params = dict(model.named_parameters())
+    for n, b in zip(trainable, go):
+        a = params[n].grad
+        assert a is not None, n
+        d = a.double().cpu() - b
+        num += float((d * d).sum()); den += float((b * b).sum())
+        if dtype == torch.float32:
+            assert relerr(a, b) < 2e-3, n
+    assert (num / den) ** 0.5 < (5e-2 if dtype == torch.bfloat16 else 1e-3)

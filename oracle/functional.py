@@ -65,7 +65,8 @@ def lora_linear(x, p, prefix, r, alpha):
 # timm ViT block / tower  (pinned dep timm 1.0.20 `vit_base_patch16_224`; restated)
 # ---------------------------------------------------------------------------------------------------
 def vit_block(x, p, prefix, heads, lora=None, eps=1e-6):
-    """Pre-LN block: x += proj(SDPA(qkv(LN1 x))); x += fc2(gelu(fc1(LN2 x))).  [pinned-dep knowledge]"""
+    """Pre-LN block: x += proj(SDPA(qkv(LN1 x))); x += fc2(gelu(fc1(LN2 x))).  [pinned-dep knowledge; the trunk is checked
+    against transformers.ViTModel in tests/test_cpu_oracle.py]"""
     B, N, D = x.shape
     dh = D // heads
     r, alpha = lora if lora else (0, 1)

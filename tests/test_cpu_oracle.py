@@ -116,3 +116,44 @@ def test_oracle_bert_stack_with_padding_matches_transformers():
     # without the mask the padded rows differ (the check above is not vacuous)
     nomask = OF.encode_text(p, ids, dict(text_layers=2, text_heads=4), pad_token_id=-1)
     assert float((nomask[1] - ref[1]).abs().max()) > 1e-6
+
+
+def test_oracle_vit_trunk_matches_transformers_vit():
+    """The oracle's ViT trunk (encode_image without adapters: conv patch embedding, CLS token + learned positions, pre-LN
+    blocks with fused qkv, exact GELU, final LayerNorm, CLS pooling, bias-free head) against transformers.ViTModel -- an
+    independent implementation of the architecture timm's `vit_base_patch16_224` implements (timm itself is not
+    installed here).  Random weights mapped name by name, fp64."""
+    transformers = pytest.importorskip("transformers")
+    import oracle.functional as OF
+    import torch.nn.functional as F
+    torch.manual_seed(32)
+    D, depth, heads, res, P = 64, 2, 4, 32, 16
+    cfg = transformers.ViTConfig(hidden_size=D, num_hidden_layers=depth, num_attention_heads=heads, intermediate_size=4 * D,
+                                 image_size=res, patch_size=P, layer_norm_eps=1e-6, hidden_act="gelu", qkv_bias=True,
+                                 hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    vit = transformers.ViTModel(cfg, add_pooling_layer=False).eval().double()
+    with torch.no_grad():
+        for p_ in vit.parameters():
+            p_.copy_(torch.randn_like(p_) * 0.1)
+    hf = vit.state_dict()
+    t = "visual.trunk."
+    p = {f"{t}patch_embed.proj.weight": hf["embeddings.patch_embeddings.projection.weight"],
+         f"{t}patch_embed.proj.bias": hf["embeddings.patch_embeddings.projection.bias"],
+         f"{t}cls_token": hf["embeddings.cls_token"], f"{t}pos_embed": hf["embeddings.position_embeddings"],
+         f"{t}norm.weight": hf["layernorm.weight"], f"{t}norm.bias": hf["layernorm.bias"]}
+    for i in range(depth):
+        h, o = f"encoder.layer.{i}.", f"{t}blocks.{i}."
+        for w in ("weight", "bias"):
+            p[f"{o}norm1.{w}"] = hf[f"{h}layernorm_before.{w}"]
+            p[f"{o}norm2.{w}"] = hf[f"{h}layernorm_after.{w}"]
+            p[f"{o}attn.qkv.{w}"] = torch.cat([hf[f"{h}attention.attention.{n}.{w}"] for n in ("query", "key", "value")], 0)
+            p[f"{o}attn.proj.{w}"] = hf[f"{h}attention.output.dense.{w}"]
+            p[f"{o}mlp.fc1.{w}"] = hf[f"{h}intermediate.dense.{w}"]
+            p[f"{o}mlp.fc2.{w}"] = hf[f"{h}output.dense.{w}"]
+    W = torch.randn(16, D, dtype=torch.float64) * 0.1
+    p["visual.head.proj.weight"] = W
+    images = torch.rand(3, 3, res, res, dtype=torch.float64)
+    with torch.no_grad():
+        ref = F.linear(vit(pixel_values=images).last_hidden_state[:, 0], W)
+    got = OF.encode_image(p, images, dict(patch=P, depth=depth, heads=heads))
+    assert float((got - ref).abs().max()) < 1e-10

@@ -343,3 +343,43 @@ def test_attention_forward_key_padding_lengths(dtype, B, N, H):
             assert float((a_ - r_).abs().max()) / max(float(r_.abs().max()), 1.0) < GTOL[dtype]
         if lens[b] < N:
             assert float(got_g[b, lens[b]:, D:].float().abs().max()) == 0.0      # dk, dv of masked keys
+
+
+def test_entry_points_are_cuda_graph_capturable():
+    """The C-ABI promises stream-ordered, sync-free, allocation-free launches: a GEMM + LayerNorm + attention (fwd, bwd) +
+    Mona conv sequence is captured into a CUDA graph (after one eager warm-up that sets the kernels' attributes) and
+    replayed on fresh inputs; results equal the eager ones bit for bit."""
+    from nextgen_uia_b200 import ops
+    torch.manual_seed(17)
+    B, N, H, dh = 4, 197, 12, 64
+    D = H * dh
+    bf = torch.bfloat16
+    x = torch.randn(B * N, D, device=dev()).to(bf)
+    Wq = (torch.randn(3 * D, D, device=dev()) * 0.03).to(bf)
+    bq = torch.randn(3 * D, device=dev())
+    w, b = torch.randn(D, device=dev()), torch.randn(D, device=dev())
+    do = torch.randn(B * N, D, device=dev()).to(bf)
+
+    def run():
+        xn, _, _ = ops.ln_fwd(x, w, b, 1e-6)
+        qkv = ops.gemm(xn, Wq, bias=bq)
+        o, lse = ops.attn_fwd_packed(qkv, B, N, H, dh)
+        g = ops.attn_bwd_packed(qkv, o, lse, do, B, N, H, dh)
+        return o, g
+
+    o0, g0 = run()                      # warm-up: function attributes, tensor-map encoder lookup
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        run()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        o1, g1 = run()
+    x.copy_(torch.randn(B * N, D, device=dev()).to(bf))          # new input in the captured buffer
+    graph.replay()
+    torch.cuda.synchronize()
+    o2, g2 = run()
+    assert torch.equal(o1, o2) and torch.equal(g1, g2)
+    assert not torch.equal(o1, o0)

@@ -72,27 +72,29 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
-        int s = 0; uint32_t ph = 0;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t st = base + s * kStageBytes;
-          const uint32_t sy = st + 2 * kMaxG * kBoxBytes;
+      // whole warp walks the loop (uniform registers, no per-lane waterfall around tcgen05.mma); one elected lane issues
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      const uint64_t a0 = make_smem_desc_sw128(base, kBoxBytes, 1024);
+      const uint64_t b0 = make_smem_desc_sw128(base + 2 * kMaxG * kBoxBytes, 0, 1024);
+      int s = 0; uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint64_t so = uint64_t((s * kStageBytes) >> 4);
+        if (elect_one()) {
           for (int m = 0; m < G; ++m) {
 #pragma unroll
-            for (int k = 0; k < KB / 16; ++k) {
-              const uint64_t ad = make_smem_desc_sw128(st + (2 * m) * kBoxBytes + k * 2048, kBoxBytes, 1024);
-              const uint64_t bd = make_smem_desc_sw128(sy + k * 2048, 0, 1024);
-              umma_ss(tmem + m * 64, ad, bd, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < KB / 16; ++k)
+              umma_ss(tmem + m * 64, a0 + so + uint64_t(((2 * m) * kBoxBytes + k * 2048) >> 4), b0 + so + uint64_t((k * 2048) >> 4), idesc,
+                      (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));
-          if (++s == kStages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(done_bar);
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
+      if (elect_one()) umma_commit(done_bar);
+      __syncwarp();
     } else {
       const int q = warp & 3;
       mbar_wait(done_bar, 0);
@@ -105,14 +107,24 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         tmem_ld32(ta, lo);
         tmem_ld32(ta + 32, hi);
         tmem_ld_wait();
-        const int row = col0 + m * 128 + q * 32 + lane;
-        if (row < p.Mo) {
-          float* dst = p.D + size_t(row) * p.ldd;
+        // Transpose the warp's 32 x 64 fp32 block through smem (the pipeline stages are idle now) so that one red
+        // instruction covers two whole 256-byte rows (4 LSU wavefronts) instead of a 16-byte piece of 32 rows (32).
+        const uint32_t scr = base + uint32_t(warp - 2) * (32 * 272);          // row pitch 272 B: conflict-free both ways
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(__uint_as_float(v[4 * j])),
-                         "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
-                         : "memory");
+        for (int j = 0; j < 16; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(scr + lane * 272 + j * 16), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                       "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+        __syncwarp();
+        const int rbase = col0 + m * 128 + q * 32;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int r = 2 * k + (lane >> 4), pc = lane & 15;
+          float4 f;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(scr + r * 272 + pc * 16));
+          if (rbase + r < p.Mo)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.D + size_t(rbase + r) * p.ldd + 4 * pc), "f"(f.x), "f"(f.y),
+                         "f"(f.z), "f"(f.w) : "memory");
         }
       }
     }

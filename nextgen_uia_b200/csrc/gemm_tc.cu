@@ -164,7 +164,10 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform values live in uniform registers, where the TMA instructions take their
+    // operands); one elected lane issues.  This warp shares its scheduler with four epilogue warps: every instruction
+    // it does not execute is a k-block that arrives earlier.
+    {
       int s = 0;
       uint32_t ph = 0;
       constexpr int kBRows = BLOCK_N / kCluster;            // rows of the B tile this CTA fetches (and multicasts)
@@ -178,26 +181,30 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
           const int kc = (main_k ? kb : kb - kb1) * BLOCK_K;
           const CUtensorMap* ta = main_k ? &p.tmA : &p.tmA2;
           const CUtensorMap* tb = main_k ? (kCluster > 1 ? &p.tmBh : &p.tmB) : (kCluster > 1 ? &p.tmB2h : &p.tmB2);
-          if (kPair) {
-            // both CTAs' loads complete on the LEADER's full barrier (it feeds the single issuing MMA thread)
-            const uint32_t lead_full = mapa_cluster(full_bar(s), 0);
-            if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);
-            tma_load_2d_2cta(sA0 + s * Cfg::kABytes, ta, lead_full, kc, m0, kEvictNormal);
-            tma_load_2d_2cta(sB0 + s * Cfg::kBBytes, tb, lead_full, kc, n0 + rank * kBRows, kEvictLast);
-          } else {
-            mbar_arrive_expect_tx(full_bar(s), Cfg::kStageBytes);
-            tma_load_2d(sA0 + s * Cfg::kABytes, ta, full_bar(s), kc, m0, kEvictNormal);
-            // A streams from HBM: warm L2 for the block kPrefetch steps ahead (next tile's rows once this tile's K is done)
-            if (main_k && p.prefetch > 0) {
-              int pk = kb + p.prefetch, pt = t;
-              if (pk >= kb1) { pk -= kb1; pt += tile_stride; }
-              if (pt < num_tiles && pk < kb1) tma_prefetch_l2_2d(&p.tmA, pk * BLOCK_K, tile_m0(pt));
+          const uint32_t da = sA0 + s * Cfg::kABytes, db = sB0 + s * Cfg::kBBytes, fb = full_bar(s);
+          if (elect_one()) {
+            if (kPair) {
+              // both CTAs' loads complete on the LEADER's full barrier (it feeds the single issuing MMA thread)
+              const uint32_t lead_full = mapa_cluster(fb, 0);
+              if (rank == 0) mbar_arrive_expect_tx(fb, 2 * Cfg::kStageBytes);
+              tma_load_2d_2cta(da, ta, lead_full, kc, m0, kEvictNormal);
+              tma_load_2d_2cta(db, tb, lead_full, kc, n0 + rank * kBRows, kEvictLast);
+            } else {
+              mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+              tma_load_2d(da, ta, fb, kc, m0, kEvictNormal);
+              // A streams from HBM: warm L2 for the block kPrefetch steps ahead (next tile's rows once this tile's K is done)
+              if (main_k && p.prefetch > 0) {
+                int pk = kb + p.prefetch, pt = t;
+                if (pk >= kb1) { pk -= kb1; pt += tile_stride; }
+                if (pt < num_tiles && pk < kb1) tma_prefetch_l2_2d(&p.tmA, pk * BLOCK_K, tile_m0(pt));
+              }
+              if (kCluster > 1)
+                tma_load_2d_mcast(db + rank * kBRows * BLOCK_K * 2, tb, fb, kc, n0 + rank * kBRows, kMask, kEvictLast);
+              else
+                tma_load_2d(db, tb, fb, kc, n0, kEvictLast);
             }
-            if (kCluster > 1)
-              tma_load_2d_mcast(sB0 + s * Cfg::kBBytes + rank * kBRows * BLOCK_K * 2, tb, full_bar(s), kc, n0 + rank * kBRows, kMask, kEvictLast);
-            else
-              tma_load_2d(sB0 + s * Cfg::kBBytes, tb, full_bar(s), kc, n0, kEvictLast);
           }
+          __syncwarp();
           if (++s == Cfg::kStages) { s = 0; ph ^= 1u; }
         }
       }

@@ -60,16 +60,18 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
 
   if (nkb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        int s = 0; uint32_t ph = 0;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
+      // whole warp walks, one elected lane issues (uniform registers for the TMA operands)
+      int s = 0; uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t st = base + s * kStageBytes;
+        if (elect_one()) {
           mbar_arrive_expect_tx(full_bar(s), (2 * G + 1) * kBoxBytes);
-          const uint32_t st = base + s * kStageBytes;
           for (int c = 0; c < 2 * G; ++c) tma_load_2d(st + c * kBoxBytes, &p.tmX, full_bar(s), col0 + c * 64, kb * KB, kEvictFirst);
           tma_load_2d(st + 2 * kMaxG * kBoxBytes, &p.tmY, full_bar(s), 0, kb * KB, kEvictFirst);
-          if (++s == kStages) { s = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     } else if (warp == 1) {
       // whole warp walks the loop (uniform registers, no per-lane waterfall around tcgen05.mma); one elected lane issues

@@ -142,13 +142,13 @@ mona_pre_bwd_kernel(const T* __restrict__ du, const T* __restrict__ dy, const T*
   constexpr int R = D / 64;  // warps per CTA = rows per tile
   static_assert(D % (32 * V) == 0 && D % 64 == 0, "unsupported width");
   extern __shared__ __align__(16) uint8_t smem_dyn[];
-  float* sp = reinterpret_cast<float*>(smem_dyn);            // [4][D]: w, b, gamma, gammax
-  float* srow = sp + 4 * D;                                  // [R][2]: mean, rstd
+  float* sp = reinterpret_cast<float*>(smem_dyn);            // [5][D]: w, b, gamma, gammax, gamma*w
+  float* srow = sp + 5 * D;                                  // [R][2]: mean, rstd
   T* sdu = reinterpret_cast<T*>(srow + 2 * R);               // [R][D]
   T* sx = sdu + R * D;
   T* sdy = sx + R * D;
   for (int c = threadIdx.x; c < D; c += D / 2) {
-    sp[c] = w[c]; sp[D + c] = b[c]; sp[2 * D + c] = gamma[c]; sp[3 * D + c] = gammax[c];
+    sp[c] = w[c]; sp[D + c] = b[c]; sp[2 * D + c] = gamma[c]; sp[3 * D + c] = gammax[c]; sp[4 * D + c] = gamma[c] * w[c];
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,7 +178,9 @@ mona_pre_bwd_kernel(const T* __restrict__ du, const T* __restrict__ dy, const T*
         *reinterpret_cast<uint4*>(sx + warp * D + c) = raw[1][it];
         *reinterpret_cast<uint4*>(sdy + warp * D + c) = raw[2][it];
       }
-      float s1 = 0.f, s2 = 0.f;
+      // With g = du * (gamma w):  s1 = mean(g),  s2 = mean(g * xhat) = rs * (mean(g x) - mu * s1);
+      // dx = dy + du * (gammax + rs * gamma w) - rs * s1 - rs^2 * s2 * (x - mu)      (4 FMA-class ops per element)
+      float s1 = 0.f, tx = 0.f;
 #pragma unroll 1
       for (int it = 0; it < kIt; ++it) {
         const int c = (it * 32 + lane) * V;
@@ -186,14 +188,22 @@ mona_pre_bwd_kernel(const T* __restrict__ du, const T* __restrict__ dy, const T*
         Vec<T>::load(sdu + warp * D + c, duv);
         Vec<T>::load(sx + warp * D + c, xv);
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float g = duv[i] * sp[2 * D + c + i] * sp[c + i];
-          s1 += g;
-          s2 = fmaf(g, (xv[i] - mu) * rs, s2);
+        for (int i4 = 0; i4 < V; i4 += 4) {
+          const float4 gw = lds128_volatile(&sp[4 * D + c + i4]);
+          const float gw4[4] = {gw.x, gw.y, gw.z, gw.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float g = duv[i4 + i] * gw4[i];
+            s1 += g;
+            tx = fmaf(g, xv[i4 + i], tx);
+          }
         }
       }
       s1 = warp_sum(s1) * (1.0f / D);
-      s2 = warp_sum(s2) * (1.0f / D);
+      tx = warp_sum(tx) * (1.0f / D);
+      const float s2 = rs * (tx - mu * s1);
+      const float cx = rs * rs * s2;                 // coefficient of x
+      const float c0 = fmaf(cx, mu, -rs * s1);       // row constant
 #pragma unroll 1
       for (int it = 0; it < kIt; ++it) {
         const int c = (it * 32 + lane) * V;
@@ -202,10 +212,14 @@ mona_pre_bwd_kernel(const T* __restrict__ du, const T* __restrict__ dy, const T*
         Vec<T>::load(sdu + warp * D + c, duv);
         Vec<T>::load(sx + warp * D + c, xv);
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float xhat = (xv[i] - mu) * rs;
-          const float g = duv[i] * sp[2 * D + c + i] * sp[c + i];
-          o[i] = dyv[i] + duv[i] * sp[3 * D + c + i] + rs * (g - s1 - xhat * s2);
+        for (int i4 = 0; i4 < V; i4 += 4) {
+          const float4 gw = lds128_volatile(&sp[4 * D + c + i4]), gx = lds128_volatile(&sp[3 * D + c + i4]);
+          const float gw4[4] = {gw.x, gw.y, gw.z, gw.w}, gx4[4] = {gx.x, gx.y, gx.z, gx.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float k1 = fmaf(rs, gw4[i], gx4[i]);
+            o[i4 + i] = fmaf(-cx, xv[i4 + i], fmaf(duv[i4 + i], k1, dyv[i4 + i])) + c0;
+          }
         }
         Vec<T>::store(dx + size_t(row) * D + c, o);
       }
@@ -214,21 +228,23 @@ mona_pre_bwd_kernel(const T* __restrict__ du, const T* __restrict__ dy, const T*
     // ---------------- phase B
     const int nr = min(R, M - tile * R);
     typedef typename Pair<T>::type P;
+    // per column: U = sum du * xhat, Sd = sum du, sum du * x, sum dy; the parameter gradients are linear in them
     for (int r = 0; r < nr; ++r) {
       const float mu = srow[2 * r], rs = srow[2 * r + 1];
       const float2 d2 = Pair<T>::get(reinterpret_cast<const P*>(sdu + r * D)[threadIdx.x]);
       const float2 x2 = Pair<T>::get(reinterpret_cast<const P*>(sx + r * D)[threadIdx.x]);
       const float2 y2 = Pair<T>::get(reinterpret_cast<const P*>(sdy + r * D)[threadIdx.x]);
-      const float xh0 = (x2.x - mu) * rs, xh1 = (x2.y - mu) * rs;
-      ag0 = fmaf(d2.x, fmaf(xh0, pw0, pb0), ag0); ag1 = fmaf(d2.y, fmaf(xh1, pw1, pb1), ag1);
-      agx0 = fmaf(d2.x, x2.x, agx0); agx1 = fmaf(d2.y, x2.y, agx1);
-      const float dn0 = d2.x * pg0, dn1 = d2.y * pg1;
-      aw0 = fmaf(dn0, xh0, aw0); aw1 = fmaf(dn1, xh1, aw1);
-      ab0 += dn0; ab1 += dn1;
+      const float t0 = d2.x * x2.x, t1 = d2.y * x2.y;
+      agx0 += t0; agx1 += t1;
+      aw0 = fmaf(rs, fmaf(-mu, d2.x, t0), aw0); aw1 = fmaf(rs, fmaf(-mu, d2.y, t1), aw1);    // U
+      ab0 += d2.x; ab1 += d2.y;                                                              // Sd
       ady0 += y2.x; ady1 += y2.y;
     }
     __syncthreads();
   }
+  // u = (xhat w + b) gamma + x gammax:  d w = gamma U,  d b = gamma Sd,  d gamma = w U + b Sd
+  ag0 = fmaf(pw0, aw0, pb0 * ab0); ag1 = fmaf(pw1, aw1, pb1 * ab1);
+  aw0 *= pg0; aw1 *= pg1; ab0 *= pg0; ab1 *= pg1;
   if (dw) { atomicAdd(dw + c2, aw0); atomicAdd(dw + c2 + 1, aw1); }
   if (db) { atomicAdd(db + c2, ab0); atomicAdd(db + c2 + 1, ab1); }
   if (dgamma) { atomicAdd(dgamma + c2, ag0); atomicAdd(dgamma + c2 + 1, ag1); }
@@ -404,7 +420,7 @@ int ln_bwd_t(const ngu_ln_bwd_desc& d, cudaStream_t s) {
 template <typename T, int D>
 int mona_pre_bwd_t(const ngu_mona_pre_bwd_desc& d, cudaStream_t s) {
   constexpr int R = D / 64;
-  const int smem = (4 * D + 2 * R) * int(sizeof(float)) + 3 * R * D * int(sizeof(T));
+  const int smem = (5 * D + 2 * R) * int(sizeof(float)) + 3 * R * D * int(sizeof(T));
   cudaError_t e = cudaFuncSetAttribute(mona_pre_bwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return cuda_status(e, "mona_pre_bwd attr");
   const int ntiles = (d.M + R - 1) / R;

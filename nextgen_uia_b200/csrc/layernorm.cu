@@ -346,14 +346,16 @@ ln_bwd_fast_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ x
     for (int i = 0; i < V; ++i) pw[it][i] = w[(it * 32 + lane) * V + i];
   for (int row = blockIdx.x * kFastWarps + warp; row < M; row += gridDim.x * kFastWarps) {
     const float mu = mean[row], rs = rstd[row];
-    float gh[IT][V], xh[IT][V], o[IT][V];
-    float s1 = 0.f, s2 = 0.f;
+    // With gh = g * w:  s1 = mean(gh),  s2 = mean(gh * xhat) = rs * (mean(gh x) - mu s1);
+    // dx = dres + rs gh - rs s1 - rs^2 s2 (x - mu)                       (three FMA-class ops per element in the second pass)
+    float gh[IT][V], xr[IT][V], o[IT][V];
+    float s1 = 0.f, tx = 0.f;
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
       const int c = (it * 32 + lane) * V;
-      float gv[V], xv[V];
+      float gv[V];
       Vec<T>::load(g + int64_t(row) * ldg + c, gv);
-      Vec<T>::load(x + int64_t(row) * ldx + c, xv);
+      Vec<T>::load(x + int64_t(row) * ldx + c, xr[it]);
       if (dres != nullptr) Vec<T>::load(dres + int64_t(row) * ldr + c, o[it]);
       else {
 #pragma unroll
@@ -362,17 +364,19 @@ ln_bwd_fast_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ x
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         gh[it][i] = gv[i] * pw[it][i];
-        xh[it][i] = (xv[i] - mu) * rs;
         s1 += gh[it][i];
-        s2 = fmaf(gh[it][i], xh[it][i], s2);
+        tx = fmaf(gh[it][i], xr[it][i], tx);
       }
     }
     s1 = warp_sum(s1) * (1.0f / D);
-    s2 = warp_sum(s2) * (1.0f / D);
+    tx = warp_sum(tx) * (1.0f / D);
+    const float s2 = rs * (tx - mu * s1);
+    const float cx = rs * rs * s2;
+    const float c0 = fmaf(cx, mu, -rs * s1);
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) o[it][i] += rs * (gh[it][i] - s1 - xh[it][i] * s2);
+      for (int i = 0; i < V; ++i) o[it][i] = fmaf(-cx, xr[it][i], fmaf(gh[it][i], rs, o[it][i])) + c0;
       Vec<T>::store(dx + int64_t(row) * lddx + (it * 32 + lane) * V, o[it]);
     }
   }

@@ -259,7 +259,7 @@ mona_pre_bwd_kernel(const T* __restrict__ du, const T* __restrict__ dy, const T*
 constexpr int kFastWarps = 8;
 
 template <typename T, int D, bool MIX>
-__global__ void __launch_bounds__(kFastWarps * 32)
+__global__ void __launch_bounds__(kFastWarps * 32, 2)   // <= 128 registers: two CTAs per SM also for the MIX variant (155 registers unconstrained)
 ln_fwd_fast_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
                    const float* __restrict__ gamma, const float* __restrict__ gammax, T* __restrict__ y, int64_t ldy,
                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, float eps) {

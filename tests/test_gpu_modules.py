@@ -503,3 +503,102 @@ def test_text_tower_lora_tune_text_encoder_vs_oracle(dtype):
         if dtype == torch.float32:
             assert relerr(a, b) < 2e-3, n
     assert (num / den) ** 0.5 < (5e-2 if dtype == torch.bfloat16 else 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Parity at the BENCHMARKED depth (BASELINE.json configs[0] / configs[1] shapes): goldens from oracle/make_golden_cfg.py
+# ---------------------------------------------------------------------------------------------------------------------
+def _report(name, payload):
+    """Per-layer error growth etc. for DESIGN.md / profiles/: written next to the test run when the directory exists."""
+    import json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, f"parity_{name}.json"), "w") as f:
+            json.dump(payload, f, indent=1)
+    except OSError:
+        pass
+    print(name, payload)
+
+
+def _cfg_model_and_taps(dtype):
+    from oracle.make_golden_cfg import build, weight_checksum, TAP_IMGS, TAP_TOKS
+    model = build(12)
+    ck = weight_checksum(model.state_dict())
+    model = model.to(dev()).eval().set_compute_dtype(dtype)
+    taps = []
+    hooks = [blk.register_forward_hook(lambda _m, _i, out: taps.append(out.detach()[:TAP_IMGS][:, list(TAP_TOKS), :].float().cpu()))
+             for blk in model.visual.trunk.blocks]
+    return model, ck, taps, hooks
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_config1_depth12_batch8_parity(golden, dtype):
+    """BASELINE.json configs[0] exactly: batch 8, 12 vision layers + Mona, 12 BERT layers, InfoNCE, backward.
+    fp32 check mode: features / loss 1e-4, every stored adapter gradient 1e-3 (fp32 accumulation over 12 layers).
+    bf16: features / loss 1e-2; tower backward with a well-conditioned cotangent, relative L2 over the adapter."""
+    import bench
+    from src.losses import InfoNCELoss
+    g = golden("cfg1_b8_d12")
+    model, ck, taps, hooks = _cfg_model_and_taps(dtype)
+    assert torch.allclose(ck, g["checksum"], rtol=1e-12, atol=0), "synthetic weights drifted from the golden's"
+    images, ids = bench.synthetic_batch(8, 1)
+    fi = model.encode_image(images.to(dev()))
+    ft = model.encode_text(ids.to(dev()))
+    loss = InfoNCELoss(0.07)(fi, ft)
+    for h in hooks:
+        h.remove()
+    layer_err = [relerr(t, g["taps"][i]) for i, t in enumerate(taps)]
+    e_i, e_t = relerr(fi, g["fi"]), relerr(ft, g["ft"])
+    e_l = abs(float(loss.detach()) - g["loss"]) / abs(g["loss"])
+    if dtype == torch.float32:
+        loss.backward()
+        ref, refn = g["grads"], g["grad_norms"]
+    else:
+        (fi * g["G"].to(dev(), dtype)).sum().backward()
+        ref, refn = g["gradsG"], g["gradG_norms"]
+    params = dict(model.named_parameters())
+    num = den = 0.0
+    worst = ("", 0.0)
+    for n, b in ref.items():
+        a = params[n].grad
+        assert a is not None and torch.isfinite(a).all(), n
+        d = a.double().cpu() - b.double()
+        num += float((d * d).sum()); den += float((b.double() ** 2).sum())
+        e = relerr(a, b)
+        if e > worst[1]:
+            worst = (n, e)
+    norm_err = max(abs(float(params[n].grad.norm()) - v) / max(v, 1e-30) for n, v in refn.items() if v > 1e-12)
+    l2 = (num / den) ** 0.5
+    _report(f"cfg1_b8_d12_{'fp32' if dtype == torch.float32 else 'bf16'}",
+            {"image_feat_relerr": e_i, "text_feat_relerr": e_t, "loss_relerr": e_l, "per_layer_residual_relerr": layer_err,
+             "adapter_grad_rel_l2_layers_0_5_11": l2, "worst_tensor": list(worst), "max_grad_norm_relerr_all_layers": norm_err})
+    assert e_i < TOL[dtype] and e_t < TOL[dtype] and e_l < TOL[dtype], (e_i, e_t, e_l, layer_err)
+    if dtype == torch.float32:
+        assert worst[1] < 1e-3 and norm_err < 1e-3, (worst, norm_err)
+    else:
+        assert l2 < 2e-2 and norm_err < 2e-2, (l2, norm_err, worst)
+
+
+def test_config2_depth12_batch256_bf16_parity(golden):
+    """BASELINE.json configs[1] shape (the benchmarked one): batch 256, 12+12 layers, bf16, eval mode.
+    Image / text features and the InfoNCE loss vs the committed CPU-oracle golden; per-layer error growth reported."""
+    import bench
+    from src.losses import InfoNCELoss
+    g = golden("cfg2_b256_d12")
+    model, ck, taps, hooks = _cfg_model_and_taps(torch.bfloat16)
+    assert torch.allclose(ck, g["checksum"], rtol=1e-12, atol=0)
+    images, ids = bench.synthetic_batch(256, 1)
+    with torch.no_grad():
+        fi = model.encode_image(images.to(dev()))
+        ft = model.encode_text(ids.to(dev()))
+        loss = InfoNCELoss(0.07)(fi, ft)
+    for h in hooks:
+        h.remove()
+    layer_err = [relerr(t, g["taps"][i]) for i, t in enumerate(taps)]
+    e_i, e_t = relerr(fi, g["fi"]), relerr(ft, g["ft"])
+    e_l = abs(float(loss) - g["loss"]) / abs(g["loss"])
+    _report("cfg2_b256_d12_bf16", {"image_feat_relerr": e_i, "text_feat_relerr": e_t, "loss_relerr": e_l,
+                                   "per_layer_residual_relerr": layer_err})
+    assert e_i < 1e-2 and e_t < 1e-2 and e_l < 1e-2, (e_i, e_t, e_l, layer_err)

@@ -48,6 +48,9 @@ extern "C" {
 #define NGU_AUX_NONE 0
 #define NGU_AUX_RESIDUAL 1 /* C = act(acc + bias) + aux            (x + attn(..), x + mlp(..)) */
 #define NGU_AUX_DACT 2     /* C = (acc + bias) * aux,  aux = act'(pre) saved by the forward (backward through fc1's activation) */
+#define NGU_AUX_MONA_DX 3  /* C = acc + aux + rowab[r].beta * aux2 + rowab[r].alpha: backward of the Mona input mix + residual
+                              (src/adapters/mona.py:124-125,150) with A = [dh | dh*rstd], B = [W1*gammax ; W1*w*gamma]^T, aux = dy,
+                              aux2 = x and the LayerNorm-backward row terms folded into two per-row scalars (ngu_mona_bwd_stage) */
 
 int ngu_version(void);
 const char* ngu_last_error(void);
@@ -79,6 +82,8 @@ typedef struct ngu_gemm_desc {
   float alpha;
   int dtype;                 /* NGU_BF16 (tcgen05 path) or NGU_F32 (check mode) */
   int block_n;               /* 0 = auto; 64/128/256 force the N tile (tuning/tests) */
+  const void* aux2; int ldaux2; /* [M,N] second elementwise operand (NGU_AUX_MONA_DX) or NULL */
+  const float* rowab;        /* [M,2] fp32 per-row (alpha, beta) of NGU_AUX_MONA_DX or NULL */
 } ngu_gemm_desc;
 int ngu_gemm(const ngu_gemm_desc* d, void* stream);
 
@@ -159,6 +164,69 @@ int ngu_mona_conv_fwd(const ngu_mona_conv_desc* d, void* stream);
 int ngu_mona_conv_bwd(const ngu_mona_conv_desc* d, void* stream);
 
 /*
+ * Fused Mona adapter, bf16 product path — src/adapters/mona.py:115-151 (BaselineMona.forward) with :85-93
+ * (BaselineMonaOp) / :261-296 (FreqEnhancedMonaOp) inside, batch-first [B,N,D] (BatchFirstMonaWrapper :54-67).
+ * The LayerNorm mix is folded INTO the 768->64 projection so x is consumed straight from HBM by TMA:
+ *     h = rstd_r * (x Wa^T) + (x Wb^T) - mean_r rstd_r ca + cb,   Wa = W1 * (ln_w*gamma),  Wb = W1 * gammax,
+ *     ca = Wa 1,  cb = b1 + W1 (ln_b*gamma)
+ * (row statistics are accumulated from the same shared-memory tiles the tensor core reads), and its backward is
+ *     dx = dy + [dh | dh*rstd] [Wb ; Wa] + beta_r x + alpha_r        (one GEMM, NGU_AUX_MONA_DX epilogue)
+ * with every parameter gradient of the input mix derived from G = x^T [dh | dh*rstd] (one token reduction).
+ *
+ *   ngu_mona_prep        : derived operands of n adapters from their fp32 parameters (after each optimiser update)
+ *   ngu_mona_fwd_stage   : x -> h, hA (= LN part of h, saved for backward), g = dropout(gelu(stage(h))), mean, rstd
+ *                          (project2 + residual is an ngu_gemm with NGU_AUX_RESIDUAL on g)
+ *   ngu_mona_bwd_stage   : (h, hA, dg, mean, rstd) -> dhcat = [dh | dh*rstd], rowab = (alpha_r, beta_r); accumulates the
+ *                          stage reductions into `ws` and dP / dbp directly
+ *   ngu_mona_finish      : ws (+ G written there by ngu_wgrad with No = 128) -> every remaining parameter gradient (+=)
+ * Grids up to 16x16, bottleneck 64, D % 64 == 0, baseline and freq_enhanced variants; other cases use the unfused entry
+ * points above.
+ */
+typedef struct ngu_mona_params {          /* fp32 parameters of one adapter, the reference's own tensors */
+  const float* w1; const float* b1;       /* project1 [64, D], [64]  (mona.py:106) */
+  const float* w2; const float* b2;       /* project2 [D, 64], [D]   (mona.py:108) */
+  const float* ln_w; const float* ln_b;   /* norm [D]                (mona.py:111) */
+  const float* gamma; const float* gammax;/* [D]                     (mona.py:112-113) */
+  ngu_mona_conv_weights conv;             /* adapter_conv.*          (mona.py:78-83) */
+} ngu_mona_params;
+typedef struct ngu_mona_derived {         /* written by ngu_mona_prep; caller-allocated */
+  void* wab;      /* bf16 [128, D]: rows 0..63 Wa, rows 64..127 Wb */
+  void* wcat_t;   /* bf16 [D, 128]: [k][c] = Wb[c][k], [k][64+c] = Wa[c][k] */
+  void* w2;       /* bf16 [D, 64] */
+  void* w2_t;     /* bf16 [64, D] */
+  float* ca; float* cb;   /* [64] */
+  float* kc;      /* [49*64] merged 7x7 stencil, tap-major: f_c (k3 + k5 + k7)/3 + delta */
+  float* bc;      /* [64] merged stencil bias */
+  void* pb;       /* bf16 [64*64] projector weight as the 128-byte-swizzled shared-memory image */
+  float* bp;      /* [64] */
+} ngu_mona_derived;
+typedef struct ngu_mona_prep_item { ngu_mona_params p; ngu_mona_derived d; } ngu_mona_prep_item;
+/* `items` is a DEVICE array of n entries (all with the same D) */
+int ngu_mona_prep(const ngu_mona_prep_item* items, int n, int D, void* stream);
+
+typedef struct ngu_mona_stage_desc {
+  ngu_mona_derived d;
+  const void* x;                      /* fwd: [B, N, D] bf16 */
+  void* h; void* hA; void* g;         /* [B, N, 64] bf16: fwd outputs; bwd reads h, hA */
+  float* mean; float* rstd;           /* [B*N] fp32: fwd outputs, bwd inputs */
+  const void* dg;                     /* bwd: [B, N, 64] bf16 */
+  void* dhcat;                        /* bwd: [B*N, 128] bf16 */
+  float* rowab;                       /* bwd: [B*N, 2] fp32 */
+  float* ws;                          /* bwd: fp32 workspace of ngu_mona_ws_floats(D) elements, zeroed by the call */
+  float* dP; float* dbp;              /* bwd: projector gradients, accumulated (+=) */
+  int B, N, H, W, D, has_cls;
+  float eps; float drop_p; uint64_t seed;
+} ngu_mona_stage_desc;
+int64_t ngu_mona_ws_floats(int D);
+int ngu_mona_fwd_stage(const ngu_mona_stage_desc* d, void* stream);
+int ngu_mona_bwd_stage(const ngu_mona_stage_desc* d, void* stream);
+typedef struct ngu_mona_grads {           /* fp32, parameter shapes, accumulated (+=) */
+  float* dw1; float* db1; float* dln_w; float* dln_b; float* dgamma; float* dgammax;
+  float* dk3; float* db3; float* dk5; float* db5; float* dk7; float* db7; float* dfreq;
+} ngu_mona_grads;
+int ngu_mona_finish(const ngu_mona_params* p, const ngu_mona_grads* g, const float* ws, int D, void* stream);
+
+/*
  * Attention core softmax(q k^T * scale) v, forward and backward (recompute from saved LSE).
  * Replaces F.scaled_dot_product_attention in timm Attention (pinned dep) and
  * src/adapters/lora.py:188-190, and nn.MultiheadAttention's core in
@@ -232,8 +300,26 @@ typedef struct ngu_adamw_desc {
   const float* gsq;        /* device scalar: squared global grad norm (after the all-reduce), or NULL */
   const float* loss;       /* device scalar: if non-finite the update is skipped, or NULL */
   int zero_grad;           /* zero the gradient buffer after use */
+  /* device-resident schedule (CUDA-graph replays cannot take a new lr / step from the host): when state != NULL the
+   * update count t = state[0] drives the bias correction (step = t + 1) and, with t_max > 0, the cosine schedule
+   * lr(t) = lr_min + (lr - lr_min)(1 + cos(pi t / t_max))/2 (torch CosineAnnealingLR, finetune.py:255); the update is
+   * skipped while state[1] != 0 (a micro-step of this accumulation window had a non-finite loss) or *gsq is non-finite. */
+  const int64_t* state;
+  float lr_min; int t_max;
 } ngu_adamw_desc;
 int ngu_adamw_step(const ngu_adamw_desc* d, void* stream);
+/* Guard / counters of the training loop on device (finetune.py:281-288): state = int64[4] {updates applied, poison flag,
+ * updates skipped, micro-steps run}.  mode 0: after a micro-step's loss (poison |= !isfinite(loss)); mode 1: after the
+ * optimiser launch of an update step (applied or skipped count, clear poison, micro-steps + 1); mode 2: end of a micro-step
+ * that does not update (micro-steps + 1). */
+int ngu_guard_tick(int64_t* state, const float* loss, const float* gsq, int mode, void* stream);
+/* Optional device counter mixed into every dropout seed of this process (Mona / LoRA dropout, mona.py:147, lora.py:82):
+ * a captured CUDA graph bakes the seeds in, the counter (e.g. &state[3] above) makes every replay draw fresh masks.
+ * NULL disables. */
+int ngu_set_seed_counter(const void* counter);
+/* Key-padding lengths of a right-padded token batch (open_clip HFTextEncoder.forward: attn_mask = (x != pad_token_id)):
+ * kv_len_out[b] = number of non-pad ids of row b; *flag |= 1 if some row's valid ids are not a non-empty prefix. */
+int ngu_kv_len(const int64_t* ids, int64_t pad_id, int* kv_len_out, int* flag, int B, int S, void* stream);
 
 /* Patch-embed im2col (stride == kernel, timm PatchEmbed / CLIP conv1): images fp32 NCHW [B,3,R,R]
  * -> [B*(R/P)^2, Kp] with row pitch Kp = 3*P*P rounded up to a multiple of 8 (P = 14: 588 -> 592; the caller zero-fills

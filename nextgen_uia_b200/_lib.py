@@ -7,11 +7,12 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libngu_b200.so")
+# NGU_LIB selects another in-tree build of the same sources (tools/: the -DNGU_CONV_PROF phase-timing build)
+LIB_PATH = os.environ.get("NGU_LIB") or os.path.join(_HERE, "libngu_b200.so")
 
 NGU_BF16, NGU_F32 = 0, 1
 ACT_NONE, ACT_GELU, ACT_QUICKGELU = 0, 1, 2
-AUX_NONE, AUX_RESIDUAL, AUX_DACT = 0, 1, 2
+AUX_NONE, AUX_RESIDUAL, AUX_DACT, AUX_MONA_DX = 0, 1, 2, 3
 
 _c_void_p, _c_int, _c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 
@@ -36,6 +37,8 @@ class GemmDesc(ctypes.Structure):
         ("alpha", _c_float),
         ("dtype", _c_int),
         ("block_n", _c_int),
+        ("aux2", _c_void_p), ("ldaux2", _c_int),
+        ("rowab", _c_void_p),
     ]
 
 
@@ -80,6 +83,31 @@ class MonaConvDesc(ctypes.Structure):
                 ("drop_p", _c_float), ("seed", _u64), ("dtype", _c_int), ("force_simt", _c_int)]
 
 
+class MonaParams(ctypes.Structure):   # ngu_mona_params
+    _fields_ = [(n, _c_void_p) for n in ("w1", "b1", "w2", "b2", "ln_w", "ln_b", "gamma", "gammax")] + [("conv", MonaConvWeights)]
+
+
+class MonaDerived(ctypes.Structure):  # ngu_mona_derived
+    _fields_ = [(n, _c_void_p) for n in ("wab", "wcat_t", "w2", "w2_t", "ca", "cb", "kc", "bc", "pb", "bp")]
+
+
+class MonaPrepItem(ctypes.Structure):
+    _fields_ = [("p", MonaParams), ("d", MonaDerived)]
+
+
+class MonaStageDesc(ctypes.Structure):
+    _fields_ = [("d", MonaDerived), ("x", _c_void_p), ("h", _c_void_p), ("hA", _c_void_p), ("g", _c_void_p),
+                ("mean", _c_void_p), ("rstd", _c_void_p), ("dg", _c_void_p), ("dhcat", _c_void_p), ("rowab", _c_void_p),
+                ("ws", _c_void_p), ("dP", _c_void_p), ("dbp", _c_void_p),
+                ("B", _c_int), ("N", _c_int), ("H", _c_int), ("W", _c_int), ("D", _c_int), ("has_cls", _c_int),
+                ("eps", _c_float), ("drop_p", _c_float), ("seed", _u64)]
+
+
+class MonaGrads(ctypes.Structure):    # ngu_mona_grads
+    _fields_ = [(n, _c_void_p) for n in ("dw1", "db1", "dln_w", "dln_b", "dgamma", "dgammax",
+                                         "dk3", "db3", "dk5", "db5", "dk7", "db7", "dfreq")]
+
+
 class AttnDesc(ctypes.Structure):
     _fields_ = [("q", _c_void_p), ("q_bs", _i64), ("q_ts", _i64),
                 ("k", _c_void_p), ("k_bs", _i64), ("k_ts", _i64),
@@ -100,7 +128,8 @@ class InfoNceDesc(ctypes.Structure):
 class AdamWDesc(ctypes.Structure):
     _fields_ = [("param", _c_void_p), ("grad", _c_void_p), ("m", _c_void_p), ("v", _c_void_p), ("n", _i64),
                 ("lr", _c_float), ("beta1", _c_float), ("beta2", _c_float), ("eps", _c_float), ("weight_decay", _c_float),
-                ("step", _c_int), ("max_norm", _c_float), ("gsq", _c_void_p), ("loss", _c_void_p), ("zero_grad", _c_int)]
+                ("step", _c_int), ("max_norm", _c_float), ("gsq", _c_void_p), ("loss", _c_void_p), ("zero_grad", _c_int),
+                ("state", _c_void_p), ("lr_min", _c_float), ("t_max", _c_int)]
 
 
 # every symbol include/ngu_b200.h declares: name -> (restype, argtypes)
@@ -119,6 +148,11 @@ PROTOTYPES = {
     "ngu_mona_pre_bwd": (_c_int, [_P(MonaPreBwdDesc), _c_void_p]),
     "ngu_mona_conv_fwd": (_c_int, [_P(MonaConvDesc), _c_void_p]),
     "ngu_mona_conv_bwd": (_c_int, [_P(MonaConvDesc), _c_void_p]),
+    "ngu_mona_ws_floats": (_i64, [_c_int]),
+    "ngu_mona_prep": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p]),
+    "ngu_mona_fwd_stage": (_c_int, [_P(MonaStageDesc), _c_void_p]),
+    "ngu_mona_bwd_stage": (_c_int, [_P(MonaStageDesc), _c_void_p]),
+    "ngu_mona_finish": (_c_int, [_P(MonaParams), _P(MonaGrads), _c_void_p, _c_int, _c_void_p]),
     "ngu_attn_fwd": (_c_int, [_P(AttnDesc), _c_void_p]),
     "ngu_attn_bwd": (_c_int, [_P(AttnDesc), _c_void_p]),
     "ngu_infonce_normalize": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
@@ -129,6 +163,9 @@ PROTOTYPES = {
     "ngu_dropout": (_c_int, [_c_void_p, _c_void_p, _i64, _c_float, _u64, _c_int, _c_int, _c_void_p]),
     "ngu_sqnorm": (_c_int, [_c_void_p, _i64, _c_void_p, _c_void_p]),
     "ngu_adamw_step": (_c_int, [_P(AdamWDesc), _c_void_p]),
+    "ngu_guard_tick": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
+    "ngu_set_seed_counter": (_c_int, [_c_void_p]),
+    "ngu_kv_len": (_c_int, [_c_void_p, _i64, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "ngu_patchify": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "ngu_assemble_tokens": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "ngu_embed_tokens": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),

@@ -131,6 +131,73 @@ class MonaFunction(torch.autograd.Function):
                 dfreq, dn[0], dn[1], dn[2], dn[3], None, None, None, None, None)
 
 
+def _fused_ok(x, owner, C, hw, N, freq, ne_w1):
+    """The fused bf16 path (csrc/mona_fused.cu): baseline / freq_enhanced stage, bottleneck 64, grids up to 16x16."""
+    import os
+    return (owner is not None and x.dtype == torch.bfloat16 and C == 64 and ne_w1 is None and hw[0] <= 16 and hw[1] <= 16
+            and N <= 256 and x.shape[-1] % 128 == 0 and os.environ.get("NGU_MONA_FUSED", "1") != "0")
+
+
+class MonaFusedFunction(torch.autograd.Function):
+    """Same function as MonaFunction on the fused kernels: the LayerNorm mix is folded into project1 (x is consumed raw by
+    TMA, u never exists), the stage runs out of shared memory in the same kernel, and backward is
+    dy -> dg (GEMM) -> stage backward -> dx = dy + [dh | dh rstd][Wb; Wa] + beta_r x + alpha_r (GEMM epilogue), with every
+    parameter gradient of the input mix derived from one token reduction G = x^T [dh | dh rstd]."""
+
+    @staticmethod
+    def forward(ctx, x, norm_w, norm_b, gamma, gammax, w1, b1, k3, b3, k5, b5, k7, b7, pw, pb, w2, b2, freq,
+                hw, has_cls, drop_p, seed, owner):
+        B, N, D = x.shape
+        x = x.contiguous()
+        x2 = x.view(B * N, D)
+        der = ops.mona_derived(owner)
+        h, hA, g, mean, rstd = ops.mona_fwd_stage(x, der, hw, has_cls, drop_p, seed, _LN_EPS)
+        y = ops.gemm(g.view(B * N, 64), der.view("w2", torch.bfloat16, (D, 64)), bias=b2.detach(), aux=x2, aux_mode=L.AUX_RESIDUAL)
+        ctx.save_for_backward(x2, h, hA, g, mean, rstd)
+        ctx.owner, ctx.der = owner, der
+        ctx.meta = (B, N, D, hw, has_cls, drop_p, seed, freq is not None)
+        return y.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, h, hA, g, mean, rstd = ctx.saved_tensors
+        owner, der = ctx.owner, ctx.der
+        B, N, D, hw, has_cls, drop_p, seed, has_freq = ctx.meta
+        dev = x2.device
+        c = owner.adapter_conv
+        dy2 = dy.contiguous().view(B * N, D)
+        ps = list(owner.parameters())
+        sink = ps[0]._ngu_sink if (ps and all(getattr(p, "_ngu_sink", None) is not None and p.grad is not None for p in ps)) else None
+        names = ["norm.weight", "norm.bias", "gamma", "gammax", "project1.weight", "project1.bias", "conv1.weight", "conv1.bias",
+                 "conv2.weight", "conv2.bias", "conv3.weight", "conv3.bias", "projector.weight", "projector.bias",
+                 "project2.weight", "project2.bias"] + (["freq"] if has_freq else [])
+        params = [owner.norm.weight, owner.norm.bias, owner.gamma, owner.gammax, owner.project1.weight, owner.project1.bias,
+                  c.conv1.weight, c.conv1.bias, c.conv2.weight, c.conv2.bias, c.conv3.weight, c.conv3.bias,
+                  c.projector.weight, c.projector.bias, owner.project2.weight, owner.project2.bias] + ([c.freq_filter] if has_freq else [])
+        gr = {n: (p.grad if sink is not None else torch.zeros(p.shape, device=dev, dtype=torch.float32)) for n, p in zip(names, params)}
+        # project2: y = x + g W2^T + b2
+        dg = ops.gemm(dy2, der.view("w2_t", torch.bfloat16, (64, D)))                  # [M, 64] = dy W2
+        ops.wgrad(dy2, g.view(B * N, 64), out=gr["project2.weight"])                   # [D, 64]
+        ops.colsum(dy2, out=gr["project2.bias"])
+        # stage backward -> [dh | dh rstd], row terms of the LayerNorm backward, stage reductions into ws
+        dhcat, rowab, ws = ops.mona_bwd_stage(h, hA, dg.view(B, N, 64), mean, rstd, der, D, hw, has_cls, drop_p, seed,
+                                              gr["projector.weight"], gr["projector.bias"])
+        ops.wgrad(x2, dhcat, out=ws[:D * 128].view(D, 128))                            # G = x^T [dh | dh rstd]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dhcat, der.view("wcat_t", torch.bfloat16, (D, 128)), aux=dy2, aux_mode=L.AUX_MONA_DX, aux2=x2, rowab=rowab)
+            dx = dx.view(B, N, D)
+        ops.mona_finish(owner, {"dw1": gr["project1.weight"], "db1": gr["project1.bias"], "dln_w": gr["norm.weight"],
+                                "dln_b": gr["norm.bias"], "dgamma": gr["gamma"], "dgammax": gr["gammax"],
+                                "dk3": gr["conv1.weight"], "db3": gr["conv1.bias"], "dk5": gr["conv2.weight"], "db5": gr["conv2.bias"],
+                                "dk7": gr["conv3.weight"], "db7": gr["conv3.bias"], "dfreq": gr.get("freq")}, ws, D)
+        if sink is not None:
+            buckets, key, count = sink
+            buckets.notify(key, count)
+            return (dx,) + (None,) * 22
+        return (dx,) + tuple(gr[n] for n in names[:16]) + (gr.get("freq"),) + (None,) * 5
+
+
 class _MonaOpBase(nn.Module):
     """Parameter container for the multi-scale depthwise stage.  forward() is not used by the adapters (the fused
     stage kernel consumes the parameters directly)."""
@@ -224,6 +291,12 @@ class BaselineMona(nn.Module):
         seed = _next_seed() if p > 0 else 0
         c = self.adapter_conv
         freq, ne_w1, ne_b1, ne_w2, ne_b2 = c.variant_tensors()
+        if _fused_ok(xb, self, self.project1.weight.shape[0], hw, N, freq, ne_w1):
+            return MonaFusedFunction.apply(xb, self.norm.weight, self.norm.bias, self.gamma, self.gammax,
+                                           self.project1.weight, self.project1.bias,
+                                           c.conv1.weight, c.conv1.bias, c.conv2.weight, c.conv2.bias, c.conv3.weight, c.conv3.bias,
+                                           c.projector.weight, c.projector.bias, self.project2.weight, self.project2.bias, freq,
+                                           hw, has_cls, p, seed, self)
         return MonaFunction.apply(xb, self.norm.weight, self.norm.bias, self.gamma, self.gammax,
                                   self.project1.weight, self.project1.bias,
                                   c.conv1.weight, c.conv1.bias, c.conv2.weight, c.conv2.bias, c.conv3.weight, c.conv3.bias,

@@ -155,6 +155,13 @@ class HFTextEncoder(nn.Module):
         self.proj = nn.Sequential(nn.Linear(d, hidden, bias=False), nn.GELU(), nn.Linear(hidden, embed_dim, bias=False))
         self.pad_token_id = pad_token_id
         self.compute_dtype = torch.bfloat16
+        self._pad_flag = None
+
+    def check_padding(self):
+        """Raise if any batch seen since the last check was not right-padded (host read of the device flag)."""
+        if self._pad_flag is not None and int(self._pad_flag.item()) != 0:
+            self._pad_flag.zero_()
+            raise NotImplementedError("ngu B200 path: only right-padded token batches (a suffix of pad ids) are supported")
 
     def _qkv_weights(self, sa, dt):
         """Fused [3d, d] q/k/v weight + bias (frozen), cached on the module."""
@@ -174,14 +181,17 @@ class HFTextEncoder(nn.Module):
         # Key-padding mask (open_clip HFTextEncoder.forward: attn_mask = (x != pad_token_id)): tokenizers pad on the right,
         # so the mask is a per-sequence valid length; padded keys are masked in every layer, padded query rows compute
         # values nobody reads (CLS pooling).  Any other mask shape is refused loudly.
-        kv_len = None
-        valid = ids != self.pad_token_id
-        if not bool(valid.all()):
-            lens = valid.sum(1)
-            prefix = torch.arange(ids.shape[1], device=ids.device)[None, :] < lens[:, None]
-            if not bool((prefix == valid).all()) or bool((lens < 1).any()):
-                raise NotImplementedError("ngu B200 path: only right-padded token batches (a suffix of pad ids) are supported")
-            kv_len = lens.to(torch.int32).contiguous()
+        # The lengths are computed on the device every call (one tiny kernel, no host round trip); the right-padding
+        # property lands in a device flag that is checked eagerly in eval mode (a host sync, inference / tests) and lazily
+        # through check_padding() in train mode, where the step must not synchronise (finetune.py:272-303 hot loop).
+        if ids.is_cuda:
+            if self._pad_flag is None or self._pad_flag.device != ids.device:
+                self._pad_flag = torch.zeros(1, device=ids.device, dtype=torch.int32)
+            kv_len = ops.kv_len(ids.contiguous(), self.pad_token_id, self._pad_flag)
+            if not self.training:
+                self.check_padding()
+        else:
+            raise L.NguError("ngu ops need CUDA tensors: there is no CPU fallback in the product path")
         has_lora = any(getattr(m, "r", 0) and hasattr(m, "w_lora_A") for m in self.modules())
         if has_lora or any(p.requires_grad for p in self.parameters()):
             return self._forward_trainable(ids, kv_len)

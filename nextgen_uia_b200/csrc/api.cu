@@ -29,6 +29,7 @@ int ngu_selftest_device(void) {
 int ngu_gemm(const ngu_gemm_desc* d, void* stream) {
   if (!d) { set_last_error("ngu_gemm: null descriptor"); return NGU_ERR_ARG; }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (d->aux_mode == NGU_AUX_MONA_DX && d->dtype != NGU_BF16) { set_last_error("ngu_gemm: NGU_AUX_MONA_DX is a bf16 (tcgen05) epilogue"); return NGU_ERR_DTYPE; }
   if (d->dtype == NGU_BF16) return gemm_tc(*d, s);
   if (d->dtype == NGU_F32) return gemm_simt(*d, s);
   if (d->dtype == 100 + NGU_BF16) { ngu_gemm_desc t = *d; t.dtype = NGU_BF16; return gemm_simt(t, s); }  // test-only: bf16 on CUDA cores
@@ -45,6 +46,15 @@ int ngu_ln_bwd(const ngu_ln_bwd_desc* d, void* stream) { NGU_NONNULL(d, "ngu_ln_
 int ngu_mona_pre_bwd(const ngu_mona_pre_bwd_desc* d, void* stream) { NGU_NONNULL(d, "ngu_mona_pre_bwd"); return mona_pre_bwd(*d, NGU_STREAM); }
 int ngu_mona_conv_fwd(const ngu_mona_conv_desc* d, void* stream) { NGU_NONNULL(d, "ngu_mona_conv_fwd"); return mona_conv_fwd(*d, NGU_STREAM); }
 int ngu_mona_conv_bwd(const ngu_mona_conv_desc* d, void* stream) { NGU_NONNULL(d, "ngu_mona_conv_bwd"); return mona_conv_bwd(*d, NGU_STREAM); }
+
+int64_t ngu_mona_ws_floats(int D) { return mona_ws_floats(D); }
+int ngu_mona_prep(const ngu_mona_prep_item* items, int n, int D, void* stream) { return mona_prep(items, n, D, NGU_STREAM); }
+int ngu_mona_fwd_stage(const ngu_mona_stage_desc* d, void* stream) { NGU_NONNULL(d, "ngu_mona_fwd_stage"); return mona_fwd_stage(*d, NGU_STREAM); }
+int ngu_mona_bwd_stage(const ngu_mona_stage_desc* d, void* stream) { NGU_NONNULL(d, "ngu_mona_bwd_stage"); return mona_bwd_stage(*d, NGU_STREAM); }
+int ngu_mona_finish(const ngu_mona_params* p, const ngu_mona_grads* g, const float* ws, int D, void* stream) {
+  if (!p || !g) { set_last_error("ngu_mona_finish: null descriptor"); return NGU_ERR_ARG; }
+  return mona_finish(*p, *g, ws, D, NGU_STREAM);
+}
 
 int ngu_attn_fwd(const ngu_attn_desc* d, void* stream) {
   NGU_NONNULL(d, "ngu_attn_fwd");
@@ -70,7 +80,7 @@ int ngu_infonce_normalize_bwd(const float* dxhat, const float* xhat, const float
 
 int ngu_wgrad(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int T, int Mo, int No, int dtype, int impl,
               void* stream) {
-  if (impl == 0 && T > 0 && wgrad_tc_supported(ldx, ldy, ldd, Mo, No, dtype, X, Y, D)) return wgrad_tc(X, ldx, Y, ldy, D, ldd, T, Mo, NGU_STREAM);
+  if (impl == 0 && T > 0 && wgrad_tc_supported(ldx, ldy, ldd, Mo, No, dtype, X, Y, D)) return wgrad_tc(X, ldx, Y, ldy, D, ldd, T, Mo, No, NGU_STREAM);
   return wgrad_simt(X, ldx, Y, ldy, D, ldd, T, Mo, No, dtype, NGU_STREAM);
 }
 int ngu_colsum(const void* X, int ldx, float* out, int T, int C, int dtype, void* stream) {
@@ -80,6 +90,9 @@ int ngu_dropout(const void* x, void* out, int64_t n, float p, uint64_t seed, int
   return dropout(x, out, size_t(n), p, seed, accumulate, dtype, NGU_STREAM);
 }
 int ngu_sqnorm(const float* x, int64_t n, float* out, void* stream) { return sqnorm(x, size_t(n), out, NGU_STREAM); }
+int ngu_guard_tick(int64_t* state, const float* loss, const float* gsq, int mode, void* stream) { return guard_tick(state, loss, gsq, mode, NGU_STREAM); }
+int ngu_kv_len(const int64_t* ids, int64_t pad_id, int* kv_len_out, int* flag, int B, int S, void* stream) { return kv_len(ids, pad_id, kv_len_out, flag, B, S, NGU_STREAM); }
+int ngu_set_seed_counter(const void* counter) { set_seed_counter(reinterpret_cast<const uint64_t*>(counter)); return NGU_OK; }
 int ngu_adamw_step(const ngu_adamw_desc* d, void* stream) { NGU_NONNULL(d, "ngu_adamw_step"); return adamw_step(*d, NGU_STREAM); }
 int ngu_patchify(const float* img, void* out, int B, int R, int P, int dtype, void* stream) {
   return patchify(img, out, B, R, P, dtype, NGU_STREAM);

@@ -29,6 +29,7 @@ NGU_DEVINL void load_tile(T* dst, const T* src, int rows, int64_t ts) {
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32)
 attn_fwd_simt_kernel(ngu_attn_desc d) {
+  pdl_prologue();
   constexpr int LD = Pad<T>::LD;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int b = blockIdx.x / d.H, hd = blockIdx.x % d.H;
@@ -97,6 +98,7 @@ attn_fwd_simt_kernel(ngu_attn_desc d) {
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32)
 attn_bwd_simt_kernel(ngu_attn_desc d, int two_phase) {
+  pdl_prologue();
   constexpr int LD = Pad<T>::LD;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const int b = blockIdx.x / d.H, hd = blockIdx.x % d.H;
@@ -230,7 +232,7 @@ int launch_fwd(const ngu_attn_desc& d, cudaStream_t st) {
   if (smem > 227 * 1024) { set_last_error("attn_fwd(simt): S=%d needs %d B smem", d.S, smem); return NGU_ERR_SHAPE; }
   cudaError_t e = cudaFuncSetAttribute(attn_fwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return cuda_status(e, "attn_fwd attr");
-  attn_fwd_simt_kernel<T><<<d.B * d.H, kWarps * 32, smem, st>>>(d);
+  launch_pdl(attn_fwd_simt_kernel<T>, dim3(d.B * d.H), dim3(kWarps * 32), size_t(smem), st, d);
   return check_launch("attn_fwd_simt");
 }
 template <typename T>
@@ -247,7 +249,7 @@ int launch_bwd(const ngu_attn_desc& d, cudaStream_t st) {
   if (smem > 227 * 1024) { set_last_error("attn_bwd(simt): N=%d S=%d needs %d B smem", d.N, d.S, smem); return NGU_ERR_SHAPE; }
   cudaError_t e = cudaFuncSetAttribute(attn_bwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return cuda_status(e, "attn_bwd attr");
-  attn_bwd_simt_kernel<T><<<d.B * d.H, kWarps * 32, smem, st>>>(d, two_phase);
+  launch_pdl(attn_bwd_simt_kernel<T>, dim3(d.B * d.H), dim3(kWarps * 32), size_t(smem), st, d, two_phase);
   return check_launch("attn_bwd_simt");
 }
 

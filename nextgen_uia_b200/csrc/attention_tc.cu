@@ -88,6 +88,7 @@ constexpr int kFwdSmem = 5 * kTileBytes + 2048 + 1024 + 1024;  // Q tile + K (2 
 // P (bf16) aliases the S columns, so every thread keeps its P values in registers until BOTH threads of the row have
 // finished reading S.
 __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = base + kTileBytes, sV = base + 3 * kTileBytes;
@@ -288,6 +289,7 @@ constexpr int kFwdPThreads = 32 * (2 * kFwdGroupWarps + 2);
 constexpr int kFwdPSmem = 12 * kTileBytes + 2 * 2048 + 1024 + 1024;   // K/V 2 x 4 tiles, Q 4 tiles, exchange, barriers
 
 __global__ void __launch_bounds__(kFwdPThreads, 1) attn_fwd_persistent_kernel(const __grid_constant__ AttnTcParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   auto sK = [&](int buf, int u) { return base + uint32_t(buf * 4 + u) * kTileBytes; };
@@ -734,6 +736,7 @@ struct BwdIssuer {
 
 template <int NT>
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = base + 2 * kTileBytes, sV = base + 4 * kTileBytes, sDO = base + 6 * kTileBytes;
@@ -1115,7 +1118,7 @@ int attn_fwd_tc(const ngu_attn_desc& d, cudaStream_t st) {
   // starting point for a single-group four-threads-per-row variant).
   static const int mode = [] { const char* e = getenv("NGU_ATTN_FWD"); return e ? atoi(e) : 0; }();
   if ((mode == 0 && d.impl != 2) || d.kv_len != nullptr) {   // key padding: only the per-tile kernel masks by kv_len
-    attn_fwd_tc_kernel<<<d.B * d.H * ((d.N + TILE - 1) / TILE), kFwdThreads, kFwdSmem, st>>>(p);
+    launch_pdl(attn_fwd_tc_kernel, dim3(d.B * d.H * ((d.N + TILE - 1) / TILE)), dim3(kFwdThreads), size_t(kFwdSmem), st, p);
     return check_launch("attn_fwd_tc");
   }
   static bool attr2 = false;
@@ -1125,7 +1128,7 @@ int attn_fwd_tc(const ngu_attn_desc& d, cudaStream_t st) {
     attr2 = true;
   }
   const int items = d.B * d.H;
-  attn_fwd_persistent_kernel<<<items < sm_count() ? items : sm_count(), kFwdPThreads, kFwdPSmem, st>>>(p);
+  launch_pdl(attn_fwd_persistent_kernel, dim3(items < sm_count() ? items : sm_count()), dim3(kFwdPThreads), size_t(kFwdPSmem), st, p);
   return check_launch("attn_fwd_persistent");
 }
 
@@ -1141,8 +1144,8 @@ int attn_bwd_tc(const ngu_attn_desc& d, cudaStream_t st) {
   }
   const int items = d.B * d.H;
   const int grid = items < sm_count() ? items : sm_count();
-  if (d.N > TILE) attn_bwd_tc_kernel<2><<<grid, kBwdThreads, kBwdSmem, st>>>(p);
-  else attn_bwd_tc_kernel<1><<<grid, kBwdThreads, kBwdSmem, st>>>(p);
+  if (d.N > TILE) launch_pdl(attn_bwd_tc_kernel<2>, dim3(grid), dim3(kBwdThreads), size_t(kBwdSmem), st, p);
+  else launch_pdl(attn_bwd_tc_kernel<1>, dim3(grid), dim3(kBwdThreads), size_t(kBwdSmem), st, p);
   return check_launch("attn_bwd_tc");
 }
 

@@ -68,6 +68,19 @@ NGU_DEVINL T warp_max(T v) {
 }
 
 // ----------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of this library starts with pdl_prologue() and is launched through
+// launch_pdl() / with the programmatic-stream-serialization attribute, so the launch of kernel i+1 (grid setup, CTA
+// scheduling) overlaps the tail of kernel i instead of following its completion.  griddepcontrol.wait returns once ALL
+// prerequisite grids have completed and flushed, so no global memory is touched before the data it depends on exists;
+// launch_dependents is issued right after so the next grid can be scheduled as soon as SM resources free up.
+// Both are no-ops when the kernel was launched without the attribute (NGU_PDL=0).
+// ----------------------------------------------------------------------------------------
+NGU_DEVINL void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------
 NGU_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
@@ -138,6 +151,13 @@ NGU_DEVINL void tma_load_2d_mcast(uint32_t smem_dst, const CUtensorMap* m, uint3
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5, %6;"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask), "l"(hint)
+      : "memory");
+}
+NGU_DEVINL void tma_load_3d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, uint64_t hint = kEvictNormal) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
 // pull a tile into L2 ahead of the TMA load that will consume it (no smem, no barrier)
@@ -317,6 +337,7 @@ NGU_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+NGU_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 NGU_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // registers -> TMEM (32 lanes x N columns)
@@ -485,6 +506,24 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld, uint64_t ldb,
                       uint32_t box_rows, uint32_t box_cols, int swizzle);
 int sm_count();
+bool pdl_enabled();               // NGU_PDL != 0 (default on)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+const uint64_t* seed_counter();   // device pointer registered with ngu_set_seed_counter, or nullptr
 
 }  // namespace ngu
 
@@ -561,6 +600,10 @@ NGU_DEVINL uint64_t dropout_bits(uint64_t seed, uint64_t group) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
+// Optional per-process device counter mixed into every dropout seed (ngu_set_seed_counter): a captured CUDA graph replays
+// with the seeds baked in, the counter (advanced on device once per micro-step) makes each replay draw fresh masks while
+// forward and backward of the same step still agree.
+NGU_DEVINL uint64_t mix_seed(uint64_t seed, const uint64_t* ctr) { return ctr ? seed + (*ctr) * 0xD1B54A32D192ED03ull : seed; }
 NGU_DEVINL uint32_t dropout_threshold(float p) { return uint32_t(p * 65536.0f); }
 NGU_DEVINL float dropout_pick(uint64_t bits, int lane4, uint32_t thr, float keep_scale) {
   return (uint32_t(bits >> (16 * lane4)) & 0xFFFFu) >= thr ? keep_scale : 0.0f;

@@ -12,6 +12,7 @@ constexpr int TM = 64, TN = 64, TK = 16;
 
 template <typename T>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs a) {
+  pdl_prologue();
   __shared__ float sA[TK][TM + 1];
   __shared__ float sB[TK][TN + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -88,8 +89,8 @@ int gemm_simt(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) { set_last_error("gemm_simt: empty problem"); return NGU_ERR_SHAPE; }
   dim3 grid((a.N + TN - 1) / TN, (a.M + TM - 1) / TM);
   if (grid.y > 65535) { set_last_error("gemm_simt: M too large for check mode"); return NGU_ERR_SHAPE; }
-  if (a.dtype == NGU_F32) gemm_simt_kernel<float><<<grid, 256, 0, stream>>>(a);
-  else gemm_simt_kernel<bf16><<<grid, 256, 0, stream>>>(a);
+  if (a.dtype == NGU_F32) launch_pdl(gemm_simt_kernel<float>, dim3(grid), dim3(256), size_t(0), stream, a);
+  else launch_pdl(gemm_simt_kernel<bf16>, dim3(grid), dim3(256), size_t(0), stream, a);
   return check_launch("gemm_simt");
 }
 

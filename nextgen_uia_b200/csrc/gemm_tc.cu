@@ -53,6 +53,9 @@ struct GemmKernelParams {
   const float* bias;  // [N] fp32 or nullptr
   const bf16* aux;    // [M, ldaux] residual / saved pre-activation, or nullptr
   int ldaux;
+  const bf16* aux2;   // [M, ldaux2] second elementwise operand (NGU_AUX_MONA_DX: x), or nullptr
+  int ldaux2;
+  const float* rowab; // [M, 2] per-row (alpha_r, beta_r) of NGU_AUX_MONA_DX
   int M, N, K, K2;
   int act;       // NGU_ACT_*
   int aux_mode;  // NGU_AUX_*
@@ -100,9 +103,26 @@ NGU_DEVINL void epi_chunk(const uint32_t (&v)[32], const uint4 (&ax)[4], float b
   }
 }
 
-template <int BLOCK_N, int kCluster, bool kPair>
+// NGU_AUX_MONA_DX epilogue: out = acc + aux + beta_r * aux2 + alpha_r  (backward of the Mona input mix + residual; the
+// LayerNorm-backward row terms arrive as two per-row scalars, see mona_fused.cu)
+NGU_DEVINL void epi_chunk_dx(const uint32_t (&v)[32], const uint4 (&ax)[4], const uint4 (&bx)[4], float alpha_r, float beta_r,
+                             uint32_t (&outp)[16]) {
+  const uint32_t* axw = reinterpret_cast<const uint32_t*>(ax);
+  const uint32_t* bxw = reinterpret_cast<const uint32_t*>(bx);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 a = unpack_bf16x2(axw[j]);
+    const float2 b = unpack_bf16x2(bxw[j]);
+    const float o0 = fmaf(beta_r, b.x, __uint_as_float(v[2 * j]) + alpha_r) + a.x;
+    const float o1 = fmaf(beta_r, b.y, __uint_as_float(v[2 * j + 1]) + alpha_r) + a.y;
+    outp[j] = pack_bf16x2(o0, o1);
+  }
+}
+
+template <int BLOCK_N, int kCluster, bool kPair, bool kDX = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
+  pdl_prologue();
   static_assert(!kPair || kCluster == 2, "pair mode is a 2-CTA cluster");
   using Cfg = GemmCfg<BLOCK_N, kPair>;
   extern __shared__ uint8_t smem_raw[];
@@ -286,15 +306,27 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) dst[j] = (ok && nc + j * 8 < p.N) ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
     };
+    auto load_aux2 = [&](int t, int c, uint4 (&dst)[4]) {
+      const int m0 = tile_m0(t), nc = tile_n0(t) + c * kChunkCols;
+      const int row = m0 + q * 32 + lane;
+      const bool ok = t < num_tiles && nc < p.N && row < p.M;
+      const uint4* ap = reinterpret_cast<const uint4*>(p.aux2 + size_t(ok ? row : 0) * p.ldaux2 + (ok ? nc : 0));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[j] = (ok && nc + j * 8 < p.N) ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
+    };
 
     if (active) {
       int acc = 0;
       uint32_t acc_ph = 0;
       uint4 axn[4];
+      uint4 bxn[kDX ? 4 : 1];
       load_aux(tile_first, c_begin, axn);
+      if (kDX) load_aux2(tile_first, c_begin, reinterpret_cast<uint4 (&)[4]>(bxn));
       for (int t = tile_first; t < num_tiles; t += tile_stride) {
         const int m0 = tile_m0(t);
         const int n0 = tile_n0(t);
+        float2 rab = make_float2(0.f, 0.f);
+        if (kDX) { const int row = m0 + q * 32 + lane; if (row < p.M) rab = __ldg(reinterpret_cast<const float2*>(p.rowab) + row); }
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
@@ -309,11 +341,20 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
           if (p.bias != nullptr && live) bias_l = (nc + lane < p.N) ? __ldg(p.bias + nc + lane) : 0.f;
           // aux chunk was prefetched one work item ago; start fetching the next one now
           uint4 ax[4];
+          uint4 bx[kDX ? 4 : 1];
 #pragma unroll
           for (int j = 0; j < 4; ++j) ax[j] = axn[j];
+          if (kDX) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bx[j] = bxn[j];
+          }
           if (use_aux) {
             if (ci + 1 < kPerWarp) load_aux(t, c + 1, axn);
             else load_aux(t + tile_stride, c_begin, axn);
+          }
+          if (kDX) {
+            if (ci + 1 < kPerWarp) load_aux2(t, c + 1, reinterpret_cast<uint4 (&)[4]>(bxn));
+            else load_aux2(t + tile_stride, c_begin, reinterpret_cast<uint4 (&)[4]>(bxn));
           }
           tmem_ld_wait();
           if (ci == kPerWarp - 1) {
@@ -328,7 +369,9 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
 
           uint32_t outp[16];
           uint32_t prep[16];
-          {
+          if (kDX) {
+            epi_chunk_dx(v, ax, reinterpret_cast<const uint4 (&)[4]>(bx), rab.x, rab.y, outp);
+          } else {
             const bool sv = p.save_pre != 0;
             const int mode = (p.aux_mode == NGU_AUX_DACT) ? 100 : p.act * 3 + p.aux_mode;  // warp-uniform
             switch (mode) {
@@ -346,7 +389,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
           // slab rows are 64 bytes; SWIZZLE_64B: 16-byte piece index ^= (row >> 1) & 3
           const uint32_t rbase = slab + lane * 64;
           const uint32_t rsw = uint32_t(lane >> 1) & 3u;
-          if (p.save_pre) {
+          if (!kDX && p.save_pre) {
             // activation derivative (saved for backward): transpose through the slab, then coalesced 64-byte row pieces
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -401,7 +444,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
   }
 }
 
-template <int BLOCK_N, int kCluster, bool kPair = false>
+template <int BLOCK_N, int kCluster, bool kPair = false, bool kDX = false>
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, kPair>;
   GemmKernelParams p;
@@ -425,6 +468,9 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   p.bias = a.bias;
   p.aux = reinterpret_cast<const bf16*>(a.aux);
   p.ldaux = a.ldaux;
+  p.aux2 = reinterpret_cast<const bf16*>(a.aux2);
+  p.ldaux2 = a.ldaux2;
+  p.rowab = a.rowab;
   p.M = a.M; p.N = a.N; p.K = a.K; p.K2 = a.K2;
   p.act = a.act; p.aux_mode = a.aux_mode; p.save_pre = a.save_pre;
   p.alpha = a.alpha;
@@ -436,7 +482,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
 
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kCluster, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kCluster, kPair, kDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_status(e, "gemm_tc smem attribute");
     attr_done = true;
   }
@@ -451,14 +497,16 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = kCluster;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kCluster, kPair>, p);
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kCluster, kPair, kDX>, p);
   count_launch(1);
   if (e != cudaSuccess) return cuda_status(e, "gemm_tc launch");
   return cuda_status(cudaGetLastError(), "gemm_tc");
@@ -479,6 +527,14 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   if (a.save_pre && (a.Pre == nullptr || (a.ldpre % 8) || (a.N % 8))) {
     set_last_error("gemm_tc: save_pre needs a Pre pointer, ldpre %% 8 == 0 and N %% 8 == 0");
     return NGU_ERR_ALIGN;
+  }
+  if (a.aux_mode == NGU_AUX_MONA_DX) {
+    if (a.aux2 == nullptr || a.rowab == nullptr || (a.ldaux2 % 8) || a.act != NGU_ACT_NONE || a.save_pre || a.bias != nullptr || a.alpha != 1.0f) {
+      set_last_error("gemm_tc: NGU_AUX_MONA_DX needs aux, aux2 (ldaux2 %% 8 == 0), rowab and no bias / activation / save_pre / alpha");
+      return NGU_ERR_ARG;
+    }
+    // short K (128), two streamed elementwise operands: epilogue-bound -> independent-CTA multicast variant
+    return a.M > BLOCK_M ? launch_gemm_tc<256, 2, false, true>(a, stream) : launch_gemm_tc<256, 1, false, true>(a, stream);
   }
   int bn = a.block_n;
   if (bn == 0) bn = (a.N > 128) ? 256 : (a.N > 64 ? 128 : 64);

@@ -15,6 +15,7 @@ namespace {
 // one warp per row: xhat = x / max(||x||, eps) (fp32 out), norm saved
 template <typename T>
 __global__ void normalize_fwd_kernel(const T* __restrict__ x, float* __restrict__ xhat, float* __restrict__ norm, int B, int E) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= B) return;
   float s = 0.f;
@@ -29,6 +30,7 @@ template <typename T>
 __global__ void normalize_bwd_kernel(const float* __restrict__ dxhat, const float* __restrict__ xhat,
                                      const float* __restrict__ norm, const float* __restrict__ gscale,
                                      T* __restrict__ dx, int B, int E) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= B) return;
   float s = 0.f;
@@ -41,6 +43,7 @@ __global__ void normalize_bwd_kernel(const float* __restrict__ dxhat, const floa
 
 // row log-sum-exp of L [n, n] (one warp per row) + accumulate sum_i (lse_i - L_ii) * w into *loss
 __global__ void row_lse_kernel(const float* __restrict__ L, float* __restrict__ lse, float* __restrict__ loss, int n, float w) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= n) return;
   const float* r = L + size_t(row) * n;
@@ -62,6 +65,7 @@ __global__ void row_lse_kernel(const float* __restrict__ L, float* __restrict__ 
 __global__ void __launch_bounds__(256)
 dfeat_kernel(const float* __restrict__ L, const float* __restrict__ lse_a, const float* __restrict__ lse_b,
              const float* __restrict__ Bf, float* __restrict__ dA, int n, int E, int r0, float coef) {
+  pdl_prologue();
   extern __shared__ float gw[];  // [n]
   const int i = r0 + blockIdx.x;
   const float la = lse_a[i];
@@ -83,8 +87,8 @@ int infonce_normalize(const void* x, float* xhat, float* norm, int B, int E, int
   if (B <= 0 || E <= 0) { set_last_error("infonce_normalize: empty"); return NGU_ERR_SHAPE; }
   const int wpb = 4;
   const int grid = (B + wpb - 1) / wpb;
-  if (dtype == NGU_F32) normalize_fwd_kernel<float><<<grid, wpb * 32, 0, st>>>(reinterpret_cast<const float*>(x), xhat, norm, B, E);
-  else normalize_fwd_kernel<bf16><<<grid, wpb * 32, 0, st>>>(reinterpret_cast<const bf16*>(x), xhat, norm, B, E);
+  if (dtype == NGU_F32) launch_pdl(normalize_fwd_kernel<float>, dim3(grid), dim3(wpb * 32), size_t(0), st, reinterpret_cast<const float*>(x), xhat, norm, B, E);
+  else launch_pdl(normalize_fwd_kernel<bf16>, dim3(grid), dim3(wpb * 32), size_t(0), st, reinterpret_cast<const bf16*>(x), xhat, norm, B, E);
   return check_launch("infonce_normalize");
 }
 
@@ -92,8 +96,8 @@ int infonce_normalize_bwd(const float* dxhat, const float* xhat, const float* no
                           int dtype, cudaStream_t st) {
   const int wpb = 4;
   const int grid = (B + wpb - 1) / wpb;
-  if (dtype == NGU_F32) normalize_bwd_kernel<float><<<grid, wpb * 32, 0, st>>>(dxhat, xhat, norm, gscale, reinterpret_cast<float*>(dx), B, E);
-  else normalize_bwd_kernel<bf16><<<grid, wpb * 32, 0, st>>>(dxhat, xhat, norm, gscale, reinterpret_cast<bf16*>(dx), B, E);
+  if (dtype == NGU_F32) launch_pdl(normalize_bwd_kernel<float>, dim3(grid), dim3(wpb * 32), size_t(0), st, dxhat, xhat, norm, gscale, reinterpret_cast<float*>(dx), B, E);
+  else launch_pdl(normalize_bwd_kernel<bf16>, dim3(grid), dim3(wpb * 32), size_t(0), st, dxhat, xhat, norm, gscale, reinterpret_cast<bf16*>(dx), B, E);
   return check_launch("infonce_normalize_bwd");
 }
 
@@ -101,6 +105,7 @@ int infonce_normalize_bwd(const float* dxhat, const float* xhat, const float* no
 // Lt = L^T for the [n, n] fp32 logits (32 x 32 smem tiles, conflict-free): the text->image logits are the transpose of the
 // image->text logits, so a second n x n x E GEMM is not needed.
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -128,21 +133,21 @@ int infonce_core(const ngu_infonce_desc& d, cudaStream_t st) {
   if (int rc = gemm_simt(g, st)) return rc;
   {
     const dim3 tg((n + 31) / 32, (n + 31) / 32);
-    transpose_kernel<<<tg, 256, 0, st>>>(L, Lt, n);
+    launch_pdl(transpose_kernel, dim3(tg), dim3(256), size_t(0), st, L, Lt, n);
     if (int rc = check_launch("infonce transpose")) return rc;
   }
   const int wpb = 4;
   const int grid = (n + wpb - 1) / wpb;
-  row_lse_kernel<<<grid, wpb * 32, 0, st>>>(L, rlse, d.loss, n, 0.5f / float(n));
+  launch_pdl(row_lse_kernel, dim3(grid), dim3(wpb * 32), size_t(0), st, L, rlse, d.loss, n, 0.5f / float(n));
   if (int rc = check_launch("infonce row_lse")) return rc;
-  row_lse_kernel<<<grid, wpb * 32, 0, st>>>(Lt, clse, d.loss, n, 0.5f / float(n));
+  launch_pdl(row_lse_kernel, dim3(grid), dim3(wpb * 32), size_t(0), st, Lt, clse, d.loss, n, 0.5f / float(n));
   if (int rc = check_launch("infonce col_lse")) return rc;
   if (d.dihat != nullptr) {
     const float coef = 1.f / (2.f * float(n) * d.temperature);
     const int smem = n * int(sizeof(float));
-    dfeat_kernel<<<d.Bl, 256, smem, st>>>(L, rlse, clse, d.that, d.dihat, n, E, d.r0, coef);
+    launch_pdl(dfeat_kernel, dim3(d.Bl), dim3(256), size_t(smem), st, L, rlse, clse, d.that, d.dihat, n, E, d.r0, coef);
     if (int rc = check_launch("infonce dI")) return rc;
-    dfeat_kernel<<<d.Bl, 256, smem, st>>>(Lt, clse, rlse, d.ihat, d.dthat, n, E, d.r0, coef);
+    launch_pdl(dfeat_kernel, dim3(d.Bl), dim3(256), size_t(smem), st, Lt, clse, rlse, d.ihat, d.dthat, n, E, d.r0, coef);
     if (int rc = check_launch("infonce dT")) return rc;
   }
   return NGU_OK;

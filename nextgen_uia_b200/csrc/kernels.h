@@ -17,6 +17,11 @@ int ln_bwd(const ngu_ln_bwd_desc& d, cudaStream_t s);
 int mona_pre_bwd(const ngu_mona_pre_bwd_desc& d, cudaStream_t s);
 int mona_conv_fwd(const ngu_mona_conv_desc& d, cudaStream_t s);
 int mona_conv_bwd(const ngu_mona_conv_desc& d, cudaStream_t s);
+int64_t mona_ws_floats(int D);
+int mona_prep(const ngu_mona_prep_item* items, int n, int D, cudaStream_t s);
+int mona_fwd_stage(const ngu_mona_stage_desc& d, cudaStream_t s);
+int mona_bwd_stage(const ngu_mona_stage_desc& d, cudaStream_t s);
+int mona_finish(const ngu_mona_params& p, const ngu_mona_grads& g, const float* ws, int D, cudaStream_t s);
 int attn_validate(const ngu_attn_desc& d, const char* what, bool bwd);
 int attn_fwd_simt(const ngu_attn_desc& d, cudaStream_t s);
 int attn_bwd_simt(const ngu_attn_desc& d, cudaStream_t s);
@@ -34,10 +39,13 @@ int cast_f32_batch(const ngu_cast_item* items, int n, int dtype, cudaStream_t s)
 int wgrad_simt(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int Tn, int Mo, int No, int dtype, cudaStream_t s);
 int dropout(const void* x, void* out, size_t n, float p, uint64_t seed, int accumulate, int dtype, cudaStream_t s);
 bool wgrad_tc_supported(int ldx, int ldy, int ldd, int Mo, int No, int dtype, const void* X, const void* Y, const float* D);
-int wgrad_tc(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int T, int Mo, cudaStream_t s);
+int wgrad_tc(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int T, int Mo, int No, cudaStream_t s);
 int colsum(const void* X, int ldx, float* out, int Tn, int Cn, int dtype, cudaStream_t s);
 
 int sqnorm(const float* x, size_t n, float* out, cudaStream_t s);
+int guard_tick(int64_t* state, const float* loss, const float* gsq, int mode, cudaStream_t s);
+int kv_len(const int64_t* ids, int64_t pad, int* out, int* flag, int B, int S, cudaStream_t s);
+void set_seed_counter(const uint64_t* p);
 int adamw_step(const ngu_adamw_desc& d, cudaStream_t s);
 
 void count_launch(int n = 1);

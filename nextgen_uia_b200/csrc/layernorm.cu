@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 ln_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
               const float* __restrict__ gamma, const float* __restrict__ gammax, T* __restrict__ y, int64_t ldy,
               float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D, float eps) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   constexpr int kMaxIt = kMaxD / (32 * V);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 ln_bwd_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ x, int64_t ldx, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ w, const T* __restrict__ dres, int64_t ldr,
               T* __restrict__ dx, int64_t lddx, int M, int D) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   constexpr int kMaxIt = kMaxD / (32 * V);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,6 +139,7 @@ mona_pre_bwd_kernel(const T* __restrict__ du, const T* __restrict__ dy, const T*
                     const float* __restrict__ gamma, const float* __restrict__ gammax,
                     T* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
                     float* __restrict__ dgamma, float* __restrict__ dgammax, float* __restrict__ dycol, int M) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   constexpr int kIt = D / (32 * V);
   constexpr int R = D / 64;  // warps per CTA = rows per tile
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(kFastWarps * 32, 2)   // <= 128 registers: two
 ln_fwd_fast_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
                    const float* __restrict__ gamma, const float* __restrict__ gammax, T* __restrict__ y, int64_t ldy,
                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, float eps) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   constexpr int IT = D / (32 * V);
   constexpr int RW = 2;  // rows in flight per warp (memory-level parallelism)
@@ -336,6 +340,7 @@ __global__ void __launch_bounds__(kFastWarps * 32)
 ln_bwd_fast_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ x, int64_t ldx, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float* __restrict__ w, const T* __restrict__ dres, int64_t ldr,
                    T* __restrict__ dx, int64_t lddx, int M) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   constexpr int IT = D / (32 * V);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -393,14 +398,14 @@ int ln_fwd_fast(const ngu_ln_desc& d, cudaStream_t s) {
   const T* x = reinterpret_cast<const T*>(d.x);
   T* y = reinterpret_cast<T*>(d.y);
   if (d.gamma != nullptr)
-    ln_fwd_fast_kernel<T, D, true><<<fast_grid(d.M, 2), kFastWarps * 32, 0, s>>>(x, d.ldx, d.w, d.b, d.gamma, d.gammax, y, d.ldy, d.mean, d.rstd, d.M, d.eps);
+    launch_pdl(ln_fwd_fast_kernel<T, D, true>, dim3(fast_grid(d.M, 2)), dim3(kFastWarps * 32), size_t(0), s, x, d.ldx, d.w, d.b, d.gamma, d.gammax, y, d.ldy, d.mean, d.rstd, d.M, d.eps);
   else
-    ln_fwd_fast_kernel<T, D, false><<<fast_grid(d.M, 2), kFastWarps * 32, 0, s>>>(x, d.ldx, d.w, d.b, nullptr, nullptr, y, d.ldy, d.mean, d.rstd, d.M, d.eps);
+    launch_pdl(ln_fwd_fast_kernel<T, D, false>, dim3(fast_grid(d.M, 2)), dim3(kFastWarps * 32), size_t(0), s, x, d.ldx, d.w, d.b, nullptr, nullptr, y, d.ldy, d.mean, d.rstd, d.M, d.eps);
   return check_launch("ln_fwd");
 }
 template <typename T, int D>
 int ln_bwd_fast(const ngu_ln_bwd_desc& d, cudaStream_t s) {
-  ln_bwd_fast_kernel<T, D><<<fast_grid(d.M), kFastWarps * 32, 0, s>>>(
+  launch_pdl(ln_bwd_fast_kernel<T, D>, dim3(fast_grid(d.M)), dim3(kFastWarps * 32), size_t(0), s, 
       reinterpret_cast<const T*>(d.g), d.ldg, reinterpret_cast<const T*>(d.x), d.ldx, d.mean, d.rstd, d.w,
       reinterpret_cast<const T*>(d.dres), d.ldr, reinterpret_cast<T*>(d.dx), d.lddx, d.M);
   return check_launch("ln_bwd");
@@ -409,14 +414,14 @@ int ln_bwd_fast(const ngu_ln_bwd_desc& d, cudaStream_t s) {
 template <typename T>
 int ln_fwd_t(const ngu_ln_desc& d, cudaStream_t s) {
   const int grid = (d.M + kLnWarps - 1) / kLnWarps;
-  ln_fwd_kernel<T><<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const T*>(d.x), d.ldx, d.w, d.b, d.gamma, d.gammax,
+  launch_pdl(ln_fwd_kernel<T>, dim3(grid), dim3(kLnWarps * 32), size_t(0), s, reinterpret_cast<const T*>(d.x), d.ldx, d.w, d.b, d.gamma, d.gammax,
                                                    reinterpret_cast<T*>(d.y), d.ldy, d.mean, d.rstd, d.M, d.D, d.eps);
   return check_launch("ln_fwd");
 }
 template <typename T>
 int ln_bwd_t(const ngu_ln_bwd_desc& d, cudaStream_t s) {
   const int grid = (d.M + kLnWarps - 1) / kLnWarps;
-  ln_bwd_kernel<T><<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const T*>(d.g), d.ldg, reinterpret_cast<const T*>(d.x), d.ldx,
+  launch_pdl(ln_bwd_kernel<T>, dim3(grid), dim3(kLnWarps * 32), size_t(0), s, reinterpret_cast<const T*>(d.g), d.ldg, reinterpret_cast<const T*>(d.x), d.ldx,
                                                    d.mean, d.rstd, d.w, reinterpret_cast<const T*>(d.dres), d.ldr,
                                                    reinterpret_cast<T*>(d.dx), d.lddx, d.M, d.D);
   return check_launch("ln_bwd");
@@ -430,7 +435,7 @@ int mona_pre_bwd_t(const ngu_mona_pre_bwd_desc& d, cudaStream_t s) {
   const int ntiles = (d.M + R - 1) / R;
   int grid = sm_count() * (sizeof(T) == 2 ? 2 : 1);
   if (grid > ntiles) grid = ntiles;
-  mona_pre_bwd_kernel<T, D><<<grid, D / 2, smem, s>>>(
+  launch_pdl(mona_pre_bwd_kernel<T, D>, dim3(grid), dim3(D / 2), size_t(smem), s, 
       reinterpret_cast<const T*>(d.du), reinterpret_cast<const T*>(d.dy), reinterpret_cast<const T*>(d.x), d.mean, d.rstd,
       d.w, d.b, d.gamma, d.gammax, reinterpret_cast<T*>(d.dx), d.dw, d.db, d.dgamma, d.dgammax, d.dycol, d.M);
   return check_launch("mona_pre_bwd");

@@ -13,6 +13,7 @@ namespace {
 // 32-bit index math.
 template <typename T>
 __global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int R, int P) {
+  pdl_prologue();
   const unsigned G = R / P, K = 3 * P * P, R8 = R / 8;
   const unsigned total8 = unsigned(B) * 3u * unsigned(R) * R8;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += gridDim.x * blockDim.x) {
@@ -40,6 +41,7 @@ __global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ o
 // initialised it (zero) so the row is a legal K operand of the GEMM.
 template <typename T>
 __global__ void patchify_generic_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int R, int P, int Kp) {
+  pdl_prologue();
   const unsigned G = R / P;
   const unsigned total = unsigned(B) * 3u * unsigned(R) * unsigned(R);
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -56,6 +58,7 @@ __global__ void patchify_generic_kernel(const float* __restrict__ img, T* __rest
 template <typename T>
 __global__ void assemble_kernel(const T* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
                                 T* __restrict__ out, int B, int np, int D) {
+  pdl_prologue();
   // one 16-byte vector of a token row per thread; 32-bit index math (the scalar 64-bit div/mod version ran 8x off the
   // HBM roofline)
   constexpr int V = Vec<T>::N;
@@ -88,6 +91,7 @@ __global__ void assemble_kernel(const T* __restrict__ patch, const float* __rest
 template <typename T>
 __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
                              const float* __restrict__ type0, T* __restrict__ out, int B, int S, int D, int vocab) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   const int vpr = D / V;
   const unsigned total = unsigned(B) * unsigned(S) * unsigned(vpr);
@@ -112,6 +116,7 @@ __global__ void embed_kernel(const int64_t* __restrict__ ids, const float* __res
 // out (T) [cols, rows] or [rows, cols] <- in fp32 [rows, cols] * scale
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, int rows, int cols, int transpose, float scale) {
+  pdl_prologue();
   const size_t total = size_t(rows) * cols;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const int r = int(i / cols), c = int(i % cols);
@@ -124,6 +129,7 @@ __global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, i
 // table of casts in one launch: blockIdx.y = item, blockIdx.x strides over its elements
 template <typename T>
 __global__ void cast_batch_kernel(const ngu_cast_item* __restrict__ items) {
+  pdl_prologue();
   const ngu_cast_item it = items[blockIdx.y];
   const unsigned total = unsigned(it.rows) * unsigned(it.cols);
   T* out = reinterpret_cast<T*>(it.out);
@@ -140,6 +146,7 @@ constexpr int WT = 64, WK = 16;
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(const T* __restrict__ X, int ldx, const T* __restrict__ Y, int ldy,
                                                          float* __restrict__ D, int ldd, int Tn, int Mo, int No, int tchunk) {
+  pdl_prologue();
   __shared__ float sX[WK][WT + 1];
   __shared__ float sY[WK][WT + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -179,6 +186,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const T* __restrict__ X
 // each warp walks rows with 16-byte loads, cross-warp reduce in smem, one atomic per column per CTA.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, int ldx, float* __restrict__ out, int Tn, int Cn, int tchunk) {
+  pdl_prologue();
   constexpr int V = Vec<T>::N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = (blockIdx.x * 32 + lane) * V;
@@ -215,7 +223,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, in
 
 // out = (accumulate ? out : 0) + x * mask(seed, i) / (1-p)   (LoRA input dropout, src/adapters/lora.py:82-83)
 template <typename T>
-__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ out, size_t n, float p, uint64_t seed, int accumulate) {
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ out, size_t n, float p, uint64_t seed, int accumulate,
+                               const uint64_t* seed_ctr) {
+  pdl_prologue();
+  seed = mix_seed(seed, seed_ctr);
   // one 16-byte vector per thread and iteration, one hash per four elements
   constexpr int V = Vec<T>::N;
   const uint32_t thr = dropout_threshold(p);
@@ -243,6 +254,23 @@ __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ out, siz
   }
 }
 
+// Key-padding lengths of a right-padded token batch (open_clip HFTextEncoder.forward: attn_mask = (x != pad_token_id)):
+// one warp per sequence; flag |= 1 when the valid tokens are not a non-empty prefix (the attention kernels only take lengths).
+__global__ void kv_len_kernel(const int64_t* __restrict__ ids, int64_t pad, int* __restrict__ out, int* __restrict__ flag, int B, int S) {
+  pdl_prologue();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  int cnt = 0, last = -1;
+  for (int j = lane; j < S; j += 32)
+    if (ids[size_t(row) * S + j] != pad) { ++cnt; last = j; }
+  cnt = warp_sum(cnt);
+  last = warp_max(last);
+  if (lane == 0) {
+    out[row] = cnt < 1 ? 1 : cnt;
+    if (cnt < 1 || last != cnt - 1) atomicOr(flag, 1);
+  }
+}
+
 int grid_for(size_t total) {
   size_t g = (total + 255) / 256;
   const size_t cap = size_t(sm_count()) * 16;
@@ -258,21 +286,21 @@ int patchify(const float* img, void* out, int B, int R, int P, int dtype, cudaSt
   if (P % 8 || R % P) {
     const int Kp = (3 * P * P + 7) & ~7;
     const size_t tot = size_t(B) * 3 * R * R;
-    if (dtype == NGU_F32) patchify_generic_kernel<float><<<grid_for(tot), 256, 0, st>>>(img, reinterpret_cast<float*>(out), B, R, P, Kp);
-    else patchify_generic_kernel<bf16><<<grid_for(tot), 256, 0, st>>>(img, reinterpret_cast<bf16*>(out), B, R, P, Kp);
+    if (dtype == NGU_F32) launch_pdl(patchify_generic_kernel<float>, dim3(grid_for(tot)), dim3(256), size_t(0), st, img, reinterpret_cast<float*>(out), B, R, P, Kp);
+    else launch_pdl(patchify_generic_kernel<bf16>, dim3(grid_for(tot)), dim3(256), size_t(0), st, img, reinterpret_cast<bf16*>(out), B, R, P, Kp);
     return check_launch("patchify");
   }
   const size_t total = size_t(B) * 3 * R * R / 8;
-  if (dtype == NGU_F32) patchify_kernel<float><<<grid_for(total), 256, 0, st>>>(img, reinterpret_cast<float*>(out), B, R, P);
-  else patchify_kernel<bf16><<<grid_for(total), 256, 0, st>>>(img, reinterpret_cast<bf16*>(out), B, R, P);
+  if (dtype == NGU_F32) launch_pdl(patchify_kernel<float>, dim3(grid_for(total)), dim3(256), size_t(0), st, img, reinterpret_cast<float*>(out), B, R, P);
+  else launch_pdl(patchify_kernel<bf16>, dim3(grid_for(total)), dim3(256), size_t(0), st, img, reinterpret_cast<bf16*>(out), B, R, P);
   return check_launch("patchify");
 }
 int assemble_tokens(const void* patch, const float* cls, const float* pos, void* out, int B, int np, int D, int dtype, cudaStream_t st) {
   if (B <= 0 || np <= 0 || D <= 0) { set_last_error("assemble_tokens: empty"); return NGU_ERR_SHAPE; }
   if (D % 8) { set_last_error("assemble_tokens: D must be a multiple of 8"); return NGU_ERR_SHAPE; }
   const size_t total = size_t(B) * (np + 1) * D / (dtype == NGU_F32 ? 4 : 8);
-  if (dtype == NGU_F32) assemble_kernel<float><<<grid_for(total), 256, 0, st>>>(reinterpret_cast<const float*>(patch), cls, pos, reinterpret_cast<float*>(out), B, np, D);
-  else assemble_kernel<bf16><<<grid_for(total), 256, 0, st>>>(reinterpret_cast<const bf16*>(patch), cls, pos, reinterpret_cast<bf16*>(out), B, np, D);
+  if (dtype == NGU_F32) launch_pdl(assemble_kernel<float>, dim3(grid_for(total)), dim3(256), size_t(0), st, reinterpret_cast<const float*>(patch), cls, pos, reinterpret_cast<float*>(out), B, np, D);
+  else launch_pdl(assemble_kernel<bf16>, dim3(grid_for(total)), dim3(256), size_t(0), st, reinterpret_cast<const bf16*>(patch), cls, pos, reinterpret_cast<bf16*>(out), B, np, D);
   return check_launch("assemble_tokens");
 }
 int embed_tokens(const int64_t* ids, const float* word, const float* pos, const float* type0, void* out, int B, int S, int D,
@@ -280,30 +308,30 @@ int embed_tokens(const int64_t* ids, const float* word, const float* pos, const 
   if (B <= 0 || S <= 0 || D <= 0 || vocab <= 0) { set_last_error("embed_tokens: empty"); return NGU_ERR_SHAPE; }
   if (D % 8) { set_last_error("embed_tokens: D must be a multiple of 8"); return NGU_ERR_SHAPE; }
   const size_t total = size_t(B) * S * D / (dtype == NGU_F32 ? 4 : 8);
-  if (dtype == NGU_F32) embed_kernel<float><<<grid_for(total), 256, 0, st>>>(ids, word, pos, type0, reinterpret_cast<float*>(out), B, S, D, vocab);
-  else embed_kernel<bf16><<<grid_for(total), 256, 0, st>>>(ids, word, pos, type0, reinterpret_cast<bf16*>(out), B, S, D, vocab);
+  if (dtype == NGU_F32) launch_pdl(embed_kernel<float>, dim3(grid_for(total)), dim3(256), size_t(0), st, ids, word, pos, type0, reinterpret_cast<float*>(out), B, S, D, vocab);
+  else launch_pdl(embed_kernel<bf16>, dim3(grid_for(total)), dim3(256), size_t(0), st, ids, word, pos, type0, reinterpret_cast<bf16*>(out), B, S, D, vocab);
   return check_launch("embed_tokens");
 }
 int cast_f32(const float* in, void* out, int rows, int cols, int transpose, float scale, int dtype, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) { set_last_error("cast: empty"); return NGU_ERR_SHAPE; }
   const size_t total = size_t(rows) * cols;
-  if (dtype == NGU_F32) cast_kernel<float><<<grid_for(total), 256, 0, st>>>(in, reinterpret_cast<float*>(out), rows, cols, transpose, scale);
-  else cast_kernel<bf16><<<grid_for(total), 256, 0, st>>>(in, reinterpret_cast<bf16*>(out), rows, cols, transpose, scale);
+  if (dtype == NGU_F32) launch_pdl(cast_kernel<float>, dim3(grid_for(total)), dim3(256), size_t(0), st, in, reinterpret_cast<float*>(out), rows, cols, transpose, scale);
+  else launch_pdl(cast_kernel<bf16>, dim3(grid_for(total)), dim3(256), size_t(0), st, in, reinterpret_cast<bf16*>(out), rows, cols, transpose, scale);
   return check_launch("cast");
 }
 int cast_f32_batch(const ngu_cast_item* items, int n, int dtype, cudaStream_t st) {
   if (n <= 0 || items == nullptr) { set_last_error("cast_batch: empty table"); return NGU_ERR_SHAPE; }
   if (n > 65535) { set_last_error("cast_batch: at most 65535 items per launch"); return NGU_ERR_ARG; }
   const dim3 grid(48, n);
-  if (dtype == NGU_F32) cast_batch_kernel<float><<<grid, 256, 0, st>>>(items);
-  else cast_batch_kernel<bf16><<<grid, 256, 0, st>>>(items);
+  if (dtype == NGU_F32) launch_pdl(cast_batch_kernel<float>, dim3(grid), dim3(256), size_t(0), st, items);
+  else launch_pdl(cast_batch_kernel<bf16>, dim3(grid), dim3(256), size_t(0), st, items);
   return check_launch("cast_batch");
 }
 int dropout(const void* x, void* out, size_t n, float p, uint64_t seed, int accumulate, int dtype, cudaStream_t st) {
   if (n == 0 || p < 0.f || p >= 1.f) { set_last_error("dropout: bad n/p"); return NGU_ERR_ARG; }
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15u) { set_last_error("dropout: pointers must be 16-byte aligned"); return NGU_ERR_ALIGN; }
-  if (dtype == NGU_F32) dropout_kernel<float><<<grid_for(n / 4 + 1), 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(out), n, p, seed, accumulate);
-  else dropout_kernel<bf16><<<grid_for(n / 8 + 1), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out), n, p, seed, accumulate);
+  if (dtype == NGU_F32) launch_pdl(dropout_kernel<float>, dim3(grid_for(n / 4 + 1)), dim3(256), size_t(0), st, reinterpret_cast<const float*>(x), reinterpret_cast<float*>(out), n, p, seed, accumulate, seed_counter());
+  else launch_pdl(dropout_kernel<bf16>, dim3(grid_for(n / 8 + 1)), dim3(256), size_t(0), st, reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out), n, p, seed, accumulate, seed_counter());
   return check_launch("dropout");
 }
 int wgrad_simt(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int Tn, int Mo, int No, int dtype, cudaStream_t st) {
@@ -314,8 +342,8 @@ int wgrad_simt(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd
   tchunk = (tchunk + WK - 1) / WK * WK;
   splits = (Tn + tchunk - 1) / tchunk;
   dim3 grid((No + WT - 1) / WT, (Mo + WT - 1) / WT, splits);
-  if (dtype == NGU_F32) wgrad_simt_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(X), ldx, reinterpret_cast<const float*>(Y), ldy, D, ldd, Tn, Mo, No, tchunk);
-  else wgrad_simt_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(X), ldx, reinterpret_cast<const bf16*>(Y), ldy, D, ldd, Tn, Mo, No, tchunk);
+  if (dtype == NGU_F32) launch_pdl(wgrad_simt_kernel<float>, dim3(grid), dim3(256), size_t(0), st, reinterpret_cast<const float*>(X), ldx, reinterpret_cast<const float*>(Y), ldy, D, ldd, Tn, Mo, No, tchunk);
+  else launch_pdl(wgrad_simt_kernel<bf16>, dim3(grid), dim3(256), size_t(0), st, reinterpret_cast<const bf16*>(X), ldx, reinterpret_cast<const bf16*>(Y), ldy, D, ldd, Tn, Mo, No, tchunk);
   return check_launch("wgrad_simt");
 }
 int colsum(const void* X, int ldx, float* out, int Tn, int Cn, int dtype, cudaStream_t st) {
@@ -329,9 +357,15 @@ int colsum(const void* X, int ldx, float* out, int Tn, int Cn, int dtype, cudaSt
   if (splits < 1) splits = 1;
   const int tchunk = (Tn + splits - 1) / splits;
   dim3 grid(gx, (Tn + tchunk - 1) / tchunk);
-  if (dtype == NGU_F32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(X), ldx, out, Tn, Cn, tchunk);
-  else colsum_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(X), ldx, out, Tn, Cn, tchunk);
+  if (dtype == NGU_F32) launch_pdl(colsum_kernel<float>, dim3(grid), dim3(256), size_t(0), st, reinterpret_cast<const float*>(X), ldx, out, Tn, Cn, tchunk);
+  else launch_pdl(colsum_kernel<bf16>, dim3(grid), dim3(256), size_t(0), st, reinterpret_cast<const bf16*>(X), ldx, out, Tn, Cn, tchunk);
   return check_launch("colsum");
+}
+
+int kv_len(const int64_t* ids, int64_t pad, int* out, int* flag, int B, int S, cudaStream_t st) {
+  if (B <= 0 || S <= 0 || !ids || !out || !flag) { set_last_error("kv_len: bad arguments"); return NGU_ERR_ARG; }
+  launch_pdl(kv_len_kernel, dim3((B + 3) / 4), dim3(128), size_t(0), st, ids, pad, out, flag, B, S);
+  return check_launch("kv_len");
 }
 
 }  // namespace ngu

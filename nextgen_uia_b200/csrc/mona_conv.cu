@@ -11,11 +11,20 @@
 // warp reads 32 consecutive channels of one token (coalesced, bank-conflict free in smem).
 #include "common.cuh"
 #include "kernels.h"
+#include "mona_stage.cuh"
 
 namespace ngu {
+#ifdef NGU_CONV_PROF
+// debug build only: per-phase clock64() stamps of CTA 0 (tools/gpu_conv_phases.py)
+__device__ long long g_conv_prof[32];
+#define NGU_PROF(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_conv_prof[i] = clock64(); } while (0)
+#else
+#define NGU_PROF(i) do { } while (0)
+#endif
 namespace {
 
-constexpr int C = 64;        // bottleneck channels (reference default --mona_bottleneck 64)
+using mona_stage::C;           // bottleneck channels (reference default --mona_bottleneck 64)
+using namespace mona_stage;
 constexpr int kThreads = 256;
 constexpr int kChunk = 32;   // tokens per projector chunk
 
@@ -86,7 +95,9 @@ NGU_DEVINL float proj_out(const ConvSmem& s, int lp, int o) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 mona_conv_fwd_kernel(const T* __restrict__ h, T* __restrict__ g, ngu_mona_conv_weights w, int N, int H, int W,
-                     int has_cls, float drop_p, uint64_t seed) {
+                     int has_cls, float drop_p, uint64_t seed, const uint64_t* seed_ctr) {
+  pdl_prologue();
+  seed = mix_seed(seed, seed_ctr);
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   ConvSmem& s = *reinterpret_cast<ConvSmem*>(smem_dyn);
   T* hs = reinterpret_cast<T*>(smem_dyn + sizeof(ConvSmem));
@@ -128,7 +139,9 @@ mona_conv_fwd_kernel(const T* __restrict__ h, T* __restrict__ g, ngu_mona_conv_w
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 mona_conv_bwd_kernel(const T* __restrict__ h, const T* __restrict__ dg, T* __restrict__ dh, ngu_mona_conv_weights w,
-                     ngu_mona_conv_grads gr, int N, int H, int W, int has_cls, float drop_p, uint64_t seed) {
+                     ngu_mona_conv_grads gr, int N, int H, int W, int has_cls, float drop_p, uint64_t seed, const uint64_t* seed_ctr) {
+  pdl_prologue();
+  seed = mix_seed(seed, seed_ctr);
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   ConvSmem& s = *reinterpret_cast<ConvSmem*>(smem_dyn);
   const int HW = H * W;
@@ -374,7 +387,9 @@ NGU_DEVINL float proj_token(const T* zrow, const float (&pcol)[C], float bp, int
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
 mona_conv_fwd_fast_kernel(const T* __restrict__ h, T* __restrict__ g, ngu_mona_conv_weights w, int N, int H, int W,
-                          int has_cls, float drop_p, uint64_t seed) {
+                          int has_cls, float drop_p, uint64_t seed, const uint64_t* seed_ctr) {
+  pdl_prologue();
+  seed = mix_seed(seed, seed_ctr);
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   FastSmem& s = *reinterpret_cast<FastSmem*>(smem_dyn);
   const int HW = H * W;
@@ -424,7 +439,9 @@ mona_conv_fwd_fast_kernel(const T* __restrict__ h, T* __restrict__ g, ngu_mona_c
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
 mona_conv_bwd_fast_kernel(const T* __restrict__ h, const T* __restrict__ dg, T* __restrict__ dh, ngu_mona_conv_weights w,
-                          ngu_mona_conv_grads gr, int N, int H, int W, int has_cls, float drop_p, uint64_t seed) {
+                          ngu_mona_conv_grads gr, int N, int H, int W, int has_cls, float drop_p, uint64_t seed, const uint64_t* seed_ctr) {
+  pdl_prologue();
+  seed = mix_seed(seed, seed_ctr);
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   FastSmem& s = *reinterpret_cast<FastSmem*>(smem_dyn);
   const int HW = H * W;
@@ -660,19 +677,6 @@ mona_conv_bwd_fast_kernel(const T* __restrict__ h, const T* __restrict__ dg, T* 
 // Tiles hs / zs / das are [HWp][64] bf16 with HWp = HW rounded up to 16 (pad rows zero); element (p, c) lives at
 // p*64 + (((c >> 3) ^ (p & 7)) << 3) + (c & 7)   (16-byte chunks XOR-swizzled by the row, so ldmatrix is conflict free).
 // =====================================================================================================
-NGU_DEVINL int swz(int p, int c) { return p * C + ((((c >> 3) ^ (p & 7))) << 3) + (c & 7); }
-NGU_DEVINL uint32_t tile_addr(uint32_t base, int row, int chunk) { return base + uint32_t(row) * 128u + (uint32_t((chunk ^ (row & 7))) << 4); }
-NGU_DEVINL void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-NGU_DEVINL void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-NGU_DEVINL void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 struct TcSmem {
   float kc[49][C];
   float bc[C];
@@ -685,29 +689,6 @@ struct TcSmem {
   float dwbr[4];
   float dgap[C];
 };
-
-// acc[nt][.] (16 rows x 64 cols) = A[rt*16 .. +16][0..64) * Bm, A from a swizzled tile; Bm(k, n) = Pb[n][k] (TRANS_B = false,
-// i.e. A P^T) or Pb[k][n] (TRANS_B = true, i.e. A P), Pb = projector weight [o][i] as a swizzled bf16 tile.
-template <bool TRANS_B>
-NGU_DEVINL void proj_mma(float (&acc)[8][4], uint32_t tileA, int rt, uint32_t pb, int lane) {
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    uint32_t a[4];
-    ldsm_x4(a, tile_addr(tileA, rt * 16 + (lane & 15), kk * 2 + (lane >> 4)));
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      uint32_t b[4];
-      if (!TRANS_B) ldsm_x4(b, tile_addr(pb, (2 * np + (lane >> 4)) * 8 + (lane & 7), kk * 2 + ((lane >> 3) & 1)));
-      else ldsm_x4_t(b, tile_addr(pb, kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), 2 * np + (lane >> 4)));
-      mma16816(acc[2 * np], a, b[0], b[1]);
-      mma16816(acc[2 * np + 1], a, b[2], b[3]);
-    }
-  }
-}
 
 // image tile, projector (bf16, swizzled), variant prologue, effective stencil.  Ends with __syncthreads().
 NGU_DEVINL void tc_load_common(TcSmem& s, bf16* hs, bf16* pbs, const bf16* hb, const ngu_mona_conv_weights& w, int HW, int HWp, int has_cls) {
@@ -769,50 +750,6 @@ NGU_DEVINL void tc_load_common(TcSmem& s, bf16* hs, bf16* pbs, const bf16* hb, c
   __syncthreads();
 }
 
-// Streaming depthwise stencil on a LINEAR bf16 tile [HW][C]: one thread owns channel c and a 4-wide column strip and
-// walks the rows once, keeping the 7 output rows that the current input row touches in a rolling register window
-// (10 loads per 196 FMAs instead of 13 per 49).  emit(y, acc[4]) receives each finished output row.
-//   FLIP = false: out[y][x] = bias + sum k[ky][kx]   in[y+ky-3][x+kx-3]
-//   FLIP = true : out[y][x] = bias + sum k[ky][kx]   in[y-(ky-3)][x-(kx-3)]     (transposed stencil)
-constexpr int kSW = 4;  // strip width
-template <bool FLIP, typename Emit>
-NGU_DEVINL void stencil_stream(const bf16* in, const float (&k)[49], float bias, int x0, int H, int W, int c, Emit emit) {
-  float acc[7][kSW];
-#pragma unroll
-  for (int s_ = 0; s_ < 7; ++s_)
-#pragma unroll
-    for (int j = 0; j < kSW; ++j) acc[s_][j] = bias;
-  for (int yy = 0; yy < H + 3; ++yy) {
-    if (yy < H) {
-      float win[kSW + 6];
-      const bf16* rowp = in + (yy * W) * C + c;
-#pragma unroll
-      for (int i = 0; i < kSW + 6; ++i) {
-        const int xx = x0 + i - 3;
-        win[i] = (unsigned(xx) < unsigned(W)) ? __bfloat162float(rowp[xx * C]) : 0.f;
-      }
-#pragma unroll
-      for (int s_ = 0; s_ < 7; ++s_) {
-        const int ky = FLIP ? s_ : 6 - s_;   // slot s_ <-> output row yy - 3 + s_
-#pragma unroll
-        for (int kx = 0; kx < 7; ++kx) {
-          const float kv = k[ky * 7 + (FLIP ? 6 - kx : kx)];
-#pragma unroll
-          for (int j = 0; j < kSW; ++j) acc[s_][j] = fmaf(kv, win[j + kx], acc[s_][j]);
-        }
-      }
-    }
-    const int yo = yy - 3;
-    if (yo >= 0) emit(yo, acc[0]);
-#pragma unroll
-    for (int s_ = 0; s_ < 6; ++s_)
-#pragma unroll
-      for (int j = 0; j < kSW; ++j) acc[s_][j] = acc[s_ + 1][j];
-#pragma unroll
-    for (int j = 0; j < kSW; ++j) acc[6][j] = bias;
-  }
-}
-
 // z = stencil(h): h linear, z written into the swizzled tile (ldmatrix operand of the projector MMAs)
 NGU_DEVINL void conv_phase_stream(const TcSmem& s, const bf16* hs, bf16* zs, int H, int W, int c, int grp) {
   float k[49];
@@ -829,7 +766,9 @@ NGU_DEVINL void conv_phase_stream(const TcSmem& s, const bf16* hs, bf16* zs, int
 
 __global__ void __launch_bounds__(kThreads, 2)
 mona_conv_fwd_tc_kernel(const bf16* __restrict__ h, bf16* __restrict__ g, ngu_mona_conv_weights w, int N, int H, int W,
-                        int has_cls, float drop_p, uint64_t seed) {
+                        int has_cls, float drop_p, uint64_t seed, const uint64_t* seed_ctr) {
+  pdl_prologue();
+  seed = mix_seed(seed, seed_ctr);
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(smem_dyn);
   const int HW = H * W, HWp = (HW + 15) & ~15;
@@ -842,7 +781,9 @@ mona_conv_fwd_tc_kernel(const bf16* __restrict__ h, bf16* __restrict__ g, ngu_mo
   const int c = threadIdx.x & (C - 1), grp = threadIdx.x >> 6;
   for (int i = threadIdx.x; i < (HWp - HW) * 8; i += kThreads)  // zero the pad rows of z
     *reinterpret_cast<uint4*>(zs + (HW + (i >> 3)) * C + ((i & 7) << 3)) = make_uint4(0, 0, 0, 0);
+  NGU_PROF(16);
   tc_load_common(s, hs, pbs, hb, w, HW, HWp, has_cls);
+  NGU_PROF(17);
   if (has_cls && grp == 0) {
     float v = gelu_erf(__bfloat162float(hb[c]));
     if (drop_p > 0.f) v *= dropout_scale(seed, (uint64_t(img) * N) * C + c, drop_p);
@@ -850,6 +791,7 @@ mona_conv_fwd_tc_kernel(const bf16* __restrict__ h, bf16* __restrict__ g, ngu_mo
   }
   conv_phase_stream(s, hs, zs, H, W, c, grp);
   __syncthreads();
+  NGU_PROF(18);
   // a = z + bp + z P^T  ->  g = dropout(gelu(a))
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
   const uint32_t zs_u = smem_u32(zs), pb_u = smem_u32(pbs);
@@ -874,11 +816,14 @@ mona_conv_fwd_tc_kernel(const bf16* __restrict__ h, bf16* __restrict__ g, ngu_mo
         }
       }
   }
+  NGU_PROF(19);
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
 mona_conv_bwd_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dg, bf16* __restrict__ dh, ngu_mona_conv_weights w,
-                        ngu_mona_conv_grads gr, int N, int H, int W, int has_cls, float drop_p, uint64_t seed) {
+                        ngu_mona_conv_grads gr, int N, int H, int W, int has_cls, float drop_p, uint64_t seed, const uint64_t* seed_ctr) {
+  pdl_prologue();
+  seed = mix_seed(seed, seed_ctr);
   extern __shared__ __align__(128) uint8_t smem_dyn[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(smem_dyn);
   const int HW = H * W, HWp = (HW + 15) & ~15;
@@ -896,7 +841,9 @@ mona_conv_bwd_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dg,
     *reinterpret_cast<uint4*>(zs + (HW + (i >> 3)) * C + ((i & 7) << 3)) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(das + (HW + (i >> 3)) * C + ((i & 7) << 3)) = make_uint4(0, 0, 0, 0);
   }
+  NGU_PROF(0);
   tc_load_common(s, hs, pbs, hb, w, HW, HWp, has_cls);
+  NGU_PROF(1);
   float db1_acc = 0.f;
   if (has_cls && grp == 0) {
     float v = __bfloat162float(dgb[c]) * gelu_erf_grad(__bfloat162float(hb[c]));
@@ -907,6 +854,7 @@ mona_conv_bwd_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dg,
   // ---- phase 1: z = stencil(h)
   conv_phase_stream(s, hs, zs, H, W, c, grp);
   __syncthreads();
+  NGU_PROF(2);
   const uint32_t zs_u = smem_u32(zs), da_u = smem_u32(das), pb_u = smem_u32(pbs);
   // ---- phase 2: da = dg * mask * gelu'(z + bp + z P^T)
   for (int rt = warp; rt < HWp / 16; rt += kThreads / 32) {
@@ -933,6 +881,7 @@ mona_conv_bwd_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dg,
       }
   }
   __syncthreads();
+  NGU_PROF(3);
   // ---- phase 3: dP[o][i] += sum_p da[p][o] z[p][i]  (A = da^T, B = z, both read transposed from k-major tiles);  dbp
   {
     const int mt = warp & 3, nh = warp >> 2;
@@ -966,6 +915,7 @@ mona_conv_bwd_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dg,
     atomicAdd(gr.dbp + c, a);
   }
   __syncthreads();
+  NGU_PROF(4);
   // ---- phase 4: dz = da + da P   (overwrites z)
   for (int rt = warp; rt < HWp / 16; rt += kThreads / 32) {
     float acc[8][4];
@@ -981,6 +931,7 @@ mona_conv_bwd_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dg,
       }
   }
   __syncthreads();
+  NGU_PROF(5);
   // ---- phase 5: correlation sums G[t][c] = sum_p dz[p][c] h[p + off_t][c], S[c] = sum_p dz[p][c]
   //      streamed over the rows of h with the 7 dz rows it pairs with held in a rolling register window
   float* Gs = reinterpret_cast<float*>(das);
@@ -1033,6 +984,7 @@ mona_conv_bwd_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dg,
     atomicAdd(&Ss[c], dsum);
   }
   __syncthreads();
+  NGU_PROF(6);
   // ---- phase 6: stencil / bias / frequency / branch-weight gradients from G and S (same as the generic fast kernel)
   const float w1 = s.wbr[0], w2 = s.wbr[1], w3 = s.wbr[2];
   if (threadIdx.x < C) {
@@ -1103,6 +1055,7 @@ mona_conv_bwd_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dg,
     if (threadIdx.x < C && gr.dfreq && w.freq) atomicAdd(gr.dfreq + c, s.part[1][c]);
   }
   // ---- phase 7: dh = transposed effective stencil of dz (+ pooled-path constant)
+  NGU_PROF(7);
   {
     float k[49];
 #pragma unroll
@@ -1116,6 +1069,7 @@ mona_conv_bwd_tc_kernel(const bf16* __restrict__ h, const bf16* __restrict__ dg,
     }
   }
   atomicAdd(gr.db1 + c, db1_acc);
+  NGU_PROF(8);
 }
 
 size_t tc_smem_bytes(int HW, bool bwd) {
@@ -1150,24 +1104,24 @@ int launch_fwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
     const int smf = int(tc_smem_bytes(d.H * d.W, false));
     cudaError_t e = cudaFuncSetAttribute(mona_conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
     if (e != cudaSuccess) return cuda_status(e, "mona_conv_fwd attr");
-    mona_conv_fwd_tc_kernel<<<d.B, kThreads, smf, st>>>(reinterpret_cast<const bf16*>(d.h), reinterpret_cast<bf16*>(d.g), d.w, d.N, d.H, d.W,
-                                                          d.has_cls, d.drop_p, d.seed);
+    launch_pdl(mona_conv_fwd_tc_kernel, dim3(d.B), dim3(kThreads), size_t(smf), st, reinterpret_cast<const bf16*>(d.h), reinterpret_cast<bf16*>(d.g), d.w, d.N, d.H, d.W,
+                                                          d.has_cls, d.drop_p, d.seed, seed_counter());
     return check_launch("mona_conv_fwd");
   }
   if (fast_ok<T>(d, false)) {
     const int smf = int(fast_smem_bytes<T>(d.H * d.W, false));
     cudaError_t e = cudaFuncSetAttribute(mona_conv_fwd_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
     if (e != cudaSuccess) return cuda_status(e, "mona_conv_fwd attr");
-    mona_conv_fwd_fast_kernel<T><<<d.B, kThreads, smf, st>>>(reinterpret_cast<const T*>(d.h), reinterpret_cast<T*>(d.g), d.w, d.N, d.H,
-                                                              d.W, d.has_cls, d.drop_p, d.seed);
+    launch_pdl(mona_conv_fwd_fast_kernel<T>, dim3(d.B), dim3(kThreads), size_t(smf), st, reinterpret_cast<const T*>(d.h), reinterpret_cast<T*>(d.g), d.w, d.N, d.H,
+                                                              d.W, d.has_cls, d.drop_p, d.seed, seed_counter());
     return check_launch("mona_conv_fwd");
   }
   const int smem = conv_smem_bytes<T>(d.H * d.W, false);
   if (smem > 227 * 1024) { set_last_error("mona_conv_fwd: %dx%d grid needs %d B smem", d.H, d.W, smem); return NGU_ERR_SHAPE; }
   cudaError_t e = cudaFuncSetAttribute(mona_conv_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return cuda_status(e, "mona_conv_fwd attr");
-  mona_conv_fwd_kernel<T><<<d.B, kThreads, smem, st>>>(reinterpret_cast<const T*>(d.h), reinterpret_cast<T*>(d.g), d.w, d.N, d.H,
-                                                        d.W, d.has_cls, d.drop_p, d.seed);
+  launch_pdl(mona_conv_fwd_kernel<T>, dim3(d.B), dim3(kThreads), size_t(smem), st, reinterpret_cast<const T*>(d.h), reinterpret_cast<T*>(d.g), d.w, d.N, d.H,
+                                                        d.W, d.has_cls, d.drop_p, d.seed, seed_counter());
   return check_launch("mona_conv_fwd");
 }
 template <typename T>
@@ -1176,26 +1130,26 @@ int launch_bwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
     const int smf = int(tc_smem_bytes(d.H * d.W, true));
     cudaError_t e = cudaFuncSetAttribute(mona_conv_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
     if (e != cudaSuccess) return cuda_status(e, "mona_conv_bwd attr");
-    mona_conv_bwd_tc_kernel<<<d.B, kThreads, smf, st>>>(reinterpret_cast<const bf16*>(d.h), reinterpret_cast<const bf16*>(d.dg),
-                                                          reinterpret_cast<bf16*>(d.dh), d.w, d.gr, d.N, d.H, d.W, d.has_cls, d.drop_p, d.seed);
+    launch_pdl(mona_conv_bwd_tc_kernel, dim3(d.B), dim3(kThreads), size_t(smf), st, reinterpret_cast<const bf16*>(d.h), reinterpret_cast<const bf16*>(d.dg),
+                                                          reinterpret_cast<bf16*>(d.dh), d.w, d.gr, d.N, d.H, d.W, d.has_cls, d.drop_p, d.seed, seed_counter());
     return check_launch("mona_conv_bwd");
   }
   if (fast_ok<T>(d, true)) {
     const int smf = int(fast_smem_bytes<T>(d.H * d.W, true));
     cudaError_t e = cudaFuncSetAttribute(mona_conv_bwd_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smf);
     if (e != cudaSuccess) return cuda_status(e, "mona_conv_bwd attr");
-    mona_conv_bwd_fast_kernel<T><<<d.B, kThreads, smf, st>>>(reinterpret_cast<const T*>(d.h), reinterpret_cast<const T*>(d.dg),
+    launch_pdl(mona_conv_bwd_fast_kernel<T>, dim3(d.B), dim3(kThreads), size_t(smf), st, reinterpret_cast<const T*>(d.h), reinterpret_cast<const T*>(d.dg),
                                                               reinterpret_cast<T*>(d.dh), d.w, d.gr, d.N, d.H, d.W, d.has_cls,
-                                                              d.drop_p, d.seed);
+                                                              d.drop_p, d.seed, seed_counter());
     return check_launch("mona_conv_bwd");
   }
   const int smem = conv_smem_bytes<T>(d.H * d.W, true);
   if (smem > 227 * 1024) { set_last_error("mona_conv_bwd: %dx%d grid needs %d B smem", d.H, d.W, smem); return NGU_ERR_SHAPE; }
   cudaError_t e = cudaFuncSetAttribute(mona_conv_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return cuda_status(e, "mona_conv_bwd attr");
-  mona_conv_bwd_kernel<T><<<d.B, kThreads, smem, st>>>(reinterpret_cast<const T*>(d.h), reinterpret_cast<const T*>(d.dg),
+  launch_pdl(mona_conv_bwd_kernel<T>, dim3(d.B), dim3(kThreads), size_t(smem), st, reinterpret_cast<const T*>(d.h), reinterpret_cast<const T*>(d.dg),
                                                         reinterpret_cast<T*>(d.dh), d.w, d.gr, d.N, d.H, d.W, d.has_cls,
-                                                        d.drop_p, d.seed);
+                                                        d.drop_p, d.seed, seed_counter());
   return check_launch("mona_conv_bwd");
 }
 
@@ -1234,4 +1188,7 @@ int mona_conv_bwd(const ngu_mona_conv_desc& d, cudaStream_t st) {
   return d.dtype == NGU_F32 ? launch_bwd<float>(d, st) : launch_bwd<bf16>(d, st);
 }
 
+#ifdef NGU_CONV_PROF
+extern "C" int ngu_debug_conv_prof(long long* out) { return cudaMemcpyFromSymbol(out, g_conv_prof, sizeof(g_conv_prof)) == cudaSuccess ? 0 : -4; }
+#endif
 }  // namespace ngu

@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <atomic>
 #include "common.cuh"
 #include "kernels.h"
@@ -112,6 +113,16 @@ int sm_count() {
   }
   return n;
 }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NGU_PDL"); v = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+  return v == 1;
+}
+
+static const uint64_t* g_seed_ctr = nullptr;
+const uint64_t* seed_counter() { return g_seed_ctr; }
+void set_seed_counter(const uint64_t* p) { g_seed_ctr = p; }
 
 const char* last_error();
 int64_t launch_count();

@@ -14,12 +14,16 @@ namespace ngu {
 namespace {
 
 constexpr int KB = 64;                 // tokens per pipeline stage
-constexpr int kMaxG = 6;               // M tiles (of 128) per CTA
 constexpr int kBoxBytes = KB * 128;    // 64 token rows x 64 bf16
-constexpr int kStageBytes = (2 * kMaxG + 1) * kBoxBytes;  // 12 X boxes + 1 Y box = 104 KB
 constexpr int kStages = 2;
 constexpr int kThreads = 32 * 6;
-constexpr int kSmem = kStages * kStageBytes + 1024 + 1024;
+// NB = number of 64-column boxes of Y (No = 64 * NB): NB = 1 -> up to 6 M tiles per CTA (6 x 64 TMEM columns),
+// NB = 2 -> up to 3 (3 x 128): Mona's G = x^T [dh | dh*rstd].
+template <int NB> struct WgCfg {
+  static constexpr int kMaxG = NB == 1 ? 6 : 3;
+  static constexpr int kStageBytes = (2 * kMaxG + NB) * kBoxBytes;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 + 1024;
+};
 
 struct WgradParams {
   CUtensorMap tmX, tmY;  // boxes 64 cols x 64 rows, SWIZZLE_128B
@@ -27,7 +31,11 @@ struct WgradParams {
   int ldd, T, Mo, G, splits, kb_per_split;
 };
 
+template <int NB>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  pdl_prologue();
+  constexpr int kMaxG = WgCfg<NB>::kMaxG;
+  constexpr int kStageBytes = WgCfg<NB>::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sBar = base + kStages * kStageBytes;
@@ -66,18 +74,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t st = base + s * kStageBytes;
         if (elect_one()) {
-          mbar_arrive_expect_tx(full_bar(s), (2 * G + 1) * kBoxBytes);
+          mbar_arrive_expect_tx(full_bar(s), (2 * G + NB) * kBoxBytes);
           for (int c = 0; c < 2 * G; ++c) tma_load_2d(st + c * kBoxBytes, &p.tmX, full_bar(s), col0 + c * 64, kb * KB, kEvictFirst);
-          tma_load_2d(st + 2 * kMaxG * kBoxBytes, &p.tmY, full_bar(s), 0, kb * KB, kEvictFirst);
+#pragma unroll
+          for (int c = 0; c < NB; ++c) tma_load_2d(st + (2 * kMaxG + c) * kBoxBytes, &p.tmY, full_bar(s), c * 64, kb * KB, kEvictFirst);
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     } else if (warp == 1) {
       // whole warp walks the loop (uniform registers, no per-lane waterfall around tcgen05.mma); one elected lane issues
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64 * NB, 1, 1);
       const uint64_t a0 = make_smem_desc_sw128(base, kBoxBytes, 1024);
-      const uint64_t b0 = make_smem_desc_sw128(base + 2 * kMaxG * kBoxBytes, 0, 1024);
+      const uint64_t b0 = make_smem_desc_sw128(base + 2 * kMaxG * kBoxBytes, NB == 1 ? 0 : kBoxBytes, 1024);
       int s = 0; uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar(s), ph);
@@ -87,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
           for (int m = 0; m < G; ++m) {
 #pragma unroll
             for (int k = 0; k < KB / 16; ++k)
-              umma_ss(tmem + m * 64, a0 + so + uint64_t(((2 * m) * kBoxBytes + k * 2048) >> 4), b0 + so + uint64_t((k * 2048) >> 4), idesc,
+              umma_ss(tmem + m * 64 * NB, a0 + so + uint64_t(((2 * m) * kBoxBytes + k * 2048) >> 4), b0 + so + uint64_t((k * 2048) >> 4), idesc,
                       (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(s));
@@ -101,11 +110,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       const int q = warp & 3;
       mbar_wait(done_bar, 0);
       tc_fence_after();
-      for (int m = 0; m < G; ++m) {
+      for (int mh = 0; mh < G * NB; ++mh) {
+        const int m = mh / NB, hb = mh % NB;     // M tile, 64-column half of its accumulator
         uint32_t v[64];
         uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
         uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-        const uint32_t ta = tmem + (uint32_t(q * 32) << 16) + m * 64;
+        const uint32_t ta = tmem + (uint32_t(q * 32) << 16) + m * 64 * NB + hb * 64;
         tmem_ld32(ta, lo);
         tmem_ld32(ta + 32, hi);
         tmem_ld_wait();
@@ -125,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
           float4 f;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(scr + r * 272 + pc * 16));
           if (rbase + r < p.Mo)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.D + size_t(rbase + r) * p.ldd + 4 * pc), "f"(f.x), "f"(f.y),
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.D + size_t(rbase + r) * p.ldd + hb * 64 + 4 * pc), "f"(f.x), "f"(f.y),
                          "f"(f.z), "f"(f.w) : "memory");
         }
       }
@@ -139,16 +149,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
 }  // namespace
 
 bool wgrad_tc_supported(int ldx, int ldy, int ldd, int Mo, int No, int dtype, const void* X, const void* Y, const float* D) {
-  return dtype == NGU_BF16 && No == 64 && Mo % 128 == 0 && (ldx % 8) == 0 && (ldy % 8) == 0 && (ldd % 4) == 0 &&
+  return dtype == NGU_BF16 && (No == 64 || No == 128) && Mo % 128 == 0 && (ldx % 8) == 0 && (ldy % 8) == 0 && (ldd % 4) == 0 &&
          (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0;
 }
 
-int wgrad_tc(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int T, int Mo, cudaStream_t st) {
+template <int NB>
+static int wgrad_tc_launch(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int T, int Mo, cudaStream_t st) {
+  constexpr int kMaxG = WgCfg<NB>::kMaxG;
+  constexpr int kSmem = WgCfg<NB>::kSmem;
   WgradParams p;
   memset(&p, 0, sizeof(p));
   int rc;
   if ((rc = make_tmap_2d_bf16(&p.tmX, X, T, Mo, ldx, KB, 64, true))) return rc;
-  if ((rc = make_tmap_2d_bf16(&p.tmY, Y, T, 64, ldy, KB, 64, true))) return rc;
+  if ((rc = make_tmap_2d_bf16(&p.tmY, Y, T, 64 * NB, ldy, KB, 64, true))) return rc;
   const int tiles = Mo / 128;
   int G = 1;
   for (int g = kMaxG; g >= 1; --g) if (tiles % g == 0) { G = g; break; }
@@ -161,12 +174,16 @@ int wgrad_tc(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, 
   p.kb_per_split = (total_kb + splits - 1) / splits;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return cuda_status(e, "wgrad_tc attr");
     attr = true;
   }
-  wgrad_tc_kernel<<<groups * splits, kThreads, kSmem, st>>>(p);
+  launch_pdl(wgrad_tc_kernel<NB>, dim3(groups * splits), dim3(kThreads), size_t(kSmem), st, p);
   return check_launch("wgrad_tc");
+}
+
+int wgrad_tc(const void* X, int ldx, const void* Y, int ldy, float* D, int ldd, int T, int Mo, int No, cudaStream_t st) {
+  return No == 128 ? wgrad_tc_launch<2>(X, ldx, Y, ldy, D, ldd, T, Mo, st) : wgrad_tc_launch<1>(X, ldx, Y, ldy, D, ldd, T, Mo, st);
 }
 
 }  // namespace ngu

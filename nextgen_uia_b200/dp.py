@@ -18,6 +18,24 @@ import torch
 import torch.distributed as dist
 
 
+class _nvtx:
+    """NVTX range around the phases of a step when NGU_NVTX=1; free otherwise."""
+    import os as _os
+    on = _os.environ.get("NGU_NVTX", "0") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if self.on and torch.cuda.is_available():
+            torch.cuda.nvtx.range_push("ngu/" + self.name)
+
+    def __exit__(self, *a):
+        if self.on and torch.cuda.is_available():
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def setup_mona(model, variant="baseline", bottleneck=64, num_layers=None):
     """finetune.py:165-177 `_setup_mona_finetuning`: freeze all, inject, thaw names containing 'mona'."""
     from .adapters.mona import inject_mona_variant_to_open_clip
@@ -166,23 +184,43 @@ class FusedAdamW:
         self.m = torch.zeros_like(buckets.flat_param)
         self.v = torch.zeros_like(buckets.flat_param)
         self.gsq = torch.zeros(1, device=buckets.flat_param.device, dtype=torch.float32)
-        self.updates = 0
+        # device-resident loop state (include/ngu_b200.h ngu_guard_tick): updates applied, poison flag, updates skipped,
+        # micro-steps run.  The LR schedule and the bias-correction step are derived from it INSIDE the kernel, so a skipped
+        # update advances neither (finetune.py:281-288: `continue` also skips scheduler.step()) and a CUDA-graph replay
+        # needs nothing from the host.
+        self.state = torch.zeros(4, device=buckets.flat_param.device, dtype=torch.int64)
+
+    @property
+    def updates(self):
+        """updates applied so far (host read: synchronises; for logging / tests)"""
+        return int(self.state[0].item())
+
+    @property
+    def skipped(self):
+        return int(self.state[2].item())
 
     @property
     def lr(self):
         return cosine_lr(self.base_lr, self.lr_min, self.updates, self.t_max)
 
+    def note_loss(self, loss):
+        """poison |= !isfinite(loss): called for EVERY micro-step, so a bad micro-batch early in an accumulation window
+        cancels the window's update instead of reaching the moments."""
+        from . import ops
+        ops.guard_tick(self.state, 0, loss=loss)
+
+    def end_micro_step(self):
+        from . import ops
+        ops.guard_tick(self.state, 2)
+
     def step(self, loss=None):
         from . import ops
-        lr = self.lr
-        self.updates += 1
-        gsq = None
-        if self.grad_clip and self.grad_clip > 0:
-            self.gsq.zero_()
-            ops.sqnorm(self.b.flat_grad, self.gsq)
-            gsq = self.gsq
-        ops.adamw_step(self.b.flat_param, self.b.flat_grad, self.m, self.v, lr=lr, betas=self.betas, eps=self.eps,
-                       weight_decay=self.wd, step=self.updates, max_norm=self.grad_clip or 0.0, gsq=gsq, loss=loss, zero_grad=True)
+        self.gsq.zero_()
+        ops.sqnorm(self.b.flat_grad, self.gsq)     # always: a non-finite gradient norm also cancels the update
+        ops.adamw_step(self.b.flat_param, self.b.flat_grad, self.m, self.v, lr=self.base_lr, betas=self.betas, eps=self.eps,
+                       weight_decay=self.wd, step=1, max_norm=self.grad_clip or 0.0, gsq=self.gsq, loss=loss, zero_grad=True,
+                       state=self.state, lr_min=self.lr_min, t_max=self.t_max)
+        ops.guard_tick(self.state, 1, gsq=self.gsq)
 
 
 class Trainer:
@@ -216,17 +254,28 @@ class Trainer:
         # One-launch refresh of the bf16 shadows (and transposes) of every Mona projection weight after each update,
         # instead of four small cast launches per layer per step.
         self.castplan = None
+        self.monaplan = None
         dt = next((getattr(m, "compute_dtype") for m in model.modules() if hasattr(m, "compute_dtype")), None)
         if on_gpu and self.fused and dt == torch.bfloat16:
+            import os
             from .adapters.mona import BaselineMona
             from . import ops
             monas = [m for m in model.modules() if isinstance(m, BaselineMona) and all(p.requires_grad for p in m.parameters())]
+            fusable = [m for m in monas if m.project1.weight.shape[0] == 64 and m.project1.weight.shape[1] % 128 == 0
+                       and not hasattr(m.adapter_conv, "noise_estimator")]
+            if fusable and len(fusable) == len(monas) and os.environ.get("NGU_MONA_FUSED", "1") != "0":
+                # fused Mona path: one launch re-derives [W1*ln_w*gamma ; W1*gammax], the merged stencil, ... of every adapter
+                self.monaplan = ops.MonaPrepPlan(fusable)
+                monas = []
             entries = [(w, tr) for m in monas for w in (m.project1.weight, m.project2.weight) for tr in (False, True)]
             if entries:
                 self.castplan = ops.CastPlan(entries, dt)
                 self.castplan.fresh = False
                 for m in monas:
                     m._ngu_castplan = self.castplan
+        self._mona_stale = True
+        self._poisoned = False
+        self.graph = None
         self.grad_clip = grad_clip
         self.accum = accumulation_steps
         self.micro = 0
@@ -246,28 +295,121 @@ class Trainer:
         if self.castplan is not None and not self.castplan.fresh:
             if self.castplan.valid():
                 self.castplan.run()
-        fi = m.encode_image(images)
-        ft = m.encode_text(ids)
-        loss = self.criterion(fi, ft)
-        (loss / self.accum).backward()
+        if self.monaplan is not None and self._mona_stale and self.monaplan.valid():
+            self.monaplan.run()
+            self._mona_stale = False
+        with _nvtx("encode_image"):
+            fi = m.encode_image(images)
+        with _nvtx("encode_text"):
+            ft = m.encode_text(ids)
+        with _nvtx("infonce"):
+            loss = self.criterion(fi, ft)
+        lossd = loss.detach().float().view(1)
+        if self.fused:
+            self.optimizer.note_loss(lossd)
+        elif not bool(torch.isfinite(lossd).all()):
+            # torch.optim path (CPU / fused_optimizer=False): the reference's host-side check, finetune.py:281-285
+            self.micro += 1
+            self._poisoned = True
+            if last:
+                self._finish_unfused_window()
+            return loss.detach()
+        with _nvtx("backward"):
+            (loss / self.accum).backward()
         self.micro += 1
         if last:
             self.buckets.wait()
             if self.fused:
-                # global-norm clip + AdamW + cosine LR + zero_grad on device; a non-finite loss skips the update
-                # (the reference's `if not torch.isfinite(loss): continue`, finetune.py:281-285, without the host sync)
-                self.optimizer.step(loss=loss.detach().float().view(1))
+                # global-norm clip + AdamW + cosine LR + zero_grad on device; a non-finite loss anywhere in the accumulation
+                # window or a non-finite gradient norm skips the update (finetune.py:281-285 without the host sync)
+                with _nvtx("optimizer"):
+                    self.optimizer.step(loss=lossd)
                 from . import ops as _ops
                 _ops.bump_param_epoch()           # raw-pointer parameter update: invalidate low-precision shadows
                 if self.castplan is not None:
                     self.castplan.fresh = False   # parameters changed: shadows are re-made at the next micro-step
+                self._mona_stale = True
             else:
-                if self.grad_clip and self.grad_clip > 0:
-                    torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip)
-                self.optimizer.step()
-                self.scheduler.step()
-                self.buckets.zero()
+                self._finish_unfused_window()
+        elif self.fused:
+            self.optimizer.end_micro_step()
         return loss.detach()
+
+    def _finish_unfused_window(self):
+        if not self._poisoned:
+            if self.grad_clip and self.grad_clip > 0:
+                torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.grad_clip)
+            self.optimizer.step()
+            self.scheduler.step()
+        self._poisoned = False
+        self.buckets.zero()
+
+    def flush(self):
+        """End of an epoch with leftover micro-batches (finetune.py:287 `or batch_idx + 1 == len(trainloader)`): apply the
+        update for the partial accumulation window.  Gradients of the partial window are averaged over `accum` like the
+        reference (it divides every micro-loss by accumulation_steps regardless)."""
+        if self.micro % self.accum == 0:
+            return
+        self.micro += self.accum - self.micro % self.accum
+        if self.distributed:
+            for key in self.buckets.buckets:
+                self.buckets.enabled = True
+                self.buckets._launch(key)
+        self.buckets.wait()
+        if self.fused:
+            self.optimizer.step()
+            from . import ops as _ops
+            _ops.bump_param_epoch()
+            if self.castplan is not None:
+                self.castplan.fresh = False
+            self._mona_stale = True
+        else:
+            self._finish_unfused_window()
+
+    # ---------------------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the whole micro-step (SURVEY.md section 5.8 / 7.3): forward, backward, collectives, optimiser
+    def capture(self, images, ids, warmup=3):
+        """Capture one full training step (accumulation_steps == 1) into a CUDA graph with static input buffers.
+        The LR schedule, bias-correction step, non-finite guard and dropout counter all live on the device
+        (FusedAdamW.state), so replays need nothing from the host.  Parameters / optimiser state are restored after the
+        warm-up iterations capture needs: capturing has no training side effects."""
+        if not (self.fused and self.accum == 1):
+            raise RuntimeError("Trainer.capture needs the fused optimiser and accumulation_steps == 1")
+        from . import ops as _ops
+        opt = self.optimizer
+        _ops.set_seed_counter(opt.state[3:4])
+        self.static_in = (torch.empty_like(images), torch.empty_like(ids))
+        self.static_in[0].copy_(images)
+        self.static_in[1].copy_(ids)
+        snap = (self.buckets.flat_param.clone(), opt.m.clone(), opt.v.clone(), opt.state.clone())
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.micro_step(*self.static_in)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            self.buckets.flat_param.copy_(snap[0]); opt.m.copy_(snap[1]); opt.v.copy_(snap[2]); opt.state.copy_(snap[3])
+            self.buckets.flat_grad.zero_()
+        _ops.bump_param_epoch()                 # every derived / low-precision shadow is re-made INSIDE the graph
+        if self.castplan is not None:
+            self.castplan.fresh = False
+        self._mona_stale = True
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self.micro_step(*self.static_in)
+        return self
+
+    def replay(self, images, ids):
+        """One captured step on a new batch (device tensors of the captured shapes); returns the (static) loss tensor."""
+        if images is not self.static_in[0]:
+            self.static_in[0].copy_(images, non_blocking=True)
+        if ids is not self.static_in[1]:
+            self.static_in[1].copy_(ids, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss
 
 
 class DeviceFeeder:

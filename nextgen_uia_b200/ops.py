@@ -43,7 +43,7 @@ def _f32(t):
 
 # ------------------------------------------------------------------------------------------------
 def gemm(A, B, *, bias=None, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save_pre=False,
-         A2=None, B2=None, alpha=1.0, out=None, block_n=0, force_simt=False):
+         A2=None, B2=None, alpha=1.0, out=None, block_n=0, force_simt=False, aux2=None, rowab=None):
     """C[M,N] = epi(alpha * (A[M,K] @ B[N,K]^T + A2 @ B2^T)); returns C, or (C, D) with save_pre where
     D = act'(pre-activation) (the factor AUX_DACT multiplies by in backward; the pre-activation itself if act is NONE)."""
     _need_cuda(A, B)
@@ -67,6 +67,12 @@ def gemm(A, B, *, bias=None, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save
         d.aux, d.ldaux = aux.data_ptr(), aux.stride(0)
     if save_pre:
         d.Pre, d.ldpre = Pre.data_ptr(), Pre.stride(0)
+    if aux2 is not None:
+        assert aux2.shape == (M, N) and aux2.stride(1) == 1 and aux2.dtype == A.dtype
+        d.aux2, d.ldaux2 = aux2.data_ptr(), aux2.stride(0)
+    if rowab is not None:
+        assert rowab.shape == (M, 2) and rowab.dtype == torch.float32 and rowab.is_contiguous()
+        d.rowab = rowab.data_ptr()
     d.M, d.N, d.K = M, N, K
     d.act, d.aux_mode, d.save_pre = act, aux_mode, int(save_pre)
     d.alpha = alpha
@@ -170,6 +176,142 @@ def mona_conv_bwd(h, dg, weights, grads, hw, has_cls, drop_p=0.0, seed=0):
         d.gr.dfreq, d.gr.dne_w1, d.gr.dne_b1, d.gr.dne_w2, d.gr.dne_b2 = (_p(t) for t in grads[9:14])
     L.check(L.lib().ngu_mona_conv_bwd(_byref(d), _stream()), "ngu_mona_conv_bwd")
     return dh
+
+
+# ------------------------------------------------------------------------------------------------
+# fused Mona path (bf16): derived operands + stage kernels (include/ngu_b200.h "Fused Mona adapter")
+class MonaDerivedBuffers:
+    """Device buffers of `ngu_mona_derived` for one adapter, carved out of one allocation."""
+
+    def __init__(self, D, device):
+        sizes = [("wab", 128 * D * 2), ("wcat_t", D * 128 * 2), ("w2", D * 64 * 2), ("w2_t", 64 * D * 2), ("ca", 256), ("cb", 256),
+                 ("kc", 49 * 64 * 4), ("bc", 256), ("pb", 64 * 64 * 2), ("bp", 256)]
+        total = sum((n + 255) // 256 * 256 for _, n in sizes)
+        self.buf = torch.empty(total, device=device, dtype=torch.uint8)
+        self.D = D
+        self.c = L.MonaDerived()
+        off = 0
+        base = self.buf.data_ptr()
+        self.off = {}
+        for name, n in sizes:
+            setattr(self.c, name, base + off)
+            self.off[name] = (off, n)
+            off += (n + 255) // 256 * 256
+
+    def view(self, name, dtype, shape):
+        off, n = self.off[name]
+        return self.buf[off:off + n].view(dtype).view(*shape)
+
+
+def mona_params_struct(m):
+    """ngu_mona_params of a BaselineMona / FreqEnhancedMona module (fp32 parameters, reference shapes)."""
+    c = m.adapter_conv
+    P = L.MonaParams()
+    P.w1, P.b1, P.w2, P.b2 = (_f32(t.detach()).data_ptr() for t in (m.project1.weight, m.project1.bias, m.project2.weight, m.project2.bias))
+    P.ln_w, P.ln_b, P.gamma, P.gammax = (_f32(t.detach()).data_ptr() for t in (m.norm.weight, m.norm.bias, m.gamma, m.gammax))
+    cw = P.conv
+    cw.k3, cw.b3, cw.k5, cw.b5, cw.k7, cw.b7 = (_f32(t.detach()).data_ptr() for t in (c.conv1.weight, c.conv1.bias, c.conv2.weight, c.conv2.bias,
+                                                                                       c.conv3.weight, c.conv3.bias))
+    cw.P, cw.bp = _f32(c.projector.weight.detach()).data_ptr(), _f32(c.projector.bias.detach()).data_ptr()
+    freq = getattr(c, "freq_filter", None)
+    cw.freq = _p(freq.detach()) if freq is not None else None
+    return P
+
+
+class MonaPrepPlan:
+    """One-launch refresh (`ngu_mona_prep`) of the derived operands of a set of adapters after each optimiser update."""
+
+    def __init__(self, monas):
+        import numpy as np
+        self.monas = list(monas)
+        dev = self.monas[0].project1.weight.device
+        self.D = self.monas[0].project1.weight.shape[1]
+        items = (L.MonaPrepItem * len(self.monas))()
+        for i, m in enumerate(self.monas):
+            if getattr(m, "_ngu_derived", None) is None or m._ngu_derived.buf.device != dev:
+                m._ngu_derived = MonaDerivedBuffers(self.D, dev)
+            items[i].p = mona_params_struct(m)
+            items[i].d = m._ngu_derived.c
+        raw = np.frombuffer(bytes(items), dtype=np.uint8).copy()
+        self.table = torch.from_numpy(raw).to(dev)
+        self.ptrs = [p.data_ptr() for m in self.monas for p in m.parameters()]
+
+    def valid(self):
+        return self.ptrs == [p.data_ptr() for m in self.monas for p in m.parameters()]
+
+    def run(self):
+        L.check(L.lib().ngu_mona_prep(self.table.data_ptr(), len(self.monas), self.D, _stream()), "ngu_mona_prep")
+        for m in self.monas:
+            m._ngu_derived_key = _mona_param_key(m)
+
+
+def _mona_param_key(m):
+    return (PARAM_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in m.parameters())
+
+
+def mona_derived(m):
+    """Fresh derived operands of adapter `m` (re-made when a parameter changed since the last prep)."""
+    if getattr(m, "_ngu_derived_key", None) != _mona_param_key(m) or getattr(m, "_ngu_derived", None) is None:
+        plan = getattr(m, "_ngu_own_plan", None)
+        if plan is None or not plan.valid():
+            plan = m._ngu_own_plan = MonaPrepPlan([m])
+        plan.run()
+    return m._ngu_derived
+
+
+_MONA_WS = {}
+
+
+def mona_ws(D, device):
+    key = (D, str(device))
+    if key not in _MONA_WS:
+        _MONA_WS[key] = torch.zeros(int(L.lib().ngu_mona_ws_floats(D)), device=device, dtype=torch.float32)
+    return _MONA_WS[key]
+
+
+def _mona_stage_desc(der, B, N, D, hw, has_cls, drop_p, seed, eps):
+    d = L.MonaStageDesc()
+    d.d = der.c
+    d.B, d.N, d.H, d.W, d.D, d.has_cls = B, N, hw[0], hw[1], D, int(has_cls)
+    d.eps, d.drop_p, d.seed = float(eps), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF
+    return d
+
+
+def mona_fwd_stage(x, der, hw, has_cls, drop_p, seed, eps):
+    """x [B,N,D] bf16 -> (h, hA, g [B,N,64] bf16, mean, rstd [B*N] fp32)."""
+    _need_cuda(x)
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    B, N, D = x.shape
+    h = torch.empty(B, N, 64, device=x.device, dtype=x.dtype)
+    hA, g = torch.empty_like(h), torch.empty_like(h)
+    mean = torch.empty(B * N, device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    d = _mona_stage_desc(der, B, N, D, hw, has_cls, drop_p, seed, eps)
+    d.x, d.h, d.hA, d.g, d.mean, d.rstd = x.data_ptr(), h.data_ptr(), hA.data_ptr(), g.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    L.check(L.lib().ngu_mona_fwd_stage(_byref(d), _stream()), "ngu_mona_fwd_stage")
+    return h, hA, g, mean, rstd
+
+
+def mona_bwd_stage(h, hA, dg, mean, rstd, der, D, hw, has_cls, drop_p, seed, dP, dbp):
+    """-> (dhcat [B*N,128] bf16, rowab [B*N,2] fp32, ws); dP / dbp accumulate."""
+    B, N, _ = h.shape
+    dhcat = torch.empty(B * N, 128, device=h.device, dtype=h.dtype)
+    rowab = torch.empty(B * N, 2, device=h.device, dtype=torch.float32)
+    ws = mona_ws(D, h.device)
+    d = _mona_stage_desc(der, B, N, D, hw, has_cls, drop_p, seed, 0.0)
+    d.h, d.hA, d.dg, d.mean, d.rstd = h.data_ptr(), hA.data_ptr(), dg.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    d.dhcat, d.rowab, d.ws, d.dP, d.dbp = dhcat.data_ptr(), rowab.data_ptr(), ws.data_ptr(), _f32(dP).data_ptr(), _f32(dbp).data_ptr()
+    L.check(L.lib().ngu_mona_bwd_stage(_byref(d), _stream()), "ngu_mona_bwd_stage")
+    return dhcat, rowab, ws
+
+
+def mona_finish(m, grads, ws, D):
+    """grads: dict name -> fp32 tensor (dw1, db1, dln_w, dln_b, dgamma, dgammax, dk3, db3, dk5, db5, dk7, db7[, dfreq])."""
+    P = mona_params_struct(m)
+    G = L.MonaGrads()
+    for k, t in grads.items():
+        setattr(G, k, _f32(t).data_ptr() if t is not None else None)
+    L.check(L.lib().ngu_mona_finish(_byref(P), _byref(G), ws.data_ptr(), D, _stream()), "ngu_mona_finish")
 
 
 def _attn_desc(q, k, v, o, B, H, N, S, dh, strides, scale, causal, impl, kv_len=None):
@@ -410,7 +552,30 @@ def sqnorm(x, out):
     L.check(L.lib().ngu_sqnorm(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "ngu_sqnorm")
 
 
-def adamw_step(param, grad, m, v, *, lr, betas, eps, weight_decay, step, max_norm=0.0, gsq=None, loss=None, zero_grad=True):
+def guard_tick(state, mode, loss=None, gsq=None):
+    """Device-side loop counters / non-finite guard (include/ngu_b200.h ngu_guard_tick); state: int64[4] CUDA tensor."""
+    _need_cuda(state)
+    assert state.dtype == torch.int64 and state.numel() >= 4
+    L.check(L.lib().ngu_guard_tick(state.data_ptr(), _p(loss), _p(gsq), int(mode), _stream()), "ngu_guard_tick")
+
+
+def set_seed_counter(counter):
+    """counter: int64 CUDA tensor element (kept alive by the caller) mixed into every dropout seed, or None."""
+    L.check(L.lib().ngu_set_seed_counter(None if counter is None else counter.data_ptr()), "ngu_set_seed_counter")
+
+
+def kv_len(ids, pad_id, flag):
+    """ids int64 [B,S] -> int32 [B] valid lengths; flag (int32[1]) |= 1 if a row is not right-padded."""
+    _need_cuda(ids)
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and flag.dtype == torch.int32
+    B, S = ids.shape
+    out = torch.empty(B, device=ids.device, dtype=torch.int32)
+    L.check(L.lib().ngu_kv_len(ids.data_ptr(), int(pad_id), out.data_ptr(), flag.data_ptr(), B, S, _stream()), "ngu_kv_len")
+    return out
+
+
+def adamw_step(param, grad, m, v, *, lr, betas, eps, weight_decay, step, max_norm=0.0, gsq=None, loss=None, zero_grad=True,
+               state=None, lr_min=0.0, t_max=0):
     _need_cuda(param)
     for t in (param, grad, m, v):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
@@ -419,4 +584,5 @@ def adamw_step(param, grad, m, v, *, lr, betas, eps, weight_decay, step, max_nor
     d.lr, d.beta1, d.beta2, d.eps, d.weight_decay = float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay)
     d.step, d.max_norm = int(step), float(max_norm)
     d.gsq, d.loss, d.zero_grad = _p(gsq), _p(loss), int(zero_grad)
+    d.state, d.lr_min, d.t_max = _p(state), float(lr_min), int(t_max)
     L.check(L.lib().ngu_adamw_step(_byref(d), _stream()), "ngu_adamw_step")

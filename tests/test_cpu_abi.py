@@ -33,7 +33,9 @@ def test_struct_sizes_match_header():
     from nextgen_uia_b200 import _lib as L
     names = {"ngu_gemm_desc": L.GemmDesc, "ngu_ln_desc": L.LnDesc, "ngu_ln_bwd_desc": L.LnBwdDesc,
              "ngu_mona_pre_bwd_desc": L.MonaPreBwdDesc, "ngu_mona_conv_desc": L.MonaConvDesc, "ngu_attn_desc": L.AttnDesc,
-             "ngu_infonce_desc": L.InfoNceDesc, "ngu_adamw_desc": L.AdamWDesc, "ngu_cast_item": L.CastItem}
+             "ngu_infonce_desc": L.InfoNceDesc, "ngu_adamw_desc": L.AdamWDesc, "ngu_cast_item": L.CastItem,
+             "ngu_mona_params": L.MonaParams, "ngu_mona_derived": L.MonaDerived, "ngu_mona_prep_item": L.MonaPrepItem,
+             "ngu_mona_stage_desc": L.MonaStageDesc, "ngu_mona_grads": L.MonaGrads}
     prog = '#include <stdio.h>\n#include "ngu_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:

@@ -32,13 +32,25 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU (configs[1]: 256)")
-    ap.add_argument("--method", default="mona", choices=["mona", "lora"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configs[] (1-based): 2 = BiomedCLIP ViT-B/16 + Mona, batch 256/GPU (the metric's config, default); "
+                         "3 = BiomedCLIP + LoRA r=8 (qkv+proj), data parallel; 4 = OpenAI CLIP ViT-L/14@336 + Mona, batch 64/GPU; "
+                         "5 = CLIPSeg ViT-B/16@352 + Mona + HF decoder + DiceCE, batch 32/GPU")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the config's: 256 / 256 / 64 / 32)")
+    ap.add_argument("--method", default="", choices=["", "mona", "lora"])
     ap.add_argument("--depth", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the whole step as a CUDA graph (default); 0: eager launches")
     ap.add_argument("--cpu-batch", type=int, default=8)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if not a.method:
+        a.method = "lora" if a.config == 3 else "mona"
+    if a.config == 3:
+        a.method = "lora"
+    if a.batch <= 0:
+        a.batch = {2: 256, 3: 256, 4: 64, 5: 32}[a.config]
+    return a
 
 
 # -------------------------------------------------------------------------------------------------
@@ -50,6 +62,111 @@ def synthetic_batch(B, seed, vocab=30522):
     ids[:, 0] = 2
     ids[:, -1] = 3
     return images, ids
+
+
+def block_flops(N, D, bwd=False):
+    """one pre-LN block per image: 24 N D^2 + 4 N^2 D forward, 24 N D^2 + 8 N^2 D dgrad-only backward."""
+    return 24.0 * N * D * D + (8.0 if bwd else 4.0) * N * N * D
+
+
+def mona_flops(N, D, r=64):
+    """Mona per image per layer: forward 4 N D r + 2 (N-1) r^2; backward (dgrad + wgrad) twice that."""
+    f = 4.0 * N * D * r + 2.0 * (N - 1) * r * r
+    return f, 2.0 * f
+
+
+def flops_per_image(config, depth):
+    """Algorithmic FLOPs of one image(-text pair) through the step of each BASELINE.json config (frozen-weight dgrad only,
+    no recompute; block 0 needs no backward in Mona mode)."""
+    if config in (2, 3):
+        N, D = 197, 768
+        mf, mb = mona_flops(N, D) if config == 2 else (12.0 * N * 8 * D, 24.0 * N * 8 * D)
+        vis = depth * (block_flops(N, D) + mf) + (depth - (1 if config == 2 else 0)) * block_flops(N, D, True) + depth * mb + 2.0 * 196 * 768 * 768
+        return vis + depth * block_flops(77, 768)
+    if config == 4:
+        N, D, L = 577, 1024, 24
+        mf, mb = mona_flops(N, D)
+        vis = L * (block_flops(N, D) + mf) + (L - 1) * block_flops(N, D, True) + L * mb + 2.0 * 576 * 588 * 1024
+        return vis + 12 * block_flops(77, 768)
+    N, D, L = 485, 768, 12
+    mf, mb = mona_flops(N, D)
+    return L * (block_flops(N, D) + mf) + (L - 1) * block_flops(N, D, True) + L * mb + 2.0 * 484 * 768 * 768 + 12 * block_flops(77, 512) / 32.0
+
+
+def clip_tokens(B, seed, vocab=49408):
+    """CLIP ids [B,77] int32 randint(1, 49406), last position = EOT 49407 (argmax picks it)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(1, 49406, (B, 77), generator=g, dtype=torch.int64)
+    ids[:, -1] = 49407
+    return ids
+
+
+def build_clip_model(config, device=None, dtype=torch.bfloat16, layers=None):
+    """config 4: OpenAI CLIP ViT-L/14@336 (24 x 1024-wide blocks, 577 tokens; text 12 x 768) + baseline Mona in every vision block
+    (src/models/clip/finetune.py:60-98).  config 5: CLIP ViT-B/16 at 352 x 352 (485 tokens; text 12 x 512) inside CLIPSegAdapter
+    with Mona re-thawed after the backbone freeze (src/models/clipseg/segmentation.py:86-111)."""
+    from nextgen_uia_b200.openai_clip import CLIP
+    from nextgen_uia_b200.adapters.mona import inject_mona_variant_to_clip
+    torch.manual_seed(1)
+    if config == 4:
+        m = CLIP(768, 336, layers or 24, 1024, 14, 77, 49408, 768, 12, 12)
+    else:
+        m = CLIP(512, 352, layers or 12, 768, 16, 77, 49408, 512, 8, 12)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.startswith("visual.") and p.dim() >= 2:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    for p in m.parameters():
+        p.requires_grad = False
+    inject_mona_variant_to_clip(m, variant="baseline", bottleneck_dim=64)
+    for n, p in m.named_parameters():
+        if "mona" in n.lower():
+            p.requires_grad = True
+    if device is not None:
+        m = m.to(device)
+    m.train()
+    return m.set_compute_dtype(dtype)
+
+
+class DiceCE(torch.nn.Module):
+    """monai.losses.DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=1e-8, smooth_dr=1e-8) restated in
+    PyTorch (monai 1.5.1 is a pinned dependency that is not installed; src/models/clipseg/segmentation.py:84): mean over batch and
+    classes of 1 - (2 sum(p t) + nr) / (sum(p^2) + sum(t^2) + dr), plus the mean cross entropy.  SURVEY.md keeps it in PyTorch."""
+
+    def forward(self, logits, labels):
+        C = logits.shape[1]
+        p = torch.softmax(logits.float(), 1)
+        t = torch.nn.functional.one_hot(labels.long().squeeze(1), C).permute(0, 3, 1, 2).float()
+        dims = (2, 3)
+        inter = (p * t).sum(dims)
+        den = (p * p).sum(dims) + (t * t).sum(dims)
+        dice = (1.0 - (2.0 * inter + 1e-8) / (den + 1e-8)).mean()
+        ce = torch.nn.functional.cross_entropy(logits.float(), labels.long().squeeze(1))
+        return dice + ce
+
+
+class SegTrainer:
+    """config 5 step (src/models/clipseg/segmentation.py:139-149): preds = model(images, prompt ids); DiceCE; backward; AdamW;
+    cosine schedule.  The CLIP encoder + Mona run on the kernels; decoder, loss and optimiser are PyTorch (library code)."""
+
+    def __init__(self, seg_model, lr=1e-4):
+        self.model = seg_model
+        self.crit = DiceCE()
+        self.params = [p for p in seg_model.parameters() if p.requires_grad]
+        self.opt = torch.optim.AdamW(self.params, lr=lr, betas=(0.9, 0.95), weight_decay=0.01, fused=self.params[0].is_cuda)
+        self.sched = torch.optim.lr_scheduler.CosineAnnealingLR(self.opt, T_max=1000, eta_min=1e-8)
+        self.graph = None
+        self.static_in = None
+
+    def micro_step(self, images, labels_and_ids):
+        labels, ids = labels_and_ids
+        self.opt.zero_grad(set_to_none=True)
+        loss = self.crit(self.model(images, input_ids=ids), labels)
+        loss.backward()
+        self.opt.step()
+        self.sched.step()
+        return loss.detach()
 
 
 def build_model(method, depth, device=None, dtype=torch.bfloat16):
@@ -117,9 +234,13 @@ class ClockSampler:
 
 # -------------------------------------------------------------------------------------------------
 def cpu_reference_rate(steps, warmup, batch, depth):
-    """The reference algorithm (oracle port: oracle/functional.py) on the host cores, fp32, all threads:
-    one training micro-step (encode_image + encode_text + InfoNCE + backward) per step."""
+    """The reference's CPU path on the host cores, fp32, all threads: one training micro-step (encode_image + encode_text +
+    InfoNCE + backward) per step.  When oracle/_ref/ holds the reference's own modules (oracle/build_ref.py) the adapters
+    are the reference's BatchFirstMonaWrapper(BaselineMona) instances and the loss is its InfoNCELoss, wrapped around the
+    oracle's ViT / BERT (timm / open_clip are pinned dependencies that exist nowhere here) -> kind "reference"; otherwise
+    the whole step is the oracle port -> kind "port".  Returns (images/s, s/step, cores, kind)."""
     from oracle import functional as OF
+    from oracle import build_ref
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     model = build_model("mona", depth)
@@ -127,15 +248,85 @@ def cpu_reference_rate(steps, warmup, batch, depth):
     trainable = [n for n, p in model.named_parameters() if p.requires_grad]
     images, ids = synthetic_batch(batch, 1)
     cfg = dict(patch=16, depth=depth, heads=12, text_layers=depth, text_heads=12)
+    rmona, rloss = build_ref.load("mona"), build_ref.load("losses")
+    kind = "port"
+    if rmona is not None and rloss is not None:
+        kind = "reference"
+        adapters = []
+        for i in range(depth):
+            m = rmona.BatchFirstMonaWrapper(rmona.BaselineMona(768, 64))
+            pre = f"visual.trunk.blocks.{i}.mona."
+            m.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, strict=True)
+            adapters.append(m.train())           # the reference loop trains with model.train(): adapter dropout active
+        crit = rloss.InfoNCELoss(temperature=0.07)
+        params = [p for m in adapters for p in m.parameters()]
+        frozen = {k: v for k, v in sd.items()}
+
+        def step():
+            for p in params:
+                p.grad = None
+            fi = OF.encode_image(frozen, images, cfg, adapters=adapters)
+            with torch.no_grad():
+                ft = OF.encode_text(frozen, ids, cfg)
+            crit(fi, ft).backward()
+    else:
+        def step():
+            OF.loss_and_grads(sd, images, ids, cfg, trainable, dtype=torch.float32)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        OF.loss_and_grads(sd, images, ids, cfg, trainable, dtype=torch.float32)
+        step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     mean = sum(times) / len(times)
-    return batch / mean, mean, cores
+    return batch / mean, mean, cores, kind
+
+
+def gpu_eager_rate(dev, batch, depth, steps=3):
+    """On-box GPU comparator: the same training step written with plain PyTorch ops (the oracle
+    restatement moved to the GPU: cuBLASLt GEMMs, native LayerNorm / depthwise-conv / softmax kernels) in bf16 with the
+    frozen weights PRE-CAST to bf16 (no per-step casts) and fp32 adapter masters under autocast.  The realistic bar an
+    unmodified PyTorch port of the reference would set on this B200."""
+    from oracle import functional as OF
+    model = build_model("mona", depth, dev)
+    trainable = [n for n, p in model.named_parameters() if p.requires_grad]
+    p = {}
+    for k, v in model.state_dict().items():
+        if k in trainable:
+            p[k] = v.detach().clone().requires_grad_(True)
+        else:
+            p[k] = v.detach().to(torch.bfloat16) if v.is_floating_point() else v.detach()
+    del model
+    cfg = dict(patch=16, depth=depth, heads=12, text_layers=depth, text_heads=12)
+    images, ids = synthetic_batch(batch, 1)
+    images, ids = images.to(dev).to(torch.bfloat16), ids.to(dev)
+    tp = [p[k] for k in trainable]
+    opt = torch.optim.AdamW(tp, lr=1e-4, fused=True)
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss, _, _, _ = OF.training_loss(p, images, ids, cfg)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(tp, 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    del p, opt
+    torch.cuda.empty_cache()
+    return {"value": batch / ms * 1e3, "unit": "images/s", "ms_per_step": ms,
+            "what": "oracle restatement of the step in plain PyTorch on this GPU: bf16 autocast, frozen weights pre-cast to bf16, "
+                    "fused AdamW; eager launches"}
 
 
 def run_reference(args):
@@ -143,16 +334,17 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    rate, sec, cores = cpu_reference_rate(steps, warm, args.cpu_batch, args.depth)
+    rate, sec, cores, kind = cpu_reference_rate(steps, warm, args.cpu_batch, args.depth)
     line = {
         "impl": "reference", "metric": "mona_finetune_images_per_sec", "value": rate, "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BiomedCLIP ViT-B/16 + Mona fine-tune micro-step (encode_image+encode_text+InfoNCE+backward), "
                                f"batch {args.cpu_batch} on host CPU, fp32", "depth": args.depth},
-        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} timed steps of batch {args.cpu_batch} (reference modules cannot travel to the GPU box; "
-                                   "oracle/functional.py is pinned to them by oracle/make_golden.py)"},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} timed steps of batch {args.cpu_batch}, fp32, train mode; " +
+                                   ("the reference's own mona.py / losses.py (oracle/_ref) around the oracle ViT-B/16 + BERT"
+                                    if kind == "reference" else "oracle/functional.py port (oracle/_ref not built)")},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -223,13 +415,44 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     L.check(L.lib().ngu_selftest_device(), "device selftest")
 
-    model = build_model(args.method, args.depth, dev)
-    trainer = dp.Trainer(model, temperature=0.07, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.01, grad_clip=1.0, accumulation_steps=1)
     B = args.batch
-    images_h, ids_h = synthetic_batch(B, 1 + rank)
-    images_h, ids_h = images_h.pin_memory(), ids_h.pin_memory()
-    images_d, ids_d = images_h.to(dev), ids_h.to(dev)
-    h2d = images_h.numel() * 4 + ids_h.numel() * 8
+    if args.config in (2, 3):
+        model = build_model(args.method, args.depth, dev)
+        trainer = dp.Trainer(model, temperature=0.07, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.01, grad_clip=1.0, accumulation_steps=1)
+        images_h, ids_h = synthetic_batch(B, 1 + rank)
+        workload = (f"BiomedCLIP ViT-B/16 + {args.method} fine-tune with InfoNCE (BASELINE.json configs[{args.config - 1}]): batch {B}/GPU, "
+                    "224x224, 77-token texts, 12+12 layers, fwd+bwd+clip+AdamW every step")
+    elif args.config == 4:
+        model = build_clip_model(4, dev)
+        trainer = dp.Trainer(model, temperature=0.07, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.01, grad_clip=1.0, accumulation_steps=1)
+        g = torch.Generator().manual_seed(1 + rank)
+        images_h, ids_h = torch.rand(B, 3, 336, 336, generator=g), clip_tokens(B, 1 + rank)
+        workload = (f"OpenAI CLIP ViT-L/14@336 + Mona fine-tune with InfoNCE (BASELINE.json configs[3]): batch {B}/GPU, 577 tokens x 1024, "
+                    "24 vision + 12 causal text layers, fwd+bwd+clip+AdamW every step")
+    else:
+        from nextgen_uia_b200.clipseg_adapter import CLIPSegAdapter
+        clip_model = build_clip_model(5, dev)
+        seg = CLIPSegAdapter(clip_model).to(dev)
+        seg.freeze_clip_backbone()
+        seg.unfreeze_adapters()
+        seg.train()
+        trainer = SegTrainer(seg)
+        model = seg
+        g = torch.Generator().manual_seed(1 + rank)
+        images_h = torch.rand(B, 3, 352, 352, generator=g)
+        labels = (torch.rand(B, 1, 352, 352, generator=g) > 0.5).float()
+        ids_h = (labels, clip_tokens(1, 7).repeat(B, 1))
+        workload = (f"CLIPSeg ViT-B/16@352 + Mona + HF CLIPSegDecoder + DiceCE (BASELINE.json configs[4]): batch {B}/GPU, 485 tokens x 768, "
+                    "12 vision layers (kernels) + text conditioning + decoder/loss/AdamW in PyTorch")
+    args.graph = args.graph if args.config in (2, 3, 4) else 0
+
+    def _pin(t):
+        return tuple(x.pin_memory() for x in t) if isinstance(t, tuple) else t.pin_memory()
+
+    def _dev(t):
+        return tuple(x.to(dev) for x in t) if isinstance(t, tuple) else t.to(dev)
+    images_h, ids_h = _pin(images_h), _pin(ids_h)
+    images_d, ids_d = _dev(images_h), _dev(ids_h)
 
     def sync():
         if world > 1:
@@ -276,15 +499,18 @@ def main():
 
     # End to end through the public API: every step's batch comes from pinned HOST memory through dp.DeviceFeeder (copy
     # of batch i+1 on a side stream while batch i computes) and every step's loss is read back through dp.ScalarLog.
+    flat_h = (images_h,) + (ids_h if isinstance(ids_h, tuple) else (ids_h,))
+
     def host_batches():
         while True:
-            yield images_h, ids_h
+            yield flat_h
 
     feeder = dp.DeviceFeeder(host_batches(), dev)
     log = dp.ScalarLog()
 
     def step_e2e():
-        im, tx = next(feeder)                      # H2D of this step's inputs (154 MB), counted in feeder.h2d_bytes
+        slot = next(feeder)                        # H2D of this step's inputs (154 MB at config 2), counted in feeder.h2d_bytes
+        im, tx = slot[0], (slot[1] if len(slot) == 2 else tuple(slot[1:]))
         log.push(run_step(im, tx))                 # D2H of this step's loss
         losses.extend(log.pop_ready())             # host sees every loss one step late; never stalls the launch queue
 
@@ -344,27 +570,38 @@ def main():
                 "traffic_note": "aggregate over shapes; per-shape DRAM bytes (QKV launch: 81 MB read + 180 MB write vs 313 MB algorithmic) in profiles/r1_gemm_qkv_ncu_full_summary.txt",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "gemm_ms_per_step": t_ms, "gemm_share_of_step": t_ms / (ms / args.steps), "gemm_launches_per_step": len(recs),
-                "step_tflops_algorithmic": FLOP_PER_IMAGE_MONA * B / (ms / args.steps * 1e-3) / 1e12}
+                "flop_per_image": flops_per_image(args.config, args.depth),
+                "step_tflops_algorithmic": flops_per_image(args.config, args.depth) * B / (ms / args.steps * 1e-3) / 1e12}
 
     # ---- block-level figure the north_star target is stated on: one ViT-B/16 block + Mona + LoRA(r=8, qkv+proj), fwd+bwd,
     #      on [B,197,768] bf16; algorithmic 6.10 GFLOP per image
     block = None
-    if rank == 0:
+    if rank == 0 and args.config in (2, 3):
         block = block_microbench(dev, B)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores = cpu_reference_rate(3, 1, args.cpu_batch, args.depth)
-        cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"3 timed micro-steps (fwd+bwd) of batch {args.cpu_batch}, fp32, oracle/functional.py, {sec:.2f} s/step"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 2:
+        rate, sec, cores, kind = cpu_reference_rate(3, 1, args.cpu_batch, args.depth)
+        cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": kind,
+               "sample": f"3 timed micro-steps (fwd+bwd) of batch {args.cpu_batch}, fp32, {sec:.2f} s/step; " +
+                         ("reference mona.py / losses.py (oracle/_ref) around the oracle ViT/BERT" if kind == "reference" else "oracle/functional.py")}
+
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline and args.config == 2:
+        try:
+            del trainer, model
+            torch.cuda.empty_cache()
+            eager = gpu_eager_rate(dev, B, args.depth)
+        except Exception as e:
+            eager = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
 
     if rank == 0:
         line = {
-            "metric": "mona_finetune_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": "mona_finetune_images_per_sec" if args.config == 2 else f"config{args.config}_finetune_images_per_sec",
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"BiomedCLIP ViT-B/16 + {args.method} fine-tune with InfoNCE (BASELINE.json configs[1]): batch {B}/GPU, "
-                                   "224x224, 77-token texts, 12+12 layers, fwd+bwd+clip+AdamW every step",
+            "config": {"workload": workload, "baseline_config": args.config,
                        "global_batch": B * world, "parallelism": f"dp{world}", "depth": args.depth,
                        "l2": "working set per step (GBs of activations) exceeds the 126 MB L2; no explicit flush needed",
                        "launch_mode": graph_note},
@@ -373,6 +610,7 @@ def main():
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
             "block": block,
             "loss_last": losses[-1] if losses else None,
         }

@@ -73,11 +73,14 @@ NGU_DEVINL T warp_max(T v) {
 // scheduling) overlaps the tail of kernel i instead of following its completion.  griddepcontrol.wait returns once ALL
 // prerequisite grids have completed and flushed, so no global memory is touched before the data it depends on exists;
 // launch_dependents is issued right after so the next grid can be scheduled as soon as SM resources free up.
-// Both are no-ops when the kernel was launched without the attribute (NGU_PDL=0).
+// Both are no-ops when the kernel was launched without the attribute (the default: NGU_PDL=1 enables it; on the
+// benchmark step it measured ~3 % SLOWER than plain stream order under a CUDA graph, profiles/r2_notes.md).
 // ----------------------------------------------------------------------------------------
 NGU_DEVINL void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifndef NGU_PDL_NO_TRIGGER
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 
 // ----------------------------------------------------------------------------------------
@@ -506,7 +509,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld, uint64_t ldb,
                       uint32_t box_rows, uint32_t box_cols, int swizzle);
 int sm_count();
-bool pdl_enabled();               // NGU_PDL != 0 (default on)
+bool pdl_enabled();               // NGU_PDL=1 (default off: measured slower on the benchmark step)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -99,8 +99,7 @@ __global__ void __launch_bounds__(256) mona_prep_kernel(const ngu_mona_prep_item
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kFwdThreads = 32 * 14;
 constexpr int kBox = 128 * 64 * 2;          // one 128-row x 64-column bf16 tile (128-byte-swizzled)
-constexpr int kRingStage = 3 * kBox;        // x tile 0, x tile 1, Wab k-block
-constexpr int kRingStages = 2;
+constexpr int kMaxRingStages = 4;
 constexpr int kConvThreads = 256;
 
 struct FwdSmall {
@@ -111,7 +110,9 @@ struct FwdSmall {
 
 struct MonaFwdParams {
   CUtensorMap tmX;   // [B, N, D] bf16, box [1, 128, 64]
+  CUtensorMap tmX1;  // same tensor, box [1, r1, 64]: second token tile (rows 128 .. 128 + r1), r1 = ceil8(N - 128)
   CUtensorMap tmW;   // [128, D] bf16, box [128, 64]
+  int r1, stages;    // rows of the second token tile's box (0 if N <= 128); ring depth
   ngu_mona_derived d;
   bf16* h; bf16* hA; bf16* g;
   float* mean; float* rstd;
@@ -128,20 +129,22 @@ NGU_DEVINL void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// shifted sums of one 128-byte row piece set (64 bf16): S1 += x - s0, S2 += (x - s0)^2
-NGU_DEVINL void row_stats(uint32_t row_addr, float s0, float& S1, float& S2) {
+// shifted sums of one 128-byte row (64 bf16): S1 += x - s0, S2 += (x - s0)^2, as four independent packed (f32x2) chains
+struct RowAcc { float2 s1[2], s2[2]; };
+NGU_DEVINL void row_stats(uint32_t row_addr, uint32_t rot, float2 ms0, RowAcc& A) {
   uint4 ch[8];
+  // the order of the pieces of a row is irrelevant for the sums; the rotation by the row index makes the 8 lanes of a
+  // quarter-warp read 8 different 16-byte bank groups (row pitch = 128 B: unrotated, every lane would hit the same one)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) lds128(ch[j], row_addr + j * 16);   // swizzle only permutes the pieces of a row: order is irrelevant
+  for (int j = 0; j < 8; ++j) lds128(ch[j], row_addr + ((uint32_t(j) ^ rot) << 4));
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint32_t w[4] = {ch[j].x, ch[j].y, ch[j].z, ch[j].w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack_bf16x2(w[i]);
-      const float a = f.x - s0, b = f.y - s0;
-      S1 += a; S2 = fmaf(a, a, S2);
-      S1 += b; S2 = fmaf(b, b, S2);
+      const float2 d = fadd2(bf16pair_to_float2(w[i]), ms0);
+      A.s1[i & 1] = fadd2(A.s1[i & 1], d);
+      A.s2[i & 1] = ffma2(d, d, A.s2[i & 1]);
     }
   }
 }
@@ -153,7 +156,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mona_fwd_stage_kernel(const __
   uint8_t* gb = smem_raw + (base - smem_u32(smem_raw));
   const int HW = p.H * p.W, HWp = (HW + 15) & ~15;
   const uint32_t tileB = uint32_t(HWp) * 128u;
-  const uint32_t oPb = kRingStages * kRingStage;
+  const int r1 = p.r1;
+  const uint32_t stageB = uint32_t(2 * kBox + r1 * 128);      // x tile 0 | x tile 1 (r1 rows) | Wab k-block
+  const int nst = p.stages;
+  const uint32_t oPb = uint32_t(nst) * stageB;
   const uint32_t oZs = oPb + C * C * 2;
   const uint32_t oHs = oZs + tileB;
   const uint32_t oSmall = oHs + 2 * tileB;
@@ -163,12 +169,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mona_fwd_stage_kernel(const __
   FwdSmall& sm = *reinterpret_cast<FwdSmall*>(gb + oSmall);
   const uint32_t sBar = base + oBar;
   auto full_bar = [&](int s) { return sBar + 8u * s; };
-  auto empty_bar = [&](int s) { return sBar + 8u * (2 + s); };
-  auto tfull_bar = [&](int a) { return sBar + 8u * (4 + a); };
-  auto tempty_bar = [&](int a) { return sBar + 8u * (6 + a); };
-  auto hsfull_bar = [&](int b) { return sBar + 8u * (8 + b); };
-  auto hsempty_bar = [&](int b) { return sBar + 8u * (10 + b); };
-  const uint32_t sTmemPtr = sBar + 8u * 12;
+  auto empty_bar = [&](int s) { return sBar + 8u * (kMaxRingStages + s); };
+  auto tfull_bar = [&](int a) { return sBar + 8u * (2 * kMaxRingStages + a); };
+  auto tempty_bar = [&](int a) { return sBar + 8u * (2 * kMaxRingStages + 2 + a); };
+  auto hsfull_bar = [&](int b) { return sBar + 8u * (2 * kMaxRingStages + 4 + b); };
+  auto hsempty_bar = [&](int b) { return sBar + 8u * (2 * kMaxRingStages + 6 + b); };
+  const uint32_t sTmemPtr = sBar + 8u * (2 * kMaxRingStages + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.D / 64;
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mona_fwd_stage_kernel(const __
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmX);
     tma_prefetch_desc(&p.tmW);
-    for (int s = 0; s < kRingStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 5); }
+    for (int s = 0; s < nst; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 5); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4);
       mbar_init(hsfull_bar(a), 4); mbar_init(hsempty_bar(a), 1);
@@ -209,15 +215,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mona_fwd_stage_kernel(const __
     for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t st = base + s * kRingStage;
+        const uint32_t st = base + s * stageB;
         if (elect_one()) {
-          mbar_arrive_expect_tx(full_bar(s), tile1 ? 3 * kBox : 2 * kBox);
+          mbar_arrive_expect_tx(full_bar(s), stageB);
           tma_load_3d(st, &p.tmX, full_bar(s), kb * 64, 0, img, kEvictFirst);
-          if (tile1) tma_load_3d(st + kBox, &p.tmX, full_bar(s), kb * 64, 128, img, kEvictFirst);
-          tma_load_2d(st + 2 * kBox, &p.tmW, full_bar(s), kb * 64, 0, kEvictLast);
+          if (tile1) tma_load_3d(st + kBox, &p.tmX1, full_bar(s), kb * 64, 128, img, kEvictFirst);
+          tma_load_2d(st + kBox + r1 * 128, &p.tmW, full_bar(s), kb * 64, 0, kEvictLast);
         }
         __syncwarp();
-        if (++s == kRingStages) { s = 0; ph ^= 1u; }
+        if (++s == nst) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -234,9 +240,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mona_fwd_stage_kernel(const __
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint64_t a0 = a_base + uint64_t((s * kRingStage) >> 4);
+        const uint64_t a0 = a_base + uint64_t((s * stageB) >> 4);
         const uint64_t a1 = a0 + uint64_t(kBox >> 4);
-        const uint64_t bd = a0 + uint64_t((2 * kBox) >> 4);
+        const uint64_t bd = a0 + uint64_t((kBox + r1 * 128) >> 4);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss(d0, a0 + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mona_fwd_stage_kernel(const __
           if (kb == nkb - 1) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
-        if (++s == kRingStages) { s = 0; ph ^= 1u; }
+        if (++s == nst) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp < 6) {
@@ -260,27 +266,32 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mona_fwd_stage_kernel(const __
     int it = 0;
     for (int img = blockIdx.x; img < p.B; img += gridDim.x, ++it) {
       const int acc = it & 1;
-      float s0a = 0.f, s0b = 0.f, S1a = 0.f, S2a = 0.f, S1b = 0.f, S2b = 0.f;
+      float s0a = 0.f, s0b = 0.f;
+      RowAcc Aa, Ab;
+      Aa.s1[0] = Aa.s1[1] = Aa.s2[0] = Aa.s2[1] = Ab.s1[0] = Ab.s1[1] = Ab.s2[0] = Ab.s2[1] = make_float2(0.f, 0.f);
+      const bool row1 = tile1 && r < r1;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_bar(s), ph);
-        const uint32_t ra = base + s * kRingStage + uint32_t(r) * 128u;
+        const uint32_t ra = base + s * stageB + uint32_t(r) * 128u;
         if (kb == 0) {
           // first logical element of the row lives in physical 16-byte piece (r & 7)
           uint32_t w0, w1;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(ra + (uint32_t(r & 7) << 4)));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(ra + kBox + (uint32_t(r & 7) << 4)));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(ra + (row1 ? kBox : 0) + (uint32_t(r & 7) << 4)));
           s0a = unpack_bf16x2(w0).x;
           s0b = unpack_bf16x2(w1).x;
         }
-        row_stats(ra, s0a, S1a, S2a);
-        if (tile1) row_stats(ra + kBox, s0b, S1b, S2b);
+        row_stats(ra, uint32_t(r & 7), make_float2(-s0a, -s0a), Aa);
+        if (row1) row_stats(ra + kBox, uint32_t(r & 7), make_float2(-s0b, -s0b), Ab);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar(s));
-        if (++s == kRingStages) { s = 0; ph ^= 1u; }
+        if (++s == nst) { s = 0; ph ^= 1u; }
       }
       if (warp == 2) NGU_FPROF(24 + it * 3);
       float mu[2], rs[2];
       {
+        const float S1a = (Aa.s1[0].x + Aa.s1[0].y) + (Aa.s1[1].x + Aa.s1[1].y), S2a = (Aa.s2[0].x + Aa.s2[0].y) + (Aa.s2[1].x + Aa.s2[1].y);
+        const float S1b = (Ab.s1[0].x + Ab.s1[0].y) + (Ab.s1[1].x + Ab.s1[1].y), S2b = (Ab.s2[0].x + Ab.s2[0].y) + (Ab.s2[1].x + Ab.s2[1].y);
         const float ma = S1a * invD, mb = S1b * invD;
         mu[0] = s0a + ma; mu[1] = s0b + mb;
         rs[0] = rsqrtf(fmaxf(S2a * invD - ma * ma, 0.f) + p.eps);
@@ -372,7 +383,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mona_fwd_stage_kernel(const __
         gbp[c] = __float2bfloat16_rn(v);
       }
       for (int x0 = grp * kSW; x0 < p.W; x0 += (kConvThreads / C) * kSW) {
-        stencil_stream<false>(hs, k, bias, x0, p.H, p.W, c, [&](int y, const float (&a)[kSW]) {
+        stencil_stream_x2<false>(hs, k, bias, x0, p.H, p.W, c, [&](int y, const float (&a)[kSW]) {
 #pragma unroll
           for (int j = 0; j < kSW; ++j)
             if (x0 + j < p.W) zs[swz(y * p.W + x0 + j, c)] = __float2bfloat16_rn(a[j]);
@@ -413,9 +424,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mona_fwd_stage_kernel(const __
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-size_t fwd_smem_bytes(int HW) {
+size_t fwd_fixed_smem_bytes(int HW) {
   const size_t HWp = (size_t(HW) + 15) & ~size_t(15);
-  return 1024 + kRingStages * kRingStage + C * C * 2 + 3 * HWp * 128 + ((sizeof(FwdSmall) + 15) & ~size_t(15)) + 8 * 12 + 16;
+  return 1024 + C * C * 2 + 3 * HWp * 128 + ((sizeof(FwdSmall) + 15) & ~size_t(15)) + 8 * (2 * kMaxRingStages + 8) + 16;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -505,7 +516,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) mona_bwd_stage_kernel(const __
 #pragma unroll
       for (int t = 0; t < 49; ++t) k[t] = s.kc[t][c];
       for (int x0 = grp * kSW; x0 < p.W; x0 += (kBwdThreads / C) * kSW) {
-        stencil_stream<false>(hs, k, s.bc[c], x0, p.H, p.W, c, [&](int y, const float (&a)[kSW]) {
+        stencil_stream_x2<false>(hs, k, s.bc[c], x0, p.H, p.W, c, [&](int y, const float (&a)[kSW]) {
 #pragma unroll
           for (int j = 0; j < kSW; ++j)
             if (x0 + j < p.W) zs[swz(y * p.W + x0 + j, c)] = __float2bfloat16_rn(a[j]);
@@ -583,7 +594,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) mona_bwd_stage_kernel(const __
 #pragma unroll
       for (int t = 0; t < 49; ++t) G[t] = 0.f;
       float dsum = 0.f;
-      float dzb[7][kSW];
+      float dzb[7][kSW];   // slot s_ <-> dz row yy - 3 + s_
       auto load_dz = [&](int y, float (&dst)[kSW]) {
 #pragma unroll
         for (int j = 0; j < kSW; ++j) {
@@ -603,7 +614,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) mona_bwd_stage_kernel(const __
         }
 #pragma unroll
         for (int s_ = 0; s_ < 7; ++s_) {
-          const int ky = 6 - s_;
+          const int ky = 6 - s_;   // h row yy = dz row (yy - 3 + s_) + ky - 3
 #pragma unroll
           for (int kx = 0; kx < 7; ++kx) {
             float a = G[ky * 7 + kx];
@@ -634,7 +645,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) mona_bwd_stage_kernel(const __
 #pragma unroll
       for (int t = 0; t < 49; ++t) k[t] = s.kc[t][c];
       for (int x0 = grp * kSW; x0 < p.W; x0 += (kBwdThreads / C) * kSW) {
-        stencil_stream<true>(zs, k, 0.f, x0, p.H, p.W, c, [&](int y, const float (&a)[kSW]) {
+        stencil_stream_x2<true>(zs, k, 0.f, x0, p.H, p.W, c, [&](int y, const float (&a)[kSW]) {
 #pragma unroll
           for (int j = 0; j < kSW; ++j)
             if (x0 + j < p.W) {
@@ -716,7 +727,7 @@ size_t bwd_smem_bytes(int HW) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// finish: workspace -> parameter gradients.  blocks [0, D/64): 64 columns k each (4 threads per k over c-quarters);
+// finish: workspace -> parameter gradients.  blocks [0, D/16): 16 columns k each (16 threads per k, 4 channels each);
 // last block: stage (conv) gradients.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mona_finish_kernel(ngu_mona_params p, ngu_mona_grads g, const float* __restrict__ ws, int D) {
@@ -725,19 +736,22 @@ __global__ void __launch_bounds__(256) mona_finish_kernel(ngu_mona_params p, ngu
   const float* Sz = Gacc + 49 * C;
   const float* Sdh = Sz + C;
   const float* Tmu = Sdh + C;
-  if (int(blockIdx.x) < D / 64) {
-    __shared__ float red[3][4][64];
-    const int kl = threadIdx.x & 63, cq = threadIdx.x >> 6;
-    const int k = blockIdx.x * 64 + kl;
+  if (int(blockIdx.x) < D / 16) {
+    // 16 columns k per block, 16 threads per k (4 bottleneck channels each): short dependent chains, 49 blocks at D = 768
+    __shared__ float red[3][16][17];
+    const int kl = threadIdx.x & 15, cq = threadIdx.x >> 4;
+    const int k = blockIdx.x * 16 + kl;
     const float wk = p.ln_w[k], bk = p.ln_b[k], gk = p.gamma[k], gxk = p.gammax[k];
     const float wg = wk * gk, bg = bk * gk;
-    const float* Gk = ws + size_t(k) * 128;
+    const float4 gx4 = *reinterpret_cast<const float4*>(ws + size_t(k) * 128 + cq * 4);
+    const float4 gs4 = *reinterpret_cast<const float4*>(ws + size_t(k) * 128 + C + cq * 4);
+    const float gxv[4] = {gx4.x, gx4.y, gx4.z, gx4.w}, gsv[4] = {gs4.x, gs4.y, gs4.z, gs4.w};
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 4
-    for (int ci = 0; ci < 16; ++ci) {
-      const int cc = cq * 16 + ci;
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      const int cc = cq * 4 + ci;
       const float w1 = p.w1[size_t(cc) * D + k];
-      const float gx = Gk[cc], gxs = Gk[C + cc] - Tmu[cc];
+      const float gx = gxv[ci], gxs = gsv[ci] - Tmu[cc];
       const float sd = Sdh[cc];
       // dW1[c][k] = sum_r dh[r][c] u[r][k],  u = x (rstd*w*gamma + gammax) + (b*gamma - mean*rstd*w*gamma)
       g.dw1[size_t(cc) * D + k] += wg * gxs + gxk * gx + bg * sd;
@@ -748,9 +762,10 @@ __global__ void __launch_bounds__(256) mona_finish_kernel(ngu_mona_params p, ngu
     red[0][cq][kl] = s0; red[1][cq][kl] = s1; red[2][cq][kl] = s2;
     __syncthreads();
     if (cq == 0) {
-      s0 = red[0][0][kl] + red[0][1][kl] + red[0][2][kl] + red[0][3][kl];   // sum_r du[r][k]
-      s1 = red[1][0][kl] + red[1][1][kl] + red[1][2][kl] + red[1][3][kl];   // sum_r du[r][k] x[r][k]
-      s2 = red[2][0][kl] + red[2][1][kl] + red[2][2][kl] + red[2][3][kl];   // sum_r du[r][k] xhat[r][k]
+      s0 = s1 = s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { s0 += red[0][i][kl]; s1 += red[1][i][kl]; s2 += red[2][i][kl]; }
+      // s0 = sum_r du[r][k], s1 = sum_r du[r][k] x[r][k], s2 = sum_r du[r][k] xhat[r][k]
       g.dgammax[k] += s1;
       g.dln_b[k] += gk * s0;
       g.dln_w[k] += gk * s2;
@@ -817,13 +832,19 @@ int mona_fwd_stage(const ngu_mona_stage_desc& d, cudaStream_t st) {
   int rc;
   if ((rc = make_tmap_3d_bf16(&p.tmX, d.x, d.B, d.N, d.D, d.D, uint64_t(d.N) * d.D, 128, 64, 1))) return rc;
   if ((rc = make_tmap_2d_bf16(&p.tmW, d.d.wab, 128, d.D, d.D, 128, 64, 1))) return rc;
+  p.r1 = d.N > 128 ? ((d.N - 128 + 7) & ~7) : 0;
+  if (p.r1 > 0) { if ((rc = make_tmap_3d_bf16(&p.tmX1, d.x, d.B, d.N, d.D, d.D, uint64_t(d.N) * d.D, p.r1, 64, 1))) return rc; }
+  else p.tmX1 = p.tmX;
+  const size_t stage_bytes = size_t(2 * kBox + p.r1 * 128), fixed = fwd_fixed_smem_bytes(d.H * d.W);
+  p.stages = int((size_t(227 * 1024) - fixed) / stage_bytes);
+  if (p.stages > kMaxRingStages) p.stages = kMaxRingStages;
+  if (p.stages < 2) { set_last_error("mona_fwd_stage: grid %dx%d leaves no room for the operand ring", d.H, d.W); return NGU_ERR_SHAPE; }
   p.d = d.d;
   p.h = reinterpret_cast<bf16*>(d.h); p.hA = reinterpret_cast<bf16*>(d.hA); p.g = reinterpret_cast<bf16*>(d.g);
   p.mean = d.mean; p.rstd = d.rstd;
   p.B = d.B; p.N = d.N; p.H = d.H; p.W = d.W; p.D = d.D; p.has_cls = d.has_cls;
   p.eps = d.eps; p.drop_p = d.drop_p; p.seed = d.seed; p.seed_ctr = seed_counter();
-  const int smem = int(fwd_smem_bytes(d.H * d.W));
-  if (smem > 227 * 1024) { set_last_error("mona_fwd_stage: %d B smem", smem); return NGU_ERR_SHAPE; }
+  const int smem = int(fixed + size_t(p.stages) * stage_bytes);
   cudaError_t e = cudaFuncSetAttribute(mona_fwd_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return cuda_status(e, "mona_fwd_stage attr");
   int grid = sm_count();
@@ -857,7 +878,7 @@ int mona_bwd_stage(const ngu_mona_stage_desc& d, cudaStream_t st) {
 
 int mona_finish(const ngu_mona_params& p, const ngu_mona_grads& g, const float* ws, int D, cudaStream_t st) {
   if ((D % 64) != 0 || ws == nullptr) { set_last_error("mona_finish: bad arguments"); return NGU_ERR_ARG; }
-  launch_pdl(mona_finish_kernel, dim3(D / 64 + 1), dim3(256), size_t(0), st, p, g, ws, D);
+  launch_pdl(mona_finish_kernel, dim3(D / 16 + 1), dim3(256), size_t(0), st, p, g, ws, D);
   return check_launch("mona_finish");
 }
 

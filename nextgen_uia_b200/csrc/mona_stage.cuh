@@ -89,6 +89,71 @@ NGU_DEVINL void stencil_stream(const bf16* in, const float (&k)[49], float bias,
   }
 }
 
+// ---- packed-fp32 variant (sm_100 FFMA2: two fp32 FMAs per instruction) -----------------------------------------
+// Same ownership as stencil_stream (one channel, 4-wide column strip, taps in registers); the two FMAs of an FFMA2 are two
+// ADJACENT output columns: the tap is a scalar operand (SASS broadcasts a 32-bit register: FFMA2 Rd, Rk.F32, Rwin.F32x2, Racc),
+// the window operand is the pair (win[i], win[i+1]).  Pairs starting at even and at odd window positions are kept as two
+// register arrays so no operand needs re-packing inside the tap loop.
+NGU_DEVINL float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)), "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+NGU_DEVINL float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+NGU_DEVINL float2 bf16pair_to_float2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+
+template <bool FLIP, typename Emit>
+NGU_DEVINL void stencil_stream_x2(const bf16* in, const float (&k)[49], float bias, int x0, int H, int W, int c, Emit emit) {
+  static_assert(kSW == 4, "two column pairs per strip");
+  float2 acc[7][2];
+#pragma unroll
+  for (int s_ = 0; s_ < 7; ++s_) acc[s_][0] = acc[s_][1] = make_float2(bias, bias);
+  for (int yy = 0; yy < H + 3; ++yy) {
+    if (yy < H) {
+      float win[kSW + 6];
+      const bf16* rowp = in + (yy * W) * C + c;
+#pragma unroll
+      for (int i = 0; i < kSW + 6; ++i) {
+        const int xx = x0 + i - 3;
+        win[i] = (unsigned(xx) < unsigned(W)) ? __bfloat162float(rowp[xx * C]) : 0.f;
+      }
+      float2 pe[5], po[4];   // pairs (win[i], win[i+1]) for even / odd i
+#pragma unroll
+      for (int m = 0; m < 5; ++m) pe[m] = make_float2(win[2 * m], win[2 * m + 1]);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) po[m] = make_float2(win[2 * m + 1], win[2 * m + 2]);
+#pragma unroll
+      for (int s_ = 0; s_ < 7; ++s_) {
+        const int ky = FLIP ? s_ : 6 - s_;   // slot s_ <-> output row yy - 3 + s_
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const float kv = k[ky * 7 + (FLIP ? 6 - kx : kx)];
+          const float2 kk = make_float2(kv, kv);
+          // output pair j covers columns (2j, 2j+1): window positions 2j + kx, 2j + kx + 1
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int i = 2 * j + kx;
+            acc[s_][j] = ffma2(kk, (i & 1) ? po[i >> 1] : pe[i >> 1], acc[s_][j]);
+          }
+        }
+      }
+    }
+    const int yo = yy - 3;
+    if (yo >= 0) {
+      const float a[kSW] = {acc[0][0].x, acc[0][0].y, acc[0][1].x, acc[0][1].y};
+      emit(yo, a);
+    }
+#pragma unroll
+    for (int s_ = 0; s_ < 6; ++s_) { acc[s_][0] = acc[s_ + 1][0]; acc[s_][1] = acc[s_ + 1][1]; }
+    acc[6][0] = acc[6][1] = make_float2(bias, bias);
+  }
+}
 
 }  // namespace mona_stage
 }  // namespace ngu

@@ -116,7 +116,7 @@ int sm_count() {
 
 bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("NGU_PDL"); v = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("NGU_PDL"); v = (e != nullptr && atoi(e) != 0) ? 1 : 0; }   // measured: PDL costs ~3 % on this step (r2 profiles), default off
   return v == 1;
 }
 

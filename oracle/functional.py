@@ -81,9 +81,11 @@ def vit_block(x, p, prefix, heads, lora=None, eps=1e-6):
     return x + F.linear(h, p[f"{prefix}mlp.fc2.weight"], p[f"{prefix}mlp.fc2.bias"])
 
 
-def encode_image(p, images, cfg, taps=None):
+def encode_image(p, images, cfg, taps=None, adapters=None):
     """open_clip TimmModel: patch_embed -> cat cls -> +pos -> blocks (each followed by Mona when injected,
-    mona.py:667-676) -> final norm -> CLS pool -> head.proj.  [pinned-dep knowledge for the trunk]"""
+    mona.py:667-676) -> final norm -> CLS pool -> head.proj.  [pinned-dep knowledge for the trunk]
+    `adapters`: optional list of callables (x [B,N,D], hw) -> [B,N,D], one per block, used INSTEAD of the restated Mona:
+    bench.py's reference arm passes the reference's own BatchFirstMonaWrapper modules here."""
     t = "visual.trunk."
     P = cfg["patch"]
     x = F.conv2d(images, p[f"{t}patch_embed.proj.weight"], p[f"{t}patch_embed.proj.bias"], stride=P)
@@ -93,7 +95,9 @@ def encode_image(p, images, cfg, taps=None):
     for i in range(cfg["depth"]):
         x = vit_block(x, p, f"{t}blocks.{i}.", cfg["heads"], cfg.get("lora"))
         mp = f"{t}blocks.{i}.mona.clip_mona."
-        if f"{mp}gamma" in p:
+        if adapters is not None:
+            x = adapters[i](x, (gh, gw))
+        elif f"{mp}gamma" in p:
             x = mona(x, p, mp, (gh, gw), True)
         if taps is not None:
             taps.append(x)

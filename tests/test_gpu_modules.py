@@ -681,6 +681,9 @@ def test_cuda_graph_step_matches_eager():
     ids = torch.randint(5, 1000, (4, 77), device=dev()); ids[:, 0] = 2; ids[:, -1] = 3
     _, te = _small_trainer()
     le = [float(te.micro_step(images, ids)) for _ in range(3)]
+    _, te2 = _small_trainer()
+    for _ in range(3):
+        te2.micro_step(images, ids)
     _, tg = _small_trainer()
     p0 = tg.buckets.flat_param.clone()
     tg.capture(images, ids)
@@ -688,8 +691,12 @@ def test_cuda_graph_step_matches_eager():
     lg = [float(tg.replay(images, ids)) for _ in range(3)]
     assert tg.optimizer.updates == 3 and te.optimizer.updates == 3
     assert max(abs(a - b) for a, b in zip(le, lg)) < 2e-3 * abs(le[0]), (le, lg)
-    d = (tg.buckets.flat_param - te.buckets.flat_param).abs().max() / (te.buckets.flat_param - p0).abs().max()
-    assert float(d) < 2e-2, float(d)      # relative to the size of the 3-step update (atomics order differs run to run)
+    # Adam normalises every element's update to ~lr, so elements whose gradient is rounding noise flip sign between ANY two
+    # runs (fp32 atomics order): measure the graph-vs-eager distance against the eager-vs-eager distance of the same update
+    upd = (te.buckets.flat_param - p0).norm()
+    d_ee = float((te2.buckets.flat_param - te.buckets.flat_param).norm() / upd)
+    d_ge = float((tg.buckets.flat_param - te.buckets.flat_param).norm() / upd)
+    assert d_ge < max(3 * d_ee, 5e-2), (d_ge, d_ee)
 
 
 def test_nonfinite_loss_poisons_the_whole_accumulation_window():
@@ -722,3 +729,23 @@ def test_text_padding_flag_is_lazy_in_train_mode():
     model.eval()
     with pytest.raises(NotImplementedError):
         model.encode_text(ids)
+
+
+@pytest.mark.parametrize("name", ["mona_cls", "mona_freq"])
+def test_mona_unfused_bf16_path_still_matches_golden(golden, name, monkeypatch):
+    """NGU_MONA_FUSED=0 keeps the round-1 kernel sequence (LN-mix -> GEMM -> stage -> GEMM; used for grids above 16x16, the
+    noise-aware variants and as the A/B switch of the fused path): same goldens, same tolerances."""
+    monkeypatch.setenv("NGU_MONA_FUSED", "0")
+    import src.adapters as A
+    from src.adapters import BatchFirstMonaWrapper
+    cls = A.FreqEnhancedMona if name == "mona_freq" else A.BaselineMona
+    g = golden(name)
+    m = BatchFirstMonaWrapper(cls(g["x"].shape[-1], 64))
+    m.load_state_dict(g["state"], strict=True)
+    m = m.to(dev()).eval()
+    x = g["x"].to(dev(), torch.bfloat16).requires_grad_(True)
+    y = m(x, g["hw"] if g["has_cls"] else None)
+    (y * g["gy"].to(dev(), torch.bfloat16)).sum().backward()
+    assert relerr(y, g["y"]) < TOL[torch.bfloat16] and relerr(x.grad, g["dx"]) < GTOL[torch.bfloat16]
+    for k, p in m.named_parameters():
+        assert relerr(p.grad, g["grads"][k]) < GTOL[torch.bfloat16], k

@@ -233,6 +233,8 @@ int ngu_mona_finish(const ngu_mona_params* p, const ngu_mona_grads* g, const flo
  * src/third_party/openai_clip/model.py:195-197.  q/k/v/o are addressed as
  * ptr + b*bs + n*ts + head*dh (+ d), so the fused timm qkv buffer [B,N,3,H,dh], separate q/k/v
  * tensors and the sequence-first [N,B,D] layout are all expressible.  lse: fp32 [B,H,N].
+ * bf16, head dim 64, packed qkv buffer: tcgen05 kernels — N <= 256 whole-sequence tiles (attention_tc.cu), 256 < N <= 1024
+ * key-tiled with online softmax (attention_long.cu); other layouts / fp32 check mode: CUDA cores (attention_simt.cu).
  */
 typedef struct ngu_attn_desc {
   const void* q; int64_t q_bs, q_ts;
@@ -250,6 +252,8 @@ typedef struct ngu_attn_desc {
   const int* kv_len;          /* NULL = every key valid: [B] device ints, keys j >= kv_len[b] are masked
                                  (right-padded token batches: the HF attention_mask of BiomedCLIP's text tower,
                                  open_clip HFTextEncoder.forward `attn_mask = (x != pad_token_id)`); 1 <= kv_len[b] <= S */
+  float* ws;                  /* backward, bf16 packed layout with 256 < N <= 1024 (ViT-L/14@336: 577, ViT-B/16@352: 485): fp32 workspace
+                                 of B*H*N elements (delta = rowsum(dO * O)) for the tiled tcgen05 kernels; NULL selects the CUDA-core path */
 } ngu_attn_desc;
 int ngu_attn_fwd(const ngu_attn_desc* d, void* stream);
 int ngu_attn_bwd(const ngu_attn_desc* d, void* stream);

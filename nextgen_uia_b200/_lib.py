@@ -116,7 +116,7 @@ class AttnDesc(ctypes.Structure):
                 ("lse", _c_void_p), ("d_o", _c_void_p),
                 ("dq", _c_void_p), ("dk", _c_void_p), ("dv", _c_void_p),
                 ("B", _c_int), ("H", _c_int), ("N", _c_int), ("S", _c_int), ("dh", _c_int),
-                ("scale", _c_float), ("causal", _c_int), ("dtype", _c_int), ("impl", _c_int), ("kv_len", _c_void_p)]
+                ("scale", _c_float), ("causal", _c_int), ("dtype", _c_int), ("impl", _c_int), ("kv_len", _c_void_p), ("ws", _c_void_p)]
 
 
 class InfoNceDesc(ctypes.Structure):

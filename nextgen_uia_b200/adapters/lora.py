@@ -156,6 +156,20 @@ class PlainMultiheadAttentionLoRA(nn.Module):
             causal = True
         if key_padding_mask is not None:
             raise NotImplementedError("key_padding_mask is not used on the reference hot path")
+        if (not causal and batched and query is key and key is value and self.head_dim == 64
+                and query.dtype == torch.bfloat16 and query.transpose(0, 1).is_contiguous()):
+            # Self-attention on a sequence-first VIEW of batch-first memory (what the CLIP vision tower hands its blocks,
+            # model.py:250): project on the batch-first rows and pack q | k | v so the attention core runs on the tcgen05
+            # kernels (attention_tc.cu / attention_long.cu) instead of the strided CUDA-core path; no layout copies.
+            from ..biomedclip import _PackedAttnFunction
+            xb = query.transpose(0, 1)                                  # [B, L, D] contiguous
+            Bn, L, D = xb.shape
+            qkv = torch.cat([_apply_linear(self.q_proj, xb), _apply_linear(self.k_proj, xb), _apply_linear(self.v_proj, xb)], -1)
+            o = _PackedAttnFunction.apply(qkv.view(Bn * L, 3 * D), Bn, L, self.num_heads, None)
+            o = _apply_linear(self.proj, o.view(Bn, L, D)).transpose(0, 1)
+            if self.batch_first:
+                return o.transpose(1, 0), None
+            return o, None
         q = _apply_linear(self.q_proj, query)
         k = _apply_linear(self.k_proj, key)
         v = _apply_linear(self.v_proj, value)

@@ -60,12 +60,14 @@ int ngu_attn_fwd(const ngu_attn_desc* d, void* stream) {
   NGU_NONNULL(d, "ngu_attn_fwd");
   if (int rc = attn_validate(*d, "ngu_attn_fwd", false)) return rc;
   if ((d->impl == 0 || d->impl == 2) && attn_tc_supported(*d, false)) return attn_fwd_tc(*d, NGU_STREAM);
+  if (d->impl == 0 && attn_long_supported(*d, false)) return attn_fwd_long(*d, NGU_STREAM);
   return attn_fwd_simt(*d, NGU_STREAM);
 }
 int ngu_attn_bwd(const ngu_attn_desc* d, void* stream) {
   NGU_NONNULL(d, "ngu_attn_bwd");
   if (int rc = attn_validate(*d, "ngu_attn_bwd", true)) return rc;
   if (d->impl == 0 && attn_tc_supported(*d, true)) return attn_bwd_tc(*d, NGU_STREAM);
+  if (d->impl == 0 && attn_long_supported(*d, true)) return attn_bwd_long(*d, NGU_STREAM);
   return attn_bwd_simt(*d, NGU_STREAM);
 }
 

@@ -57,6 +57,7 @@ struct AttnTcParams {
   int B, H, N;
   float scale;
   const int* kv_len;  // forward: per-batch number of valid keys (NULL = N)
+  int causal;         // forward (per-tile kernel): key j is visible to query i iff j <= i (CLIP text tower, model.py:344-350)
 };
 
 NGU_DEVINL uint64_t desc_kmajor(uint32_t addr) { return make_smem_desc_sw128(addr, 16, 1024); }
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
     const int cb = hf ? nc0 : 0, ce = hf ? nch : nc0;
     const uint32_t my_red = sRed + 4u * uint32_t(hf * 128 + rt), other_red = sRed + 4u * uint32_t((hf ^ 1) * 128 + rt);
     float sum = 0.f, mx = -INFINITY;
+    if (p.causal) Lk = min(Lk, min(r, N - 1) + 1);   // per-row key limit: the causal mask is one more upper bound on the key index
     if (live) {
       mbar_wait(bar_s, 0);
       tc_fence_after();
@@ -1053,7 +1055,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
 bool is_packed(const ngu_attn_desc& d) {
   const int64_t D = int64_t(d.H) * d.dh;
   const char* q = reinterpret_cast<const char*>(d.q);
-  return d.N == d.S && !d.causal && d.q_ts == 3 * D && d.k_ts == 3 * D && d.v_ts == 3 * D && d.o_ts == D &&
+  return d.N == d.S && d.q_ts == 3 * D && d.k_ts == 3 * D && d.v_ts == 3 * D && d.o_ts == D &&
          d.q_bs == int64_t(d.N) * 3 * D && d.k_bs == d.q_bs && d.v_bs == d.q_bs && d.o_bs == int64_t(d.N) * D &&
          reinterpret_cast<const char*>(d.k) == q + D * 2 && reinterpret_cast<const char*>(d.v) == q + 4 * D;
 }
@@ -1082,6 +1084,7 @@ int fill_params(const ngu_attn_desc& d, AttnTcParams& p, bool bwd) {
   p.B = d.B; p.H = d.H; p.N = d.N;
   p.scale = d.scale;
   p.kv_len = d.kv_len;
+  p.causal = d.causal;
   return NGU_OK;
 }
 
@@ -1096,6 +1099,7 @@ extern "C" int ngu_debug_attn_trace(void* out, int reset) {
 
 bool attn_tc_supported(const ngu_attn_desc& d, bool bwd) {
   if (d.dtype != NGU_BF16 || d.dh != DH || d.N > 2 * TILE || !is_packed(d)) return false;
+  if (d.causal && bwd) return false;    // causal towers are frozen on this path (CLIP text): forward only on tensor cores
   if (bwd) {
     const int64_t D = int64_t(d.H) * d.dh;
     const char* dq = reinterpret_cast<const char*>(d.dq);
@@ -1117,7 +1121,7 @@ int attn_fwd_tc(const ngu_attn_desc& d, cudaStream_t st) {
   // desc.impl = 2 selects the persistent two-group kernel (164 us: its two groups fall into lock-step on the MUFU pipe; kept as the
   // starting point for a single-group four-threads-per-row variant).
   static const int mode = [] { const char* e = getenv("NGU_ATTN_FWD"); return e ? atoi(e) : 0; }();
-  if ((mode == 0 && d.impl != 2) || d.kv_len != nullptr) {   // key padding: only the per-tile kernel masks by kv_len
+  if ((mode == 0 && d.impl != 2) || d.kv_len != nullptr || d.causal) {   // key padding / causal: only the per-tile kernel masks
     launch_pdl(attn_fwd_tc_kernel, dim3(d.B * d.H * ((d.N + TILE - 1) / TILE)), dim3(kFwdThreads), size_t(kFwdSmem), st, p);
     return check_launch("attn_fwd_tc");
   }

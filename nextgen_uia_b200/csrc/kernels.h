@@ -28,6 +28,9 @@ int attn_bwd_simt(const ngu_attn_desc& d, cudaStream_t s);
 bool attn_tc_supported(const ngu_attn_desc& d, bool bwd);
 int attn_fwd_tc(const ngu_attn_desc& d, cudaStream_t s);
 int attn_bwd_tc(const ngu_attn_desc& d, cudaStream_t s);
+bool attn_long_supported(const ngu_attn_desc& d, bool bwd);
+int attn_fwd_long(const ngu_attn_desc& d, cudaStream_t s);
+int attn_bwd_long(const ngu_attn_desc& d, cudaStream_t s);
 int infonce_normalize(const void* x, float* xhat, float* norm, int B, int E, int dtype, cudaStream_t s);
 int infonce_core(const ngu_infonce_desc& d, cudaStream_t s);
 int infonce_normalize_bwd(const float* dxhat, const float* xhat, const float* norm, const float* gscale, void* dx, int B, int E, int dtype, cudaStream_t s);

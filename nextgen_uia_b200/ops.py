@@ -349,6 +349,9 @@ def attn_bwd_packed(qkv, o, lse, do, B, N, H, dh, *, causal=False, impl=0, kv_le
     d = _attn_desc(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B, H, N, N, dh, st, dh ** -0.5, causal, impl, kv_len)
     d.lse, d.d_o = lse.data_ptr(), do.data_ptr()
     d.dq, d.dk, d.dv = dqkv.data_ptr(), dqkv[:, D:].data_ptr(), dqkv[:, 2 * D:].data_ptr()
+    if N > 256 and qkv.dtype == torch.bfloat16 and dh == 64:
+        ws = torch.empty(B * H * N, device=qkv.device, dtype=torch.float32)    # delta of the key-tiled tcgen05 backward
+        d.ws = ws.data_ptr()
     L.check(L.lib().ngu_attn_bwd(_byref(d), _stream()), "ngu_attn_bwd")
     return dqkv
 

@@ -102,7 +102,7 @@ def test_layernorm_strided_rows(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("B,N,H,causal", [(2, 197, 12, False), (3, 77, 12, False), (2, 50, 4, True)])
+@pytest.mark.parametrize("B,N,H,causal", [(2, 197, 12, False), (3, 77, 12, False), (2, 50, 4, True), (3, 77, 8, True), (2, 200, 2, True)])
 def test_attention(dtype, B, N, H, causal):
     from nextgen_uia_b200 import ops
     torch.manual_seed(4)
@@ -133,8 +133,9 @@ def test_attention_tc_persistent_paths(B, N, H):
     qkv = torch.randn(B * N, 3 * D).to(dev(), torch.bfloat16)
     do = torch.randn(B * N, D).to(dev(), torch.bfloat16)
     o, lse = ops.attn_fwd_packed(qkv, B, N, H, dh, impl=0)
-    o1, lse1 = ops.attn_fwd_packed(qkv, B, N, H, dh, impl=1)
-    assert relerr(o, o1) < 1e-2 and relerr(lse, lse1) < 1e-4
+    if N <= 640:                                     # the CUDA-core kernel's shared-memory score row ends there
+        o1, lse1 = ops.attn_fwd_packed(qkv, B, N, H, dh, impl=1)
+        assert relerr(o, o1) < 1e-2 and relerr(lse, lse1) < 1e-4
     o2, lse2 = ops.attn_fwd_packed(qkv, B, N, H, dh, impl=2)
     assert relerr(o2, o1) < 1e-2 and relerr(lse2, lse1) < 1e-4
     g = ops.attn_bwd_packed(qkv, o1, lse1, do, B, N, H, dh, impl=0)
@@ -283,25 +284,34 @@ def test_patchify_matches_unfold(dtype, R, P):
     assert float(out[:, K:].float().abs().max()) == 0.0 if out.shape[1] > K else True
 
 
-@pytest.mark.parametrize("N", [485, 577])
+@pytest.mark.parametrize("N", [577, 485, 257, 640, 1024])
 def test_attention_long_sequences_bf16(N):
-    """Sequence lengths of configs 4 / 5 (ViT-L/14@336: 577 tokens, ViT-B/16@352: 485): beyond the tcgen05 kernels' 256,
-    served by the CUDA-core kernels; the backward runs in its two-phase shared-memory mode."""
-    from nextgen_uia_b200 import ops
+    """Sequence lengths of configs 4 / 5 (ViT-L/14@336: 577 tokens, ViT-B/16@352: 485) and the edges of the range: the
+    key-tiled tcgen05 kernels of attention_long.cu (online softmax forward, FlashAttention-2-style dQ and dK/dV backward).
+    Output, LSE and all three gradients vs SDPA in fp64; the CUDA-core kernels (impl = 1) must agree as well, which also
+    proves the default dispatch took a different (the tensor-core) path."""
+    from nextgen_uia_b200 import ops, _lib as L
     torch.manual_seed(15)
     B, H, dh = 2, 3, 64
     D = H * dh
     qkv = torch.randn(B * N, 3 * D).to(dev(), torch.bfloat16)
     do = torch.randn(B * N, D).to(dev(), torch.bfloat16)
+    n0 = L.launch_count()
     o, lse = ops.attn_fwd_packed(qkv, B, N, H, dh)
     dqkv = ops.attn_bwd_packed(qkv, o, lse, do, B, N, H, dh)
+    assert L.launch_count() - n0 == 4          # fwd + (delta, dQ, dK/dV): the tiled tcgen05 path, not the 2-launch CUDA-core one
     t = qkv.double().cpu().requires_grad_(True)
     q, k, v = t.view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, D)
     (dref,) = torch.autograd.grad((ref * do.double().cpu()).sum(), t)
+    lse_ref = torch.logsumexp((q @ k.transpose(-1, -2)) * dh ** -0.5, -1)          # [B, H, N]
     assert relerr(o, ref) < 1e-2
+    assert float((lse.double().cpu() - lse_ref.detach()).abs().max()) < 2e-2
     for sl in (slice(0, D), slice(D, 2 * D), slice(2 * D, 3 * D)):
         assert relerr(dqkv[:, sl], dref[:, sl]) < 1.5e-2
+    if N <= 640:                                     # the CUDA-core kernel's shared-memory score row ends there
+        o1, lse1 = ops.attn_fwd_packed(qkv, B, N, H, dh, impl=1)
+        assert relerr(o, o1) < 1e-2
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -7,12 +7,17 @@ import bench
 from nextgen_uia_b200 import dp
 from torch.profiler import profile, ProfilerActivity
 
-method = sys.argv[1] if len(sys.argv) > 1 else "mona"
+method = sys.argv[1] if len(sys.argv) > 1 else "mona"      # mona | lora | cfg4
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda:0")
-model = bench.build_model(method, 12, dev)
-tr = dp.Trainer(model)
-im, ids = bench.synthetic_batch(256, 1)
+if method == "cfg4":
+    model = bench.build_clip_model(4, dev)
+    tr = dp.Trainer(model)
+    im, ids = torch.rand(64, 3, 336, 336), bench.clip_tokens(64, 1)
+else:
+    model = bench.build_model(method, 12, dev)
+    tr = dp.Trainer(model)
+    im, ids = bench.synthetic_batch(256, 1)
 im, ids = im.to(dev), ids.to(dev)
 for _ in range(4):
     tr.micro_step(im, ids)

@@ -36,11 +36,24 @@ m = tr.model
 tr.buckets.enabled = True
 fi = m.encode_image(images[sl].to(dev)); ft = m.encode_text(ids[sl].to(dev))
 loss = tr.criterion(fi, ft)
-loss.backward()
+# fp32 check mode: the full chain (all-gathered InfoNCE backward + SUM all-reduce) against the oracle at 1e-3.
+# bf16: with random weights every image maps to nearly the same feature, so d(InfoNCE)/d(feature) is a difference of
+# near-equal vectors and ANY bf16 tower amplifies its 4e-3 feature rounding ~50x in that cotangent; the gradient
+# plumbing (per-rank backward, bucketed SUM all-reduce) is therefore checked with a well-conditioned fixed cotangent G
+# on the image features, the InfoNCE value with the global loss.
+G = torch.randn(Bl * world, 512, generator=torch.Generator().manual_seed(3))
+if dtype == torch.float32:
+    loss.backward()
+else:
+    (fi.float() * G[sl].to(dev)).sum().backward()
 tr.buckets.wait()
 torch.cuda.synchronize()
 if rank == 0:
     lo, _, _, _, go = OF.loss_and_grads(sd, images, ids, cfg, trainable)
+    if dtype != torch.float32:
+        p64 = {k: (v.double().clone().requires_grad_(k in trainable) if v.is_floating_point() else v) for k, v in sd.items()}
+        fo = OF.encode_image(p64, images.double(), cfg)
+        go = dict(zip(trainable, torch.autograd.grad((fo * G.double()).sum(), [p64[k] for k in trainable])))
     num = den = 0.0
     worst = ("", 0.0)
     for n, p in model.named_parameters():
@@ -51,7 +64,7 @@ if rank == 0:
             if e > worst[1]: worst = (n, e)
     print(f"[{dtype}] world={world} global loss {float(loss):.6f} vs oracle {float(lo):.6f} rel {abs(float(loss)-float(lo))/float(lo):.2e}; "
           f"grad L2 relerr {(num/den)**0.5:.3e}; worst tensor {worst}")
-    tol_l, tol_g = (1e-5, 1e-3) if dtype == torch.float32 else (1e-2, 0.15)
+    tol_l, tol_g = (1e-5, 1e-3) if dtype == torch.float32 else (1e-2, 3e-2)
     ok = abs(float(loss) - float(lo)) / float(lo) < tol_l and (num / den) ** 0.5 < tol_g
     print("DP_CHECK_OK" if ok else "DP_CHECK_FAIL", flush=True)
 dist.barrier()

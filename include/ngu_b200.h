@@ -84,6 +84,8 @@ typedef struct ngu_gemm_desc {
   int block_n;               /* 0 = auto; 64/128/256 force the N tile (tuning/tests) */
   const void* aux2; int ldaux2; /* [M,N] second elementwise operand (NGU_AUX_MONA_DX) or NULL */
   const float* rowab;        /* [M,2] fp32 per-row (alpha, beta) of NGU_AUX_MONA_DX or NULL */
+  int c_dtype;               /* 0 = C has the operand dtype; NGU_F32 with dtype NGU_BF16 = fp32 C from bf16 operands (plain alpha * acc
+                                epilogue): InfoNCE logits and feature gradients, src/losses/losses.py:34 */
 } ngu_gemm_desc;
 int ngu_gemm(const ngu_gemm_desc* d, void* stream);
 
@@ -264,7 +266,8 @@ int ngu_attn_bwd(const ngu_attn_desc* d, void* stream);
  *   ngu_infonce_normalize : xhat (fp32, written at the caller's row offset of the gather buffer), norms
  *   ngu_infonce_core      : loss (global mean, fp32 scalar) + d loss / d xhat for the local rows
  *   ngu_infonce_normalize_bwd : d loss / d x for the local rows (times *gscale, the upstream scalar grad)
- * ws: fp32 workspace of 2*Bg*Bg + 2*Bg elements.
+ * ws: fp32 workspace of 2*Bg*Bg + 2*Bg elements.  Each rank evaluates the global [Bg,Bg] logits once; the loss is exact
+ * for the global batch and the feature gradients of the local rows need no second collective.
  */
 int ngu_infonce_normalize(const void* x, float* xhat, float* norm, int B, int E, int dtype, void* stream);
 typedef struct ngu_infonce_desc {
@@ -273,6 +276,11 @@ typedef struct ngu_infonce_desc {
   float* loss; float* ws;
   int Bg, Bl, r0, E;
   float temperature;
+  /* bf16 product path (all NULL = fp32 check mode on CUDA cores): bf16 copies of the gathered normalised features and their
+   * transposes, so the logit matrix and both feature-gradient contractions run on the tcgen05 GEMM (fp32 accumulate/output) */
+  const void* ihat16; const void* that16;       /* [Bg, E] bf16 */
+  const void* ihat16_t; const void* that16_t;   /* [E, Bg] bf16 (gradients only) */
+  void* g_ws;                                   /* bf16 workspace of 2*Bl*Bg elements (gradients only) */
 } ngu_infonce_desc;
 int ngu_infonce_core(const ngu_infonce_desc* d, void* stream);
 int ngu_infonce_normalize_bwd(const float* dxhat, const float* xhat, const float* norm, const float* gscale,

@@ -39,6 +39,7 @@ class GemmDesc(ctypes.Structure):
         ("block_n", _c_int),
         ("aux2", _c_void_p), ("ldaux2", _c_int),
         ("rowab", _c_void_p),
+        ("c_dtype", _c_int),
     ]
 
 
@@ -122,7 +123,8 @@ class AttnDesc(ctypes.Structure):
 class InfoNceDesc(ctypes.Structure):
     _fields_ = [("ihat", _c_void_p), ("that", _c_void_p), ("dihat", _c_void_p), ("dthat", _c_void_p),
                 ("loss", _c_void_p), ("ws", _c_void_p),
-                ("Bg", _c_int), ("Bl", _c_int), ("r0", _c_int), ("E", _c_int), ("temperature", _c_float)]
+                ("Bg", _c_int), ("Bl", _c_int), ("r0", _c_int), ("E", _c_int), ("temperature", _c_float),
+                ("ihat16", _c_void_p), ("that16", _c_void_p), ("ihat16_t", _c_void_p), ("that16_t", _c_void_p), ("g_ws", _c_void_p)]
 
 
 class AdamWDesc(ctypes.Structure):

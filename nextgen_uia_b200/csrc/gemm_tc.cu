@@ -56,6 +56,8 @@ struct GemmKernelParams {
   const bf16* aux2;   // [M, ldaux2] second elementwise operand (NGU_AUX_MONA_DX: x), or nullptr
   int ldaux2;
   const float* rowab; // [M, 2] per-row (alpha_r, beta_r) of NGU_AUX_MONA_DX
+  float* cf32;        // fp32 output [M, ldcf] (c_dtype == NGU_F32: plain alpha * acc epilogue, InfoNCE logits / feature grads)
+  int ldcf;
   int M, N, K, K2;
   int act;       // NGU_ACT_*
   int aux_mode;  // NGU_AUX_*
@@ -366,6 +368,19 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
             }
           }
           if (!live) continue;
+          if (p.cf32 != nullptr) {
+            // fp32 output: every lane stores its row's 32 accumulators (scaled) straight to global memory
+            const int row = m0 + q * 32 + lane;
+            if (row < p.M) {
+              float* crow = p.cf32 + size_t(row) * p.ldcf + nc;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (nc + 4 * j < p.N)
+                  *reinterpret_cast<float4*>(crow + 4 * j) = make_float4(__uint_as_float(v[4 * j]) * p.alpha, __uint_as_float(v[4 * j + 1]) * p.alpha,
+                                                                        __uint_as_float(v[4 * j + 2]) * p.alpha, __uint_as_float(v[4 * j + 3]) * p.alpha);
+            }
+            continue;
+          }
 
           uint32_t outp[16];
           uint32_t prep[16];
@@ -462,7 +477,11 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     p.tmB2 = p.tmB;
     p.tmB2h = p.tmBh;
   }
-  if ((rc = make_tmap_2d_bf16(&p.tmC, a.C, a.M, a.N, a.ldc, 32, kChunkCols, 2))) return rc;
+  if (a.c_dtype == NGU_F32) {
+    p.tmC = p.tmA;   // unused
+    p.cf32 = reinterpret_cast<float*>(a.C);
+    p.ldcf = a.ldc;
+  } else if ((rc = make_tmap_2d_bf16(&p.tmC, a.C, a.M, a.N, a.ldc, 32, kChunkCols, 2))) return rc;
   p.pre = a.Pre;
   p.ldpre = a.ldpre;
   p.bias = a.bias;
@@ -516,7 +535,12 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
 
 int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) { set_last_error("gemm_tc: empty problem M=%d N=%d K=%d", a.M, a.N, a.K); return NGU_ERR_SHAPE; }
-  if ((a.K % 8) || (a.lda % 8) || (a.ldb % 8) || (a.ldc % 8) || (a.K2 % 8)) {
+  if (a.c_dtype == NGU_F32 && (a.bias != nullptr || a.act != NGU_ACT_NONE || a.aux_mode != NGU_AUX_NONE || a.save_pre || (a.N % 4) || (a.ldc % 4) ||
+                               (reinterpret_cast<uintptr_t>(a.C) & 15))) {
+    set_last_error("gemm_tc: fp32 output supports the plain alpha * acc epilogue only (N, ldc multiples of 4, C 16-byte aligned)");
+    return NGU_ERR_ARG;
+  }
+  if ((a.K % 8) || (a.lda % 8) || (a.ldb % 8) || ((a.ldc % 8) && a.c_dtype != NGU_F32) || (a.K2 % 8)) {
     set_last_error("gemm_tc: K, K2 and leading dimensions must be multiples of 8 (16-byte rows)");
     return NGU_ERR_ALIGN;
   }

@@ -81,6 +81,22 @@ dfeat_kernel(const float* __restrict__ L, const float* __restrict__ lse_a, const
   }
 }
 
+// bf16 product path: G[i - r0][j] = coef (exp(L_ij - lse_a[i]) + exp(L_ij - lse_b[j]) - 2 delta_ij) as the bf16 A operand of the
+// tcgen05 feature-gradient GEMM  dA = G . Bf   (one block per local row, coalesced over j)
+__global__ void __launch_bounds__(256)
+infonce_g_kernel(const float* __restrict__ L, const float* __restrict__ lse_a, const float* __restrict__ lse_b, bf16* __restrict__ G,
+                 int n, int r0, float coef) {
+  pdl_prologue();
+  const int i = r0 + blockIdx.x;
+  const float la = lse_a[i];
+  const float* Lr = L + size_t(i) * n;
+  bf16* Gr = G + size_t(blockIdx.x) * n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float l = Lr[j];
+    Gr[j] = __float2bfloat16_rn((expf(l - la) + expf(l - lse_b[j]) - (j == i ? 2.f : 0.f)) * coef);
+  }
+}
+
 }  // namespace
 
 int infonce_normalize(const void* x, float* xhat, float* norm, int B, int E, int dtype, cudaStream_t st) {
@@ -126,11 +142,21 @@ int infonce_core(const ngu_infonce_desc& d, cudaStream_t st) {
   float* clse = rlse + n;
   cudaError_t e = cudaMemsetAsync(d.loss, 0, sizeof(float), st);
   if (e != cudaSuccess) return cuda_status(e, "infonce memset");
+  // bf16 product path (ihat16 given): logits and both feature-gradient contractions on the tcgen05 GEMM (bf16 operands, fp32
+  // accumulate / output); fp32 check mode: CUDA cores
+  const bool tc = d.ihat16 != nullptr;
+  if (tc && (!d.that16 || (d.dihat && (!d.ihat16_t || !d.that16_t || !d.g_ws)) || (E % 8) || (n % 8))) {
+    set_last_error("infonce: the bf16 path needs ihat16 / that16 (+ transposes and g_ws for gradients), E and Bg multiples of 8");
+    return NGU_ERR_ARG;
+  }
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M = n; g.N = n; g.K = E; g.lda = E; g.ldb = E; g.ldc = n; g.alpha = 1.f / d.temperature; g.dtype = NGU_F32;
   g.A = d.ihat; g.B = d.that; g.C = L;
-  if (int rc = gemm_simt(g, st)) return rc;
+  if (tc) {
+    g.A = d.ihat16; g.B = d.that16; g.dtype = NGU_BF16; g.c_dtype = NGU_F32;
+    if (int rc = gemm_tc(g, st)) return rc;
+  } else if (int rc = gemm_simt(g, st)) return rc;
   {
     const dim3 tg((n + 31) / 32, (n + 31) / 32);
     launch_pdl(transpose_kernel, dim3(tg), dim3(256), size_t(0), st, L, Lt, n);
@@ -142,9 +168,33 @@ int infonce_core(const ngu_infonce_desc& d, cudaStream_t st) {
   if (int rc = check_launch("infonce row_lse")) return rc;
   launch_pdl(row_lse_kernel, dim3(grid), dim3(wpb * 32), size_t(0), st, Lt, clse, d.loss, n, 0.5f / float(n));
   if (int rc = check_launch("infonce col_lse")) return rc;
-  if (d.dihat != nullptr) {
+  if (d.dihat != nullptr && tc) {
+    const float coef = 1.f / (2.f * float(n) * d.temperature);
+    bf16* G1 = reinterpret_cast<bf16*>(d.g_ws);
+    bf16* G2 = G1 + size_t(d.Bl) * n;
+    launch_pdl(infonce_g_kernel, dim3(d.Bl), dim3(256), size_t(0), st, L, rlse, clse, G1, n, d.r0, coef);
+    if (int rc = check_launch("infonce G (image rows)")) return rc;
+    launch_pdl(infonce_g_kernel, dim3(d.Bl), dim3(256), size_t(0), st, Lt, clse, rlse, G2, n, d.r0, coef);
+    if (int rc = check_launch("infonce G (text rows)")) return rc;
+    GemmArgs h;
+    memset(&h, 0, sizeof(h));
+    h.M = d.Bl; h.N = E; h.K = n; h.lda = n; h.ldb = n; h.ldc = E; h.alpha = 1.f; h.dtype = NGU_BF16; h.c_dtype = NGU_F32;
+    h.A = G1; h.B = d.that16_t; h.C = d.dihat;          // dIhat = G1 . That
+    if (int rc = gemm_tc(h, st)) return rc;
+    h.A = G2; h.B = d.ihat16_t; h.C = d.dthat;          // dThat = G2 . Ihat
+    if (int rc = gemm_tc(h, st)) return rc;
+  } else if (d.dihat != nullptr) {
     const float coef = 1.f / (2.f * float(n) * d.temperature);
     const int smem = n * int(sizeof(float));
+    if (smem > 48 * 1024) {
+      static bool attr = false;
+      if (!attr) {
+        cudaError_t ea = cudaFuncSetAttribute(dfeat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (ea != cudaSuccess) return cuda_status(ea, "infonce dfeat attr");
+        attr = true;
+      }
+      if (smem > 200 * 1024) { set_last_error("infonce (fp32 check mode): global batch %d exceeds the %d rows the weight-row staging holds", n, 200 * 1024 / 4); return NGU_ERR_SHAPE; }
+    }
     launch_pdl(dfeat_kernel, dim3(d.Bl), dim3(256), size_t(smem), st, L, rlse, clse, d.that, d.dihat, n, E, d.r0, coef);
     if (int rc = check_launch("infonce dI")) return rc;
     launch_pdl(dfeat_kernel, dim3(d.Bl), dim3(256), size_t(smem), st, Lt, clse, rlse, d.ihat, d.dthat, n, E, d.r0, coef);

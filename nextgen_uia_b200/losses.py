@@ -41,7 +41,9 @@ class _InfoNCEFunction(torch.autograd.Function):
             ihat = allb[:, 0].reshape(Bg, E).contiguous()
             that = allb[:, 1].reshape(Bg, E).contiguous()
         want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        loss, di, dt_ = ops.infonce_core(ihat, that, r0, Bl, temperature, want_grad=want)
+        # bf16 features: logits / feature gradients on the tcgen05 GEMM; fp32 features (check mode): CUDA cores
+        tc = img.dtype == torch.bfloat16 and txt.dtype == torch.bfloat16
+        loss, di, dt_ = ops.infonce_core(ihat, that, r0, Bl, temperature, want_grad=want, tensor_cores=tc)
         if want:
             ctx.save_for_backward(di, dt_, ihat[r0:r0 + Bl], that[r0:r0 + Bl], ni, nt)
         ctx.dtypes = (img.dtype, txt.dtype)

@@ -523,11 +523,13 @@ def infonce_normalize(x, xhat_out, norm_out):
             "ngu_infonce_normalize")
 
 
-def infonce_core(ihat, that, r0, Bl, temperature, want_grad=True):
-    """ihat/that: fp32 [Bg,E] gathered normalised features. Returns (loss[1], dihat[Bl,E], dthat[Bl,E])."""
+def infonce_core(ihat, that, r0, Bl, temperature, want_grad=True, tensor_cores=False):
+    """ihat/that: fp32 [Bg,E] gathered normalised features. Returns (loss[1], dihat[Bl,E], dthat[Bl,E]).
+    tensor_cores=True (bf16 product path): logits and feature gradients on the tcgen05 GEMM from bf16 copies."""
     _need_cuda(ihat, that)
     Bg, E = ihat.shape
     dev = ihat.device
+    tc = tensor_cores and Bg % 8 == 0 and E % 8 == 0
     loss = torch.empty(1, device=dev, dtype=torch.float32)
     ws = torch.empty(2 * Bg * Bg + 2 * Bg, device=dev, dtype=torch.float32)
     di = torch.empty(Bl, E, device=dev, dtype=torch.float32) if want_grad else None
@@ -536,6 +538,13 @@ def infonce_core(ihat, that, r0, Bl, temperature, want_grad=True):
     d.ihat, d.that, d.dihat, d.dthat = ihat.data_ptr(), that.data_ptr(), _p(di), _p(dt_)
     d.loss, d.ws = loss.data_ptr(), ws.data_ptr()
     d.Bg, d.Bl, d.r0, d.E, d.temperature = Bg, Bl, r0, E, float(temperature)
+    if tc:
+        keep = [cast(ihat, torch.bfloat16), cast(that, torch.bfloat16)]
+        d.ihat16, d.that16 = keep[0].data_ptr(), keep[1].data_ptr()
+        if want_grad:
+            keep += [cast(ihat, torch.bfloat16, transpose=True), cast(that, torch.bfloat16, transpose=True),
+                     torch.empty(2 * Bl * Bg, device=dev, dtype=torch.bfloat16)]
+            d.ihat16_t, d.that16_t, d.g_ws = keep[2].data_ptr(), keep[3].data_ptr(), keep[4].data_ptr()
     L.check(L.lib().ngu_infonce_core(_byref(d), _stream()), "ngu_infonce_core")
     return loss, di, dt_
 

@@ -333,6 +333,16 @@ int ngu_set_seed_counter(const void* counter);
  * kv_len_out[b] = number of non-pad ids of row b; *flag |= 1 if some row's valid ids are not a non-empty prefix. */
 int ngu_kv_len(const int64_t* ids, int64_t pad_id, int* kv_len_out, int* flag, int B, int S, void* stream);
 
+/*
+ * Zero-shot prompt-ensemble scorer — src/models/biomedclip/zero_shot.py:176-228: per class, the mean over its prompts of
+ * 100 * Ihat . That_p, stacked to [B, n_classes] logits (argmax = prediction, src/utils/tools.py:211).  The mean commutes with the
+ * dot product, so one prototype per class is built once (mean of the L2-normalised prompt features) and an image batch is scored
+ * in one launch (normalise + dot + argmax).  text_feat [P,E] / image_feat [B,E] in `dtype`; class_of_prompt int32 [P] in [0,C).
+ */
+int ngu_zero_shot_prototypes(const void* text_feat, const int* class_of_prompt, float* proto, int P, int E, int C, int dtype, void* stream);
+int ngu_zero_shot_score(const void* image_feat, const float* proto, float* logits, int* pred, int B, int E, int C, float scale,
+                        int dtype, void* stream);
+
 /* Patch-embed im2col (stride == kernel, timm PatchEmbed / CLIP conv1): images fp32 NCHW [B,3,R,R]
  * -> [B*(R/P)^2, Kp] with row pitch Kp = 3*P*P rounded up to a multiple of 8 (P = 14: 588 -> 592; the caller zero-fills
  * the buffer once, the kernel writes the 3*P*P live columns; pixels past the last whole patch are dropped like the conv);

@@ -167,6 +167,8 @@ PROTOTYPES = {
     "ngu_adamw_step": (_c_int, [_P(AdamWDesc), _c_void_p]),
     "ngu_guard_tick": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "ngu_set_seed_counter": (_c_int, [_c_void_p]),
+    "ngu_zero_shot_prototypes": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "ngu_zero_shot_score": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_int, _c_void_p]),
     "ngu_kv_len": (_c_int, [_c_void_p, _i64, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "ngu_patchify": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "ngu_assemble_tokens": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),

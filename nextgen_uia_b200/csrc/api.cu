@@ -94,6 +94,12 @@ int ngu_dropout(const void* x, void* out, int64_t n, float p, uint64_t seed, int
 int ngu_sqnorm(const float* x, int64_t n, float* out, void* stream) { return sqnorm(x, size_t(n), out, NGU_STREAM); }
 int ngu_guard_tick(int64_t* state, const float* loss, const float* gsq, int mode, void* stream) { return guard_tick(state, loss, gsq, mode, NGU_STREAM); }
 int ngu_kv_len(const int64_t* ids, int64_t pad_id, int* kv_len_out, int* flag, int B, int S, void* stream) { return kv_len(ids, pad_id, kv_len_out, flag, B, S, NGU_STREAM); }
+int ngu_zero_shot_prototypes(const void* text_feat, const int* class_of_prompt, float* proto, int P, int E, int C, int dtype, void* stream) {
+  return zero_shot_prototypes(text_feat, class_of_prompt, proto, P, E, C, dtype, NGU_STREAM);
+}
+int ngu_zero_shot_score(const void* image_feat, const float* proto, float* logits, int* pred, int B, int E, int C, float scale, int dtype, void* stream) {
+  return zero_shot_score(image_feat, proto, logits, pred, B, E, C, scale, dtype, NGU_STREAM);
+}
 int ngu_set_seed_counter(const void* counter) { set_seed_counter(reinterpret_cast<const uint64_t*>(counter)); return NGU_OK; }
 int ngu_adamw_step(const ngu_adamw_desc* d, void* stream) { NGU_NONNULL(d, "ngu_adamw_step"); return adamw_step(*d, NGU_STREAM); }
 int ngu_patchify(const float* img, void* out, int B, int R, int P, int dtype, void* stream) {

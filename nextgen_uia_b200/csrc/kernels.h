@@ -49,6 +49,8 @@ int sqnorm(const float* x, size_t n, float* out, cudaStream_t s);
 int guard_tick(int64_t* state, const float* loss, const float* gsq, int mode, cudaStream_t s);
 int kv_len(const int64_t* ids, int64_t pad, int* out, int* flag, int B, int S, cudaStream_t s);
 void set_seed_counter(const uint64_t* p);
+int zero_shot_prototypes(const void* tf, const int* cls, float* proto, int P, int E, int C, int dtype, cudaStream_t s);
+int zero_shot_score(const void* f, const float* proto, float* logits, int* pred, int B, int E, int C, float scale, int dtype, cudaStream_t s);
 int adamw_step(const ngu_adamw_desc& d, cudaStream_t s);
 
 void count_launch(int n = 1);

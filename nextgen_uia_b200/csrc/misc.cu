@@ -271,6 +271,57 @@ __global__ void kv_len_kernel(const int64_t* __restrict__ ids, int64_t pad, int*
   }
 }
 
+// Zero-shot prompt-ensemble scorer (src/models/biomedclip/zero_shot.py:176-228): the mean over a class's prompts of
+// 100 * Ihat . That_p equals 100 * Ihat . mean_p(That_p), so scoring needs one prototype per class.
+//   prototypes: proto[c] = mean over prompts p of class c of  t_p / ||t_p||          (one block per class)
+//   scores    : logits[b][c] = scale * <f_b / ||f_b||, proto[c]>,  pred[b] = argmax_c  (one warp per image)
+template <typename T>
+__global__ void __launch_bounds__(256) zs_proto_kernel(const T* __restrict__ tf, const int* __restrict__ cls, float* __restrict__ proto, int P, int E) {
+  pdl_prologue();
+  __shared__ float red[8];
+  __shared__ float inv_s;
+  const int c = blockIdx.x;
+  int cnt = 0;
+  for (int e = threadIdx.x; e < E; e += 256) proto[size_t(c) * E + e] = 0.f;
+  for (int pi = 0; pi < P; ++pi) {
+    if (cls[pi] != c) continue;      // block-uniform
+    ++cnt;
+    float s = 0.f;
+    for (int e = threadIdx.x; e < E; e += 256) { const float v = to_f32<T>(tf[size_t(pi) * E + e]); s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; inv_s = rsqrtf(fmaxf(t, 1e-24f)); }
+    __syncthreads();
+    const float inv = inv_s;
+    for (int e = threadIdx.x; e < E; e += 256) proto[size_t(c) * E + e] += to_f32<T>(tf[size_t(pi) * E + e]) * inv;
+    __syncthreads();
+  }
+  const float k = cnt > 0 ? 1.f / float(cnt) : 0.f;
+  for (int e = threadIdx.x; e < E; e += 256) proto[size_t(c) * E + e] *= k;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) zs_score_kernel(const T* __restrict__ f, const float* __restrict__ proto, float* __restrict__ logits,
+                                                       int* __restrict__ pred, int B, int E, int C, float scale) {
+  pdl_prologue();
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float ss = 0.f;
+  for (int e = lane; e < E; e += 32) { const float v = to_f32<T>(f[size_t(b) * E + e]); ss = fmaf(v, v, ss); }
+  const float inv = rsqrtf(fmaxf(warp_sum(ss), 1e-24f));
+  float best = -INFINITY;
+  int arg = 0;
+  for (int c = 0; c < C; ++c) {
+    float d = 0.f;
+    for (int e = lane; e < E; e += 32) d = fmaf(to_f32<T>(f[size_t(b) * E + e]), proto[size_t(c) * E + e], d);
+    d = warp_sum(d) * inv * scale;
+    if (lane == 0) logits[size_t(b) * C + c] = d;
+    if (d > best) { best = d; arg = c; }       // first maximum wins, like torch.argmax
+  }
+  if (lane == 0) pred[b] = arg;
+}
+
 int grid_for(size_t total) {
   size_t g = (total + 255) / 256;
   const size_t cap = size_t(sm_count()) * 16;
@@ -366,6 +417,19 @@ int kv_len(const int64_t* ids, int64_t pad, int* out, int* flag, int B, int S, c
   if (B <= 0 || S <= 0 || !ids || !out || !flag) { set_last_error("kv_len: bad arguments"); return NGU_ERR_ARG; }
   launch_pdl(kv_len_kernel, dim3((B + 3) / 4), dim3(128), size_t(0), st, ids, pad, out, flag, B, S);
   return check_launch("kv_len");
+}
+
+int zero_shot_prototypes(const void* tf, const int* cls, float* proto, int P, int E, int C, int dtype, cudaStream_t st) {
+  if (P <= 0 || E <= 0 || C <= 0 || !tf || !cls || !proto) { set_last_error("zero_shot_prototypes: bad arguments"); return NGU_ERR_ARG; }
+  if (dtype == NGU_F32) launch_pdl(zs_proto_kernel<float>, dim3(C), dim3(256), size_t(0), st, reinterpret_cast<const float*>(tf), cls, proto, P, E);
+  else launch_pdl(zs_proto_kernel<bf16>, dim3(C), dim3(256), size_t(0), st, reinterpret_cast<const bf16*>(tf), cls, proto, P, E);
+  return check_launch("zero_shot_prototypes");
+}
+int zero_shot_score(const void* f, const float* proto, float* logits, int* pred, int B, int E, int C, float scale, int dtype, cudaStream_t st) {
+  if (B <= 0 || E <= 0 || C <= 0 || !f || !proto || !logits || !pred) { set_last_error("zero_shot_score: bad arguments"); return NGU_ERR_ARG; }
+  if (dtype == NGU_F32) launch_pdl(zs_score_kernel<float>, dim3((B + 3) / 4), dim3(128), size_t(0), st, reinterpret_cast<const float*>(f), proto, logits, pred, B, E, C, scale);
+  else launch_pdl(zs_score_kernel<bf16>, dim3((B + 3) / 4), dim3(128), size_t(0), st, reinterpret_cast<const bf16*>(f), proto, logits, pred, B, E, C, scale);
+  return check_launch("zero_shot_score");
 }
 
 }  // namespace ngu

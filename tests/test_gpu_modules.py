@@ -213,6 +213,19 @@ def test_zero_shot_argmax_matches_oracle():
     cfg = dict(patch=16, depth=2, heads=12, text_layers=2, text_heads=12)
     ref = OF.zero_shot_predict(OF.encode_image(sd, images.double(), cfg), [OF.encode_text(sd, p, cfg) for p in prompts])
     model = model.to(dev()).eval().set_compute_dtype(torch.bfloat16)
+    # on-device scorer (nextgen_uia_b200/zero_shot.py: prototypes + fused normalise / dot / argmax kernel)
+    from nextgen_uia_b200.zero_shot import ZeroShotScorer
+    scorer = ZeroShotScorer(model)
+    scorer.set_prompts({"benign": prompts[0].to(dev()), "malignant": prompts[1].to(dev())})
+    logits, pred = scorer(images.to(dev()))
+    assert torch.equal(pred.cpu().long(), ref)
+    # its logits are the reference recipe's: mean over prompts of 100 * Ihat . That
+    fio = OF.encode_image(sd, images.double(), cfg)
+    io = fio / fio.norm(dim=-1, keepdim=True)
+    lo = torch.stack([(100.0 * io @ (t / t.norm(dim=-1, keepdim=True)).t()).mean(1) for t in (OF.encode_text(sd, p, cfg) for p in prompts)], 1)
+    # random towers give nearly orthogonal image / text features: the logits are 100 x cosines of ~1e-3, so the bf16 feature
+    # error shows up as an ABSOLUTE cosine error; 1e-3 in cosine = 0.1 in logit units
+    assert float((logits.double().cpu() - lo).abs().max()) < 0.1
     with torch.no_grad():
         fi = model.encode_image(images.to(dev())).float().cpu()
         tf = [model.encode_text(p.to(dev())).float().cpu() for p in prompts]
@@ -749,3 +762,46 @@ def test_mona_unfused_bf16_path_still_matches_golden(golden, name, monkeypatch):
     assert relerr(y, g["y"]) < TOL[torch.bfloat16] and relerr(x.grad, g["dx"]) < GTOL[torch.bfloat16]
     for k, p in m.named_parameters():
         assert relerr(p.grad, g["grads"][k]) < GTOL[torch.bfloat16], k
+
+
+@pytest.mark.parametrize("task", ["seg", "cls"])
+def test_timm_clip_adapter_heads_vs_oracle(task):
+    """f4: downstream heads on tapped block activations (reference TimmCLIPAdapter, timm/clip_adapter.py:118-160): taps from the
+    kernels (Mona inside) feed the reduce -> LayerNorm/MLP pyramid and the seg / cls head; logits and the gradients of head +
+    Mona parameters vs the same head applied to the CPU oracle's taps."""
+    import copy
+    from nextgen_uia_b200.clip_adapter import TimmCLIPAdapter
+    from oracle import functional as OF
+    torch.manual_seed(3)
+    clip = _tiny_model("mona", depth=3)
+    ad = TimmCLIPAdapter(clip, extract_layers=[0, 2], reduce_dim=64, num_classes=2, img_size=224, task=task).eval()
+    ad.freeze_clip_backbone()
+    head64 = copy.deepcopy(torch.nn.ModuleList([ad.reduces, ad.blocks, ad.seg_head, ad.cls_head])).double()
+    sd = {k: v.detach().double().clone() for k, v in clip.state_dict().items()}
+    trainable = [n for n, p in clip.named_parameters() if p.requires_grad]
+    assert trainable and all("mona" in n for n in trainable)
+    images = torch.rand(2, 3, 224, 224)
+    p64 = {k: v.clone().requires_grad_(k in trainable) for k, v in sd.items()}
+    taps = []
+    OF.encode_image(p64, images.double(), dict(patch=16, depth=3, heads=12), taps=taps)
+    red, blk, seg, cls = head64
+    fused = None
+    for lvl, ti in ((1, 2), (0, 0)):
+        y = blk[lvl](red[lvl](taps[ti][:, 1:, :]))
+        fused = y if fused is None else fused + y
+    fmap = fused.transpose(1, 2).reshape(2, 64, 14, 14)
+    lo = seg(fmap) if task == "seg" else cls(fmap)
+    gl = torch.randn(lo.shape, dtype=torch.float64)
+    head_params = [p for p in head64.parameters()]
+    go = torch.autograd.grad((lo * gl).sum(), [p64[n] for n in trainable] + head_params, allow_unused=True)
+    ad = ad.to(dev())
+    clip.set_compute_dtype(torch.bfloat16)
+    logits = ad(images.to(dev()))
+    (logits.double() * gl.to(dev())).sum().backward()
+    assert logits.shape == lo.shape and relerr(logits, lo) < 2e-2
+    num = den = 0.0
+    params = dict(clip.named_parameters())
+    for n, b in zip(trainable, go):
+        d = params[n].grad.double().cpu() - b
+        num += float((d * d).sum()); den += float((b * b).sum())
+    assert (num / den) ** 0.5 < 5e-2

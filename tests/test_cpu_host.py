@@ -158,3 +158,30 @@ def test_device_feeder_and_scalar_log_cpu():
         got += log.pop_ready()
     assert got == [0.0, 1.0, 2.0, 3.0]
     assert log.drain() == [4.0]
+
+
+def test_src_nets_shim_importable_with_reference_signatures():
+    """src.nets keeps conv_layer, linear_layer, CoordConv, Projector, FPN_AD, CARAFE, Masker, gumbel_softmax
+    importable with the reference's signatures (dead code there too); plus the src.third_party re-export paths."""
+    import inspect
+    from src.nets.layers import conv_layer, linear_layer, CoordConv, Projector, FPN_AD
+    from src.nets.carafe import CARAFE
+    from src.nets.masker import Masker, gumbel_softmax
+    assert list(inspect.signature(conv_layer).parameters) == ["in_dim", "out_dim", "kernel_size", "padding", "stride"]
+    assert list(inspect.signature(linear_layer).parameters) == ["in_dim", "out_dim", "bias"]
+    assert list(inspect.signature(CARAFE.__init__).parameters)[1:] == ["inC", "outC", "kernel_size", "up_factor"]
+    assert list(inspect.signature(Projector.__init__).parameters)[1:] == ["word_dim", "in_dim", "kernel_size"]
+    assert list(inspect.signature(Masker.__init__).parameters)[1:] == ["in_dim", "outdim"]
+    assert list(inspect.signature(FPN_AD.__init__).parameters)[1:] == ["in_channels", "out_channels"]
+    x = torch.randn(2, 16, 5, 7)
+    assert CARAFE(16, 8)(x).shape == (2, 8, 10, 14)
+    assert CoordConv(16, 4)(x).shape == (2, 4, 5, 7)
+    assert Masker(16, 16).eval()(x).shape == (2, 16, 5, 7)
+    assert Projector(32, 8).eval()(torch.randn(2, 16, 3, 3), torch.randn(2, 32)).shape == (2, 1, 48, 48)
+    p = gumbel_softmax(torch.randn(4, 5))
+    assert torch.allclose(p.sum(-1), torch.ones(4))
+    assert "masker5.conv.weight" in FPN_AD().state_dict() and "carafe.encoder.weight" in FPN_AD().state_dict()
+    from src.third_party.timm.clip_adapter import TimmCLIPAdapter  # noqa: F401
+    from src.third_party.openai_clip.clip_adapter import CLIPAdapter  # noqa: F401
+    from src.third_party.openai_clip.clipseg_adapter import CLIPSegAdapter  # noqa: F401
+    from src.third_party.openai_clip.model import CLIP  # noqa: F401

@@ -374,12 +374,30 @@ def block_microbench(dev, B, iters=10, profile=False):
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+    run = step
+    if not profile:
+        # replay the block's forward + backward as one CUDA graph, like the training step: the figure is kernel time, not launch time
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                step()
+            run = gr.replay
+            run()
+            torch.cuda.synchronize()
+        except Exception:
+            run = step
+            torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if profile:
         torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for _ in range(iters):
-        step()
+        run()
     e1.record()
     torch.cuda.synchronize()
     if profile:
@@ -570,8 +588,12 @@ def main():
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMA GEMM, all launches of one step)", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                "traffic_note": "aggregate over shapes; per-shape DRAM bytes (QKV launch: 81 MB read + 180 MB write vs 313 MB algorithmic) in profiles/r1_gemm_qkv_ncu_full_summary.txt",
+                "unit": "TFLOP/s", "frac": ach / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel (the QKV projection, M=50432 N=2304 K=768,
+                # 178.5 GFLOP, 313 MB algorithmic): profiles/r2_gemm_qkv_ncu_full_summary.txt (ncu --set full, 81.2 MB read + 181.5 MB
+                # written; part of the output is still in L2 when the launch ends)
+                "traffic": 262.66e6 if args.config == 2 else None,
+                "traffic_note": "per launch, QKV projection of config 2 (ncu --set full): 262.7 MB DRAM vs 313 MB algorithmic, 178.5 GFLOP",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "gemm_ms_per_step": t_ms, "gemm_share_of_step": t_ms / (ms / args.steps), "gemm_launches_per_step": len(recs),
                 "flop_per_image": flops_per_image(args.config, args.depth),
@@ -582,6 +604,10 @@ def main():
     block = None
     if rank == 0 and args.config in (2, 3):
         block = block_microbench(dev, B)
+        if roof is not None:
+            # the fraction the north_star target (>= 0.60) is stated on: ViT-B/16 block + Mona + LoRA, fwd + bwd, algorithmic FLOPs
+            roof["block_frac"] = block["frac_of_measured_sustained_peak"]
+            roof["block_ms"] = block["ms"]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 2:

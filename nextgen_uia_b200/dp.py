@@ -274,6 +274,10 @@ class Trainer:
                 for m in monas:
                     m._ngu_castplan = self.castplan
         self._mona_stale = True
+        # overlap the frozen text tower with the vision forward (NGU_TEXT_STREAM=0 disables)
+        import os as _os
+        text_frozen = hasattr(model, "text") and not any(p.requires_grad for p in model.text.parameters())
+        self._text_stream = (torch.cuda.Stream() if (on_gpu and text_frozen and _os.environ.get("NGU_TEXT_STREAM", "1") != "0") else None)
         self._poisoned = False
         self.graph = None
         self.grad_clip = grad_clip
@@ -298,10 +302,22 @@ class Trainer:
         if self.monaplan is not None and self._mona_stale and self.monaplan.valid():
             self.monaplan.run()
             self._mona_stale = False
-        with _nvtx("encode_image"):
-            fi = m.encode_image(images)
-        with _nvtx("encode_text"):
-            ft = m.encode_text(ids)
+        if self._text_stream is not None:
+            # the frozen text tower has no dependency on the vision tower: run it on a second stream so its kernels fill the
+            # tails / launch gaps of the vision forward (one fork-join; a parallel branch of the graph under capture)
+            cur = torch.cuda.current_stream()
+            self._text_stream.wait_stream(cur)
+            with torch.cuda.stream(self._text_stream), _nvtx("encode_text"):
+                ft = m.encode_text(ids)
+            with _nvtx("encode_image"):
+                fi = m.encode_image(images)
+            cur.wait_stream(self._text_stream)
+            ft.record_stream(cur)
+        else:
+            with _nvtx("encode_image"):
+                fi = m.encode_image(images)
+            with _nvtx("encode_text"):
+                ft = m.encode_text(ids)
         with _nvtx("infonce"):
             loss = self.criterion(fi, ft)
         lossd = loss.detach().float().view(1)

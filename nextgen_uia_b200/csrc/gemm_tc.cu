@@ -31,23 +31,30 @@ constexpr int kGemmThreads = 32 * (2 + kNumEpiWarps);
 constexpr int kChunkCols = 32;              // columns per epilogue work item
 constexpr int kSlabBytes = 32 * kChunkCols * 2;  // 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
 
-template <int BLOCK_N, bool kPair = false>
+// kAuxTma: number of elementwise [M,N] operands (0, 1 = residual, 2 = Mona dx) that reach the epilogue through per-warp TMA
+// rings of 32x32 slabs instead of per-lane global loads.  For the short-K launches (Mona project2 K = 64, Mona dx K = 128) the
+// epilogue IS the kernel: per-lane loads of 64-byte row pieces cost 32 LSU wavefronts per instruction and bounded those
+// launches at ~2.5 TB/s; the TMA engine writes the slabs without touching the LSU and keeps kAuxDepth slabs per warp in flight.
+constexpr int kAuxDepth = 2;
+template <int BLOCK_N, bool kPair = false, int kAuxTma = 0>
 struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = (kPair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // pair mode: each CTA holds half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBytes = kNumEpiWarps * kSlabBytes;  // one 32x32 slab per epilogue warp
+  static constexpr int kAuxBytes = kNumEpiWarps * kAuxDepth * kAuxTma * kSlabBytes;
   static constexpr int kBarBytes = 1024;  // mbarriers + tmem ptr
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/;
-  static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes - kBarBytes) / kStageBytes;
+  static constexpr int kStagesRaw = (kSmemBudget - kEpiBytes - kAuxBytes - kBarBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kAuxBytes + kBarBytes + 1024;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
 };
 
 struct GemmKernelParams {
   CUtensorMap tmA, tmB, tmA2, tmB2, tmC;
   CUtensorMap tmBh, tmB2h;  // B with a half-height box (cluster multicast: each CTA fetches BLOCK_N/2 rows)
+  CUtensorMap tmAux, tmAux2;  // kAuxTma: 32 x 32 boxes (SWIZZLE_64B) of the elementwise operands
   void* pre;   // [M, ldpre] pre-activation output (save_pre)
   int ldpre;
   const float* bias;  // [N] fp32 or nullptr
@@ -121,24 +128,27 @@ NGU_DEVINL void epi_chunk_dx(const uint32_t (&v)[32], const uint4 (&ax)[4], cons
   }
 }
 
-template <int BLOCK_N, int kCluster, bool kPair, bool kDX = false>
+template <int BLOCK_N, int kCluster, bool kPair, bool kDX = false, int kAuxTma = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
   pdl_prologue();
   static_assert(!kPair || kCluster == 2, "pair mode is a 2-CTA cluster");
-  using Cfg = GemmCfg<BLOCK_N, kPair>;
+  static_assert(kAuxTma == 0 || kAuxTma == (kDX ? 2 : 1), "TMA aux rings: one operand (residual) or two (Mona dx)");
+  using Cfg = GemmCfg<BLOCK_N, kPair, kAuxTma>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA0 = smem_base;
   const uint32_t sB0 = smem_base + Cfg::kStages * Cfg::kABytes;
   const uint32_t sEpi = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  const uint32_t sBar = sEpi + Cfg::kEpiBytes;
+  const uint32_t sAux = sEpi + Cfg::kEpiBytes;        // [epilogue warp][slot][operand] 2 KB slabs
+  const uint32_t sBar = sAux + Cfg::kAuxBytes;
   // barrier slots (8 bytes each)
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int a) { return sBar + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return sBar + 8u * (2 * Cfg::kStages + 2 + a); };
   const uint32_t sTmemPtr = sBar + 8u * (2 * Cfg::kStages + 4);
+  auto aux_bar = [&](int ew, int slot) { return sBar + 8u * (2 * Cfg::kStages + 6 + ew * kAuxDepth + slot); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -167,6 +177,9 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), kPair ? 1 : kCluster);  // released by the MMA warp(s) of every CTA that reads this slot
     }
+    if (kAuxTma > 0)
+      for (int w = 0; w < kNumEpiWarps; ++w)
+        for (int sl = 0; sl < kAuxDepth; ++sl) mbar_init(aux_bar(w, sl), 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), ((BLOCK_N / kChunkCols >= 4) ? kNumEpiWarps : 4 * (BLOCK_N / kChunkCols)) * (kPair ? 2 : 1));  // pair: both CTAs' epilogues
@@ -317,13 +330,33 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
       for (int j = 0; j < 4; ++j) dst[j] = (ok && nc + j * 8 < p.N) ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
     };
 
+    // TMA aux ring: work item n of this warp = (tile tile_first + (n / kPerWarp) * tile_stride, chunk c_begin + n % kPerWarp)
+    auto aux_issue = [&](int n) {
+      const int t = tile_first + (n / kPerWarp) * tile_stride, c = c_begin + n % kPerWarp;
+      if (t >= num_tiles) return;
+      const int nc = tile_n0(t) + c * kChunkCols;
+      if (nc >= p.N) return;
+      const int sl = n % kAuxDepth;
+      const uint32_t dst = sAux + uint32_t((ew * kAuxDepth + sl) * kAuxTma) * kSlabBytes, bar = aux_bar(ew, sl);
+      mbar_arrive_expect_tx(bar, kAuxTma * kSlabBytes);
+      tma_load_2d(dst, &p.tmAux, bar, nc, tile_m0(t) + q * 32, kEvictFirst);
+      if (kAuxTma == 2) tma_load_2d(dst + kSlabBytes, &p.tmAux2, bar, nc, tile_m0(t) + q * 32, kEvictFirst);
+    };
     if (active) {
       int acc = 0;
       uint32_t acc_ph = 0;
+      int item = 0;
+      uint32_t aux_ph = 0;       // bit sl = parity of the next completion of ring slot sl (advances only for armed = live items)
       uint4 axn[4];
       uint4 bxn[kDX ? 4 : 1];
-      load_aux(tile_first, c_begin, axn);
-      if (kDX) load_aux2(tile_first, c_begin, reinterpret_cast<uint4 (&)[4]>(bxn));
+      if (kAuxTma > 0) {
+        if (lane == 0)
+          for (int n = 0; n < kAuxDepth; ++n) aux_issue(n);
+        __syncwarp();
+      } else {
+        load_aux(tile_first, c_begin, axn);
+        if (kDX) load_aux2(tile_first, c_begin, reinterpret_cast<uint4 (&)[4]>(bxn));
+      }
       for (int t = tile_first; t < num_tiles; t += tile_stride) {
         const int m0 = tile_m0(t);
         const int n0 = tile_n0(t);
@@ -344,19 +377,36 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
           // aux chunk was prefetched one work item ago; start fetching the next one now
           uint4 ax[4];
           uint4 bx[kDX ? 4 : 1];
+          if (kAuxTma > 0) {
+            if (live) {
+              // this item's slabs have landed (TMA zero-fills rows / columns past the matrix): lane = row, 64-byte rows, SWIZZLE_64B
+              const int sl = item % kAuxDepth;
+              mbar_wait(aux_bar(ew, sl), (aux_ph >> sl) & 1u);
+              aux_ph ^= 1u << sl;
+              const uint32_t src = sAux + uint32_t((ew * kAuxDepth + sl) * kAuxTma) * kSlabBytes + lane * 64;
+              const uint32_t sw = uint32_t(lane >> 1) & 3u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ax[j] = axn[j];
-          if (kDX) {
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t a = src + ((uint32_t(j) ^ sw) << 4);
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ax[j].x), "=r"(ax[j].y), "=r"(ax[j].z), "=r"(ax[j].w) : "r"(a));
+                if (kDX) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(bx[j].x), "=r"(bx[j].y), "=r"(bx[j].z), "=r"(bx[j].w) : "r"(a + kSlabBytes));
+              }
+            }
+          } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bx[j] = bxn[j];
-          }
-          if (use_aux) {
-            if (ci + 1 < kPerWarp) load_aux(t, c + 1, axn);
-            else load_aux(t + tile_stride, c_begin, axn);
-          }
-          if (kDX) {
-            if (ci + 1 < kPerWarp) load_aux2(t, c + 1, reinterpret_cast<uint4 (&)[4]>(bxn));
-            else load_aux2(t + tile_stride, c_begin, reinterpret_cast<uint4 (&)[4]>(bxn));
+            for (int j = 0; j < 4; ++j) ax[j] = axn[j];
+            if (kDX) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) bx[j] = bxn[j];
+            }
+            if (use_aux) {
+              if (ci + 1 < kPerWarp) load_aux(t, c + 1, axn);
+              else load_aux(t + tile_stride, c_begin, axn);
+            }
+            if (kDX) {
+              if (ci + 1 < kPerWarp) load_aux2(t, c + 1, reinterpret_cast<uint4 (&)[4]>(bxn));
+              else load_aux2(t + tile_stride, c_begin, reinterpret_cast<uint4 (&)[4]>(bxn));
+            }
           }
           tmem_ld_wait();
           if (ci == kPerWarp - 1) {
@@ -367,7 +417,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
               if (kPair && rank != 0) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc));
             }
           }
-          if (!live) continue;
+          if (!live) { ++item; continue; }
           if (p.cf32 != nullptr) {
             // fp32 output: every lane stores its row's 32 accumulators (scaled) straight to global memory
             const int row = m0 + q * 32 + lane;
@@ -379,6 +429,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
                   *reinterpret_cast<float4*>(crow + 4 * j) = make_float4(__uint_as_float(v[4 * j]) * p.alpha, __uint_as_float(v[4 * j + 1]) * p.alpha,
                                                                         __uint_as_float(v[4 * j + 2]) * p.alpha, __uint_as_float(v[4 * j + 3]) * p.alpha);
             }
+            ++item;
             continue;
           }
 
@@ -399,6 +450,12 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
               default: epi_chunk<NGU_ACT_NONE, NGU_AUX_NONE>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
             }
           }
+          if (kAuxTma > 0) {
+            // the slabs of this item were consumed into `outp`: refill the slot with the item kAuxDepth ahead
+            __syncwarp();
+            if (lane == 0) aux_issue(item + kAuxDepth);
+          }
+          ++item;
           if (lane == 0) tma_store_wait_read<0>();   // previous TMA store has finished reading this warp's slab
           __syncwarp();
           // slab rows are 64 bytes; SWIZZLE_64B: 16-byte piece index ^= (row >> 1) & 3
@@ -459,9 +516,10 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
   }
 }
 
-template <int BLOCK_N, int kCluster, bool kPair = false, bool kDX = false>
+template <int BLOCK_N, int kCluster, bool kPair = false, bool kDX = false, int kAuxTma = 0>
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, kPair>;
+  using Cfg = GemmCfg<BLOCK_N, kPair, kAuxTma>;
+  static_assert(Cfg::kStages >= 2, "operand ring too shallow");
   GemmKernelParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -482,6 +540,13 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     p.cf32 = reinterpret_cast<float*>(a.C);
     p.ldcf = a.ldc;
   } else if ((rc = make_tmap_2d_bf16(&p.tmC, a.C, a.M, a.N, a.ldc, 32, kChunkCols, 2))) return rc;
+  if (kAuxTma > 0) {
+    if ((rc = make_tmap_2d_bf16(&p.tmAux, a.aux, a.M, a.N, a.ldaux, 32, kChunkCols, 2))) return rc;
+    if (kAuxTma == 2) { if ((rc = make_tmap_2d_bf16(&p.tmAux2, a.aux2, a.M, a.N, a.ldaux2, 32, kChunkCols, 2))) return rc; }
+    else p.tmAux2 = p.tmAux;
+  } else {
+    p.tmAux = p.tmA; p.tmAux2 = p.tmA;
+  }
   p.pre = a.Pre;
   p.ldpre = a.ldpre;
   p.bias = a.bias;
@@ -501,7 +566,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
 
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kCluster, kPair, kDX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kCluster, kPair, kDX, kAuxTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_status(e, "gemm_tc smem attribute");
     attr_done = true;
   }
@@ -525,7 +590,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kCluster, kPair, kDX>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kCluster, kPair, kDX, kAuxTma>, p);
   count_launch(1);
   if (e != cudaSuccess) return cuda_status(e, "gemm_tc launch");
   return cuda_status(cudaGetLastError(), "gemm_tc");
@@ -557,8 +622,17 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
       set_last_error("gemm_tc: NGU_AUX_MONA_DX needs aux, aux2 (ldaux2 %% 8 == 0), rowab and no bias / activation / save_pre / alpha");
       return NGU_ERR_ARG;
     }
-    // short K (128), two streamed elementwise operands: epilogue-bound -> independent-CTA multicast variant
-    return a.M > BLOCK_M ? launch_gemm_tc<256, 2, false, true>(a, stream) : launch_gemm_tc<256, 1, false, true>(a, stream);
+    // short K (128), two streamed elementwise operands: the epilogue IS the kernel -> independent-CTA multicast variant with both
+    // operands staged through the per-warp TMA rings (NGU_GEMM_AUXTMA=0: per-lane loads, A/B switch)
+    static const int auxtma = [] { const char* e = getenv("NGU_GEMM_AUXTMA"); return e ? atoi(e) : 1; }();
+    if (a.M <= BLOCK_M) return launch_gemm_tc<256, 1, false, true>(a, stream);
+    if (auxtma && a.K + a.K2 <= 256) return launch_gemm_tc<128, 2, false, true, 2>(a, stream);
+    return launch_gemm_tc<256, 2, false, true>(a, stream);
+  }
+  if (a.aux_mode == NGU_AUX_RESIDUAL && a.act == NGU_ACT_NONE && !a.save_pre && a.c_dtype != NGU_F32 && a.block_n == 0 && a.M > BLOCK_M &&
+      a.N > 128 && a.K + a.K2 <= 256) {
+    static const int auxtma = [] { const char* e = getenv("NGU_GEMM_AUXTMA"); return e ? atoi(e) : 1; }();
+    if (auxtma) return launch_gemm_tc<256, 2, false, false, 1>(a, stream);   // Mona project2 + residual (K = 64)
   }
   int bn = a.block_n;
   if (bn == 0) bn = (a.N > 128) ? 256 : (a.N > 64 ? 128 : 64);

@@ -414,7 +414,10 @@ class Trainer:
             self.castplan.fresh = False
         self._mona_stale = True
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # with NCCL in the step the process-group watchdog thread polls CUDA events while we capture: only thread-local
+        # capture-mode checks are compatible with that
+        mode = "thread_local" if self.distributed else "global"
+        with torch.cuda.graph(self.graph, capture_error_mode=mode):
             self.static_loss = self.micro_step(*self.static_in)
         return self
 

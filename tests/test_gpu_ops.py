@@ -417,3 +417,36 @@ def test_entry_points_are_cuda_graph_capturable():
     o2, g2 = run()
     assert torch.equal(o1, o2) and torch.equal(g1, g2)
     assert not torch.equal(o1, o0)
+
+
+@pytest.mark.parametrize("M,N,K", [(50432, 768, 64), (1000, 768, 64), (300, 800, 128), (4096, 1024, 64)])
+def test_gemm_residual_tma_aux_ring(M, N, K, monkeypatch):
+    """Short-K GEMM + residual (Mona project2): the elementwise operand reaches the epilogue through per-warp TMA rings;
+    ragged M / N (zero-filled slabs, clipped stores) and agreement with the per-lane-load epilogue (NGU_GEMM_AUXTMA is read
+    once per process, so the A/B here is against the fp64 reference)."""
+    from nextgen_uia_b200 import ops, _lib as L
+    torch.manual_seed(7)
+    A = torch.randn(M, K).to(dev(), torch.bfloat16)
+    W = (torch.randn(N, K) * 0.1).to(dev(), torch.bfloat16)
+    R = torch.randn(M, N).to(dev(), torch.bfloat16)
+    b = torch.randn(N, device=dev())
+    y = ops.gemm(A, W, bias=b, aux=R, aux_mode=L.AUX_RESIDUAL)
+    ref = A.double().cpu() @ W.double().cpu().t() + b.double().cpu() + R.double().cpu()
+    assert relerr(y, ref) < 1e-2
+
+
+@pytest.mark.parametrize("M", [50432, 777])
+def test_gemm_mona_dx_epilogue(M):
+    """NGU_AUX_MONA_DX: C = A B^T + aux + beta_r * aux2 + alpha_r (two operands through the TMA rings, per-row scalars)."""
+    from nextgen_uia_b200 import ops, _lib as L
+    torch.manual_seed(8)
+    N, K = 768, 128
+    A = torch.randn(M, K).to(dev(), torch.bfloat16)
+    W = (torch.randn(N, K) * 0.1).to(dev(), torch.bfloat16)
+    dy = torch.randn(M, N).to(dev(), torch.bfloat16)
+    x = torch.randn(M, N).to(dev(), torch.bfloat16)
+    rowab = torch.randn(M, 2, device=dev())
+    y = ops.gemm(A, W, aux=dy, aux_mode=L.AUX_MONA_DX, aux2=x, rowab=rowab)
+    ab = rowab.double().cpu()
+    ref = A.double().cpu() @ W.double().cpu().t() + dy.double().cpu() + ab[:, 1:2] * x.double().cpu() + ab[:, 0:1]
+    assert relerr(y, ref) < 1e-2

@@ -493,9 +493,10 @@ def main():
         return float(ms.item())
 
     graph_note = "eager"
-    if args.graph and world > 1 and os.environ.get("NGU_GRAPH_DP", "0") != "1":
+    if args.graph and world > 1:
         # capturing the step with its NCCL collectives (all-gather inside InfoNCE, bucketed all-reduce on a side stream) hung on
-        # this stack (torch 2.11 / NCCL 2.28, r2 2-GPU run): multi-GPU steps are launched eagerly, one process per GPU
+        # this stack (torch 2.11 / NCCL 2.28; both "global" and "thread_local" capture modes, r2 2-GPU runs): multi-GPU steps are
+        # launched eagerly, one process per GPU
         graph_note = "eager (CUDA-graph capture is single-GPU only: NCCL capture hangs on this stack)"
     elif args.graph:
         try:

@@ -574,10 +574,15 @@ def main():
 
     ops.gemm = timed_gemm
     n0 = L.launch_count()
+    ts_saved = getattr(trainer, "_text_stream", None)
+    if ts_saved is not None:
+        trainer._text_stream = None       # one stream for this pass: an event pair must bracket its own launch only
     trainer.micro_step(images_d, ids_d)   # eager (so each launch can be bracketed); every rank runs it (collectives); rank 0 reports
     torch.cuda.synchronize()
     launches = (L.launch_count() - n0) * args.steps      # kernels of THIS library per step x timed steps (graph replays launch the same nodes)
     ops.gemm = orig
+    if ts_saved is not None:
+        trainer._text_stream = ts_saved
     if rank == 0:
         t_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
         fl = sum(f for _, _, f in recs)

@@ -48,6 +48,7 @@ extern "C" {
 #define NGU_AUX_NONE 0
 #define NGU_AUX_RESIDUAL 1 /* C = act(acc + bias) + aux            (x + attn(..), x + mlp(..)) */
 #define NGU_AUX_DACT 2     /* C = (acc + bias) * aux,  aux = act'(pre) saved by the forward (backward through fc1's activation) */
+#define NGU_AUX_DACT_U8 4  /* NGU_AUX_DACT with aux = the ONE-BYTE derivative [M, ldaux] a forward with save_pre == 2 wrote (bf16 path) */
 #define NGU_AUX_MONA_DX 3  /* C = acc + aux + rowab[r].beta * aux2 + rowab[r].alpha: backward of the Mona input mix + residual
                               (src/adapters/mona.py:124-125,150) with A = [dh | dh*rstd], B = [W1*gammax ; W1*w*gamma]^T, aux = dy,
                               aux2 = x and the LayerNorm-backward row terms folded into two per-row scalars (ngu_mona_bwd_stage) */
@@ -76,7 +77,8 @@ typedef struct ngu_gemm_desc {
   const void* B2; int ldb2;  /* [N,K2] or NULL */
   const float* bias;         /* [N] fp32 or NULL */
   const void* aux; int ldaux;/* [M,N] or NULL (see NGU_AUX_*) */
-  void* Pre;      int ldpre; /* [M,N] when save_pre != 0: act'(acc + bias) (the derivative backward needs); acc + bias if act == NONE */
+  void* Pre;      int ldpre; /* [M,N] when save_pre != 0: act'(acc + bias) (the derivative backward needs); acc + bias if act == NONE.
+                                save_pre == 2 (bf16 path, act != NONE): one byte per element, q = round((d + 0.25) * 170) */
   int M, N, K, K2;
   int act, aux_mode, save_pre;
   float alpha;

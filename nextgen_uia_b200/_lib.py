@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("NGU_LIB") or os.path.join(_HERE, "libngu_b200.so")
 
 NGU_BF16, NGU_F32 = 0, 1
 ACT_NONE, ACT_GELU, ACT_QUICKGELU = 0, 1, 2
-AUX_NONE, AUX_RESIDUAL, AUX_DACT, AUX_MONA_DX = 0, 1, 2, 3
+AUX_NONE, AUX_RESIDUAL, AUX_DACT, AUX_MONA_DX, AUX_DACT_U8 = 0, 1, 2, 3, 4
 
 _c_void_p, _c_int, _c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 

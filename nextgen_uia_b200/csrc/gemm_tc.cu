@@ -68,7 +68,8 @@ struct GemmKernelParams {
   int M, N, K, K2;
   int act;       // NGU_ACT_*
   int aux_mode;  // NGU_AUX_*
-  int save_pre;  // also store (acc + bias) through tmPre
+  int save_pre;  // 1: also store act'(acc + bias) (bf16) in `pre`; 2: as one byte per element (pack_dact4)
+  int aux_u8;    // NGU_AUX_DACT operand is the one-byte form
   float alpha;   // scale on the accumulator before bias
   int prefetch;  // L2 prefetch distance for A in k-blocks (0 = off)
 };
@@ -76,7 +77,21 @@ struct GemmKernelParams {
 // Epilogue math for one 32-column chunk of one row: v = raw fp32 accumulators, ax = aux row chunk (bf16x2 words),
 // bias_l = this lane's bias[chunk column `lane`].  Compile-time ACT/AUX so the hot loop stays small (the run-time
 // switch happens once per chunk, warp-uniform).
-template <int ACT, int AUX>
+// 8-bit activation derivative (save_pre == 2 / NGU_AUX_DACT_U8): act'(pre) of GELU / QuickGELU lies in [-0.17, 1.13]; stored as
+// q = round((d + 0.25) * 170) in one byte (step 1/170 = 0.0059, |error| <= 0.003: the size of a bf16 rounding of a value near 1),
+// which halves the bytes fc1 writes for backward and the bytes the dGELU-multiply dgrad reads.
+constexpr float kDactScale = 170.0f, kDactOff = 0.25f;
+NGU_DEVINL uint32_t pack_dact4(const float (&d)[4]) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float qf = fminf(fmaxf(fmaf(d[i], kDactScale, kDactOff * kDactScale + 0.5f), 0.f), 255.f);
+    w |= uint32_t(int(qf)) << (8 * i);
+  }
+  return w;
+}
+
+template <int ACT, int AUX, bool U8 = false>
 NGU_DEVINL void epi_chunk(const uint32_t (&v)[32], const uint4 (&ax)[4], float bias_l, float alpha, bool save,
                           uint32_t (&outp)[16], uint32_t (&prep)[16]) {
   const uint32_t* axw = reinterpret_cast<const uint32_t*>(ax);
@@ -89,9 +104,16 @@ NGU_DEVINL void epi_chunk(const uint32_t (&v)[32], const uint4 (&ax)[4], float b
       x[i] = fmaf(__uint_as_float(v[4 * j4 + i]), alpha, b);
       d[i] = x[i];
     }
-    const float2 a01 = unpack_bf16x2(axw[2 * j4]);
-    const float2 a23 = unpack_bf16x2(axw[2 * j4 + 1]);
-    const float a[4] = {a01.x, a01.y, a23.x, a23.y};
+    float a[4];
+    if (U8 && AUX == NGU_AUX_DACT) {
+      const uint32_t w = axw[j4];   // 4 bytes = 4 derivatives
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = fmaf(float((w >> (8 * i)) & 0xffu), 1.0f / kDactScale, -kDactOff);
+    } else {
+      const float2 a01 = unpack_bf16x2(axw[2 * j4]);
+      const float2 a23 = unpack_bf16x2(axw[2 * j4 + 1]);
+      a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (AUX == NGU_AUX_DACT) {
@@ -105,8 +127,12 @@ NGU_DEVINL void epi_chunk(const uint32_t (&v)[32], const uint4 (&ax)[4], float b
         if (AUX == NGU_AUX_RESIDUAL) x[i] += a[i];
       }
     }
-    prep[2 * j4] = pack_bf16x2(d[0], d[1]);
-    prep[2 * j4 + 1] = pack_bf16x2(d[2], d[3]);
+    if (U8 && AUX != NGU_AUX_DACT) {
+      prep[j4] = pack_dact4(d);
+    } else {
+      prep[2 * j4] = pack_bf16x2(d[0], d[1]);
+      prep[2 * j4 + 1] = pack_bf16x2(d[2], d[3]);
+    }
     outp[2 * j4] = pack_bf16x2(x[0], x[1]);
     outp[2 * j4 + 1] = pack_bf16x2(x[2], x[3]);
   }
@@ -313,10 +339,17 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     const bool use_aux = p.aux_mode != NGU_AUX_NONE;
     const bf16* pre_out = reinterpret_cast<const bf16*>(p.pre);
 
+    const bool aux_u8 = p.aux_mode == NGU_AUX_DACT && p.aux_u8;
     auto load_aux = [&](int t, int c, uint4 (&dst)[4]) {
       const int m0 = tile_m0(t), nc = tile_n0(t) + c * kChunkCols;
       const int row = m0 + q * 32 + lane;
       const bool ok = use_aux && t < num_tiles && nc < p.N && row < p.M;
+      if (aux_u8) {   // one byte per element: 32 bytes of this lane's row
+        const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.aux) + size_t(ok ? row : 0) * p.ldaux + (ok ? nc : 0));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dst[j] = (ok && nc + j * 16 < p.N) ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
+        return;
+      }
       const uint4* ap = reinterpret_cast<const uint4*>(p.aux + size_t(ok ? row : 0) * p.ldaux + (ok ? nc : 0));
 #pragma unroll
       for (int j = 0; j < 4; ++j) dst[j] = (ok && nc + j * 8 < p.N) ? __ldg(ap + j) : make_uint4(0, 0, 0, 0);
@@ -441,11 +474,20 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
             const bool sv = p.save_pre != 0;
             const int mode = (p.aux_mode == NGU_AUX_DACT) ? 100 : p.act * 3 + p.aux_mode;  // warp-uniform
             switch (mode) {
-              case 100: epi_chunk<NGU_ACT_NONE, NGU_AUX_DACT>(v, ax, bias_l, p.alpha, false, outp, prep); break;
+              case 100:
+                if (aux_u8) epi_chunk<NGU_ACT_NONE, NGU_AUX_DACT, true>(v, ax, bias_l, p.alpha, false, outp, prep);
+                else epi_chunk<NGU_ACT_NONE, NGU_AUX_DACT>(v, ax, bias_l, p.alpha, false, outp, prep);
+                break;
               case NGU_ACT_NONE * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_NONE, NGU_AUX_RESIDUAL>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
-              case NGU_ACT_GELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_GELU, NGU_AUX_NONE>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
+              case NGU_ACT_GELU * 3 + NGU_AUX_NONE:
+                if (p.save_pre == 2) epi_chunk<NGU_ACT_GELU, NGU_AUX_NONE, true>(v, ax, bias_l, p.alpha, true, outp, prep);
+                else epi_chunk<NGU_ACT_GELU, NGU_AUX_NONE>(v, ax, bias_l, p.alpha, sv, outp, prep);
+                break;
               case NGU_ACT_GELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_GELU, NGU_AUX_RESIDUAL>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
-              case NGU_ACT_QUICKGELU * 3 + NGU_AUX_NONE: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_NONE>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
+              case NGU_ACT_QUICKGELU * 3 + NGU_AUX_NONE:
+                if (p.save_pre == 2) epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_NONE, true>(v, ax, bias_l, p.alpha, true, outp, prep);
+                else epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_NONE>(v, ax, bias_l, p.alpha, sv, outp, prep);
+                break;
               case NGU_ACT_QUICKGELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_QUICKGELU, NGU_AUX_RESIDUAL>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
               default: epi_chunk<NGU_ACT_NONE, NGU_AUX_NONE>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
             }
@@ -461,7 +503,15 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
           // slab rows are 64 bytes; SWIZZLE_64B: 16-byte piece index ^= (row >> 1) & 3
           const uint32_t rbase = slab + lane * 64;
           const uint32_t rsw = uint32_t(lane >> 1) & 3u;
-          if (!kDX && p.save_pre) {
+          if (!kDX && p.save_pre == 2) {
+            // 8-bit derivative: this lane's row chunk is 32 bytes = one full DRAM sector, stored directly
+            const int row = m0 + q * 32 + lane;
+            if (row < p.M) {
+              uint4* pb = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.pre) + size_t(row) * p.ldpre + nc);
+              if (nc < p.N) pb[0] = make_uint4(prep[0], prep[1], prep[2], prep[3]);
+              if (nc + 16 < p.N) pb[1] = make_uint4(prep[4], prep[5], prep[6], prep[7]);
+            }
+          } else if (!kDX && p.save_pre) {
             // activation derivative (saved for backward): transpose through the slab, then coalesced 64-byte row pieces
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -557,6 +607,8 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   p.rowab = a.rowab;
   p.M = a.M; p.N = a.N; p.K = a.K; p.K2 = a.K2;
   p.act = a.act; p.aux_mode = a.aux_mode; p.save_pre = a.save_pre;
+  p.aux_u8 = 0;
+  if (a.aux_mode == NGU_AUX_DACT_U8) { p.aux_mode = NGU_AUX_DACT; p.aux_u8 = 1; }
   p.alpha = a.alpha;
   {
     static int pf = -1;
@@ -609,7 +661,15 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     set_last_error("gemm_tc: K, K2 and leading dimensions must be multiples of 8 (16-byte rows)");
     return NGU_ERR_ALIGN;
   }
-  if (a.aux_mode != NGU_AUX_NONE && (a.aux == nullptr || (a.ldaux % 8) || (a.N % 8))) {
+  if (a.aux_mode == NGU_AUX_DACT_U8 && (a.aux == nullptr || (a.ldaux % 16) || (a.N % 16) || (reinterpret_cast<uintptr_t>(a.aux) & 15))) {
+    set_last_error("gemm_tc: NGU_AUX_DACT_U8 needs a 16-byte aligned aux pointer, ldaux %% 16 == 0 and N %% 16 == 0");
+    return NGU_ERR_ALIGN;
+  }
+  if (a.save_pre == 2 && (a.act == NGU_ACT_NONE || a.aux_mode != NGU_AUX_NONE || (a.ldpre % 16) || (a.N % 16) || (reinterpret_cast<uintptr_t>(a.Pre) & 15))) {
+    set_last_error("gemm_tc: save_pre = 2 (one-byte derivative) needs an activation, no aux operand, ldpre %% 16 == 0, N %% 16 == 0, aligned Pre");
+    return NGU_ERR_ARG;
+  }
+  if (a.aux_mode != NGU_AUX_NONE && a.aux_mode != NGU_AUX_DACT_U8 && (a.aux == nullptr || (a.ldaux % 8) || (a.N % 8))) {
     set_last_error("gemm_tc: aux operand needs a pointer, ldaux %% 8 == 0 and N %% 8 == 0");
     return NGU_ERR_ALIGN;
   }
@@ -651,7 +711,7 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   // NGU_GEMM_PAIR: 0 never, 1 heuristic (default), 2 whenever legal.
   static const int pair_mode = [] { const char* e = getenv("NGU_GEMM_PAIR"); return e ? atoi(e) : 1; }();
   if (a.block_n == 0 && bn == 256 && a.M > BLOCK_M && pair_mode > 0) {
-    const bool heavy_epi = a.act != NGU_ACT_NONE || a.save_pre || a.aux_mode == NGU_AUX_DACT;
+    const bool heavy_epi = a.act != NGU_ACT_NONE || a.save_pre || a.aux_mode == NGU_AUX_DACT || a.aux_mode == NGU_AUX_DACT_U8;
     if (pair_mode >= 2 || !heavy_epi || a.K + a.K2 >= 2048) return launch_gemm_tc<256, 2, true>(a, stream);
   }
   const bool no_cluster = a.block_n >= 1000;

@@ -53,7 +53,9 @@ def gemm(A, B, *, bias=None, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save
     N = B.shape[0]
     C = out if out is not None else torch.empty(M, N, device=A.device, dtype=A.dtype)
     assert C.shape == (M, N) and C.stride(1) == 1 and C.dtype == A.dtype
-    Pre = torch.empty(M, N, device=A.device, dtype=A.dtype) if save_pre else None
+    # bf16 path with an activation: the saved derivative act'(pre) travels as ONE byte per element (include/ngu_b200.h save_pre == 2)
+    pre_u8 = bool(save_pre) and A.dtype == torch.bfloat16 and act != L.ACT_NONE and N % 16 == 0 and aux is None and not force_simt
+    Pre = torch.empty(M, N, device=A.device, dtype=(torch.uint8 if pre_u8 else A.dtype)) if save_pre else None
     d = L.GemmDesc()
     d.A, d.lda, d.B, d.ldb, d.C, d.ldc = A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), C.data_ptr(), C.stride(0)
     if A2 is not None:
@@ -63,7 +65,12 @@ def gemm(A, B, *, bias=None, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save
     if bias is not None:
         d.bias = _f32(bias).data_ptr()
     if aux is not None:
-        assert aux.shape == (M, N) and aux.stride(1) == 1 and aux.dtype == A.dtype
+        if aux.dtype == torch.uint8:
+            assert aux_mode == L.AUX_DACT and A.dtype == torch.bfloat16, "one-byte operand = saved activation derivative of the bf16 path"
+            aux_mode = L.AUX_DACT_U8
+        else:
+            assert aux.dtype == A.dtype
+        assert aux.shape == (M, N) and aux.stride(1) == 1
         d.aux, d.ldaux = aux.data_ptr(), aux.stride(0)
     if save_pre:
         d.Pre, d.ldpre = Pre.data_ptr(), Pre.stride(0)
@@ -74,7 +81,7 @@ def gemm(A, B, *, bias=None, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save
         assert rowab.shape == (M, 2) and rowab.dtype == torch.float32 and rowab.is_contiguous()
         d.rowab = rowab.data_ptr()
     d.M, d.N, d.K = M, N, K
-    d.act, d.aux_mode, d.save_pre = act, aux_mode, int(save_pre)
+    d.act, d.aux_mode, d.save_pre = act, aux_mode, (2 if pre_u8 else int(save_pre))
     d.alpha = alpha
     d.dtype = (100 + L.NGU_BF16) if (force_simt and A.dtype == torch.bfloat16) else _dt(A)
     d.block_n = block_n

@@ -78,7 +78,7 @@ typedef struct ngu_gemm_desc {
   const float* bias;         /* [N] fp32 or NULL */
   const void* aux; int ldaux;/* [M,N] or NULL (see NGU_AUX_*) */
   void* Pre;      int ldpre; /* [M,N] when save_pre != 0: act'(acc + bias) (the derivative backward needs); acc + bias if act == NONE.
-                                save_pre == 2 (bf16 path, act != NONE): one byte per element, q = round((d + 0.25) * 170) */
+                                save_pre == 2 (bf16 path, act != NONE): one byte per element, q = round(d * 170 + 43) */
   int M, N, K, K2;
   int act, aux_mode, save_pre;
   float alpha;

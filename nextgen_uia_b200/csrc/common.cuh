@@ -437,19 +437,61 @@ NGU_DEVINL float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed fp32 pairs (FFMA2 / FADD2 / FMUL2): one issue slot per two lanes' worth of work; the FMA pipe rate is unchanged
+// (128 lanes/clk/SM), so these pay where a loop is issue-bound, not FMA-bound.
+NGU_DEVINL float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)), "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+NGU_DEVINL float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+NGU_DEVINL float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
 constexpr float kGa0 = 7.97704294e-01f, kGa1 = 3.68194288e-02f, kGa2 = -3.20606757e-04f;
+// The odd polynomial u(x) = x * P(x^2) turns over at x^2 = 133.7; tanh(u) is already exactly +-1 in fp32 for |x| >= 7.3, so x^2
+// is clamped to 100 inside P (and P') and u stays monotone for every finite x.
+constexpr float kGeluS2Max = 100.0f;
 NGU_DEVINL float gelu_fast(float x) {
-  const float x2 = x * x;
+  const float x2 = fminf(x * x, kGeluS2Max);
   const float t = tanh_approx(x * fmaf(fmaf(kGa2, x2, kGa1), x2, kGa0));
   return x * fmaf(0.5f, t, 0.5f);
 }
 NGU_DEVINL void gelu_and_grad(float x, float& y, float& dy) {
-  const float x2 = x * x;
+  const float x2 = fminf(x * x, kGeluS2Max);
   const float t = tanh_approx(x * fmaf(fmaf(kGa2, x2, kGa1), x2, kGa0));
   const float cdf = fmaf(0.5f, t, 0.5f);
   const float hdu = fmaf(fmaf(2.5f * kGa2, x2, 1.5f * kGa1), x2, 0.5f * kGa0);   // u'(x) / 2
   y = x * cdf;
   dy = fmaf(x * fmaf(-t, t, 1.0f), hdu, cdf);
+}
+// The same on a register pair: 12 packed FMA-pipe instructions (+ 2 MUFU, 2 FMNMX) for two elements.
+template <bool GRAD>
+NGU_DEVINL void gelu_pair(float2 x, float2& y, float2& dy) {
+  float2 s = fmul2(x, x);
+  s.x = fminf(s.x, kGeluS2Max);
+  s.y = fminf(s.y, kGeluS2Max);
+  const float2 pl = ffma2(ffma2(make_float2(kGa2, kGa2), s, make_float2(kGa1, kGa1)), s, make_float2(kGa0, kGa0));
+  const float2 u = fmul2(x, pl);
+  const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  const float2 cdf = ffma2(make_float2(0.5f, 0.5f), t, make_float2(0.5f, 0.5f));
+  y = fmul2(x, cdf);
+  if (GRAD) {
+    // dy = cdf + (1 - t^2) * x * u'/2, written as (t^2 - 1) * (x * -u'/2) + cdf: no negated operands for the packed forms
+    const float2 nh = ffma2(ffma2(make_float2(-2.5f * kGa2, -2.5f * kGa2), s, make_float2(-1.5f * kGa1, -1.5f * kGa1)), s,
+                            make_float2(-0.5f * kGa0, -0.5f * kGa0));
+    const float2 q = ffma2(t, t, make_float2(-1.0f, -1.0f));
+    dy = ffma2(q, fmul2(x, nh), cdf);
+  }
 }
 NGU_DEVINL float lg2_approx(float x) {
   float y;

@@ -36,12 +36,15 @@ constexpr int kSlabBytes = 32 * kChunkCols * 2;  // 32 rows x 32 bf16 (64-byte r
 // epilogue IS the kernel: per-lane loads of 64-byte row pieces cost 32 LSU wavefronts per instruction and bounded those
 // launches at ~2.5 TB/s; the TMA engine writes the slabs without touching the LSU and keeps kAuxDepth slabs per warp in flight.
 constexpr int kAuxDepth = 2;
-template <int BLOCK_N, bool kPair = false, int kAuxTma = 0>
+// kPreU8: the one-byte activation derivative (save_pre == 2) leaves through its own per-warp 32 x 32-byte slab and a TMA store:
+// per-lane 16-byte stores (64 partial-sector requests per chunk) cost fc1 ~70 us of 280.
+constexpr int kPreSlabBytes = 32 * kChunkCols;
+template <int BLOCK_N, bool kPair = false, int kAuxTma = 0, bool kPreU8 = false>
 struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = (kPair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // pair mode: each CTA holds half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytes = kNumEpiWarps * kSlabBytes;  // one 32x32 slab per epilogue warp
+  static constexpr int kEpiBytes = kNumEpiWarps * (kSlabBytes + (kPreU8 ? kPreSlabBytes : 0));  // one 32x32 slab per epilogue warp (+ derivative bytes)
   static constexpr int kAuxBytes = kNumEpiWarps * kAuxDepth * kAuxTma * kSlabBytes;
   static constexpr int kBarBytes = 1024;  // mbarriers + tmem ptr
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/;
@@ -55,6 +58,7 @@ struct GemmKernelParams {
   CUtensorMap tmA, tmB, tmA2, tmB2, tmC;
   CUtensorMap tmBh, tmB2h;  // B with a half-height box (cluster multicast: each CTA fetches BLOCK_N/2 rows)
   CUtensorMap tmAux, tmAux2;  // kAuxTma: 32 x 32 boxes (SWIZZLE_64B) of the elementwise operands
+  CUtensorMap tmPre;          // kPreU8: the [M, N] byte matrix seen as [M, N/2] bf16, boxes of 32 rows x 16 (= 32 bytes)
   void* pre;   // [M, ldpre] pre-activation output (save_pre)
   int ldpre;
   const float* bias;  // [N] fp32 or nullptr
@@ -78,17 +82,64 @@ struct GemmKernelParams {
 // bias_l = this lane's bias[chunk column `lane`].  Compile-time ACT/AUX so the hot loop stays small (the run-time
 // switch happens once per chunk, warp-uniform).
 // 8-bit activation derivative (save_pre == 2 / NGU_AUX_DACT_U8): act'(pre) of GELU / QuickGELU lies in [-0.17, 1.13]; stored as
-// q = round((d + 0.25) * 170) in one byte (step 1/170 = 0.0059, |error| <= 0.003: the size of a bf16 rounding of a value near 1),
+// q = round(d * 170 + 43) in one byte (step 1/170 = 0.0059, |error| <= 0.003: the size of a bf16 rounding of a value near 1),
 // which halves the bytes fc1 writes for backward and the bytes the dGELU-multiply dgrad reads.
-constexpr float kDactScale = 170.0f, kDactOff = 0.25f;
+constexpr float kDactScale = 170.0f, kDactZero = 43.0f, kDactOff = kDactZero / kDactScale;
 NGU_DEVINL uint32_t pack_dact4(const float (&d)[4]) {
   uint32_t w = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float qf = fminf(fmaxf(fmaf(d[i], kDactScale, kDactOff * kDactScale + 0.5f), 0.f), 255.f);
+    const float qf = fminf(fmaxf(fmaf(d[i], kDactScale, kDactZero + 0.5f), 0.f), 255.f);
     w |= uint32_t(int(qf)) << (8 * i);
   }
   return w;
+}
+// The same quantisation through the 2^23 magic add: fma rounds d * 170 + 43 to the nearest integer, which then sits in the low
+// mantissa byte (d in [-0.25, 1.24] covers every finite input of both activations); three PRMTs gather four bytes.
+NGU_DEVINL uint32_t quant_dact4(float2 d01, float2 d23) {
+  const float2 k = make_float2(kDactScale, kDactScale), m = make_float2(8388608.0f + kDactZero, 8388608.0f + kDactZero);
+  const float2 a = ffma2(d01, k, m), b = ffma2(d23, k, m);
+  const uint32_t lo = __byte_perm(__float_as_uint(a.x), __float_as_uint(a.y), 0x0040);
+  const uint32_t hi = __byte_perm(__float_as_uint(b.x), __float_as_uint(b.y), 0x0040);
+  return __byte_perm(lo, hi, 0x5410);
+}
+
+// Packed-pair forms of the two heaviest epilogues of the block.  With 128 x 256 accumulators per tile and a K = 768 mainloop of
+// ~6100 clk, the scalar GELU + derivative epilogue (~22 issue slots per element, 5900 clk per tile over four schedulers) set the
+// pace of fc1; on register pairs it needs ~10 (FMA pipe: 14 clk per 32 elements) and the tensor pipe is the bound again.
+//   fc1 forward (bf16):  y = gelu(acc * alpha + bias), derivative as one byte.  bias4 = this chunk's 32 biases or nullptr.
+template <bool SAVE>
+NGU_DEVINL void epi_chunk_gelu_x2(const uint32_t (&v)[32], const float4* bias4, float alpha, uint32_t (&outp)[16], uint32_t (&prep)[16]) {
+  const float2 al = make_float2(alpha, alpha);
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 b = bias4 != nullptr ? __ldg(bias4 + j4) : make_float4(0.f, 0.f, 0.f, 0.f);   // warp-uniform address: one L1 broadcast
+    const float2 x01 = ffma2(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), al, make_float2(b.x, b.y));
+    const float2 x23 = ffma2(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), al, make_float2(b.z, b.w));
+    float2 y01, y23, d01, d23;
+    gelu_pair<SAVE>(x01, y01, d01);
+    gelu_pair<SAVE>(x23, y23, d23);
+    outp[2 * j4] = pack_bf16x2(y01.x, y01.y);
+    outp[2 * j4 + 1] = pack_bf16x2(y23.x, y23.y);
+    if (SAVE) prep[j4] = quant_dact4(d01, d23);
+  }
+}
+//   fc2 dgrad (bf16):  out = acc * alpha * (q - 43) / 170 with q the saved derivative byte (no bias on this path)
+NGU_DEVINL void epi_chunk_dact_u8_x2(const uint32_t (&v)[32], const uint4 (&ax)[4], float alpha, uint32_t (&outp)[16]) {
+  const uint32_t* axw = reinterpret_cast<const uint32_t*>(ax);
+  const float2 al = make_float2(alpha / kDactScale, alpha / kDactScale);
+  const float2 nz = make_float2(-(8388608.0f + kDactZero), -(8388608.0f + kDactZero));
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const uint32_t w = axw[j4];
+    // byte -> 2^23 + q (PRMT into the mantissa of 0x4B000000), minus (2^23 + 43): exact
+    const float2 e01 = fadd2(make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651))), nz);
+    const float2 e23 = fadd2(make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653))), nz);
+    const float2 o01 = fmul2(fmul2(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), al), e01);
+    const float2 o23 = fmul2(fmul2(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), al), e23);
+    outp[2 * j4] = pack_bf16x2(o01.x, o01.y);
+    outp[2 * j4 + 1] = pack_bf16x2(o23.x, o23.y);
+  }
 }
 
 template <int ACT, int AUX, bool U8 = false>
@@ -154,18 +205,19 @@ NGU_DEVINL void epi_chunk_dx(const uint32_t (&v)[32], const uint4 (&ax)[4], cons
   }
 }
 
-template <int BLOCK_N, int kCluster, bool kPair, bool kDX = false, int kAuxTma = 0>
+template <int BLOCK_N, int kCluster, bool kPair, bool kDX = false, int kAuxTma = 0, bool kPreU8 = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
   pdl_prologue();
   static_assert(!kPair || kCluster == 2, "pair mode is a 2-CTA cluster");
   static_assert(kAuxTma == 0 || kAuxTma == (kDX ? 2 : 1), "TMA aux rings: one operand (residual) or two (Mona dx)");
-  using Cfg = GemmCfg<BLOCK_N, kPair, kAuxTma>;
+  using Cfg = GemmCfg<BLOCK_N, kPair, kAuxTma, kPreU8>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA0 = smem_base;
   const uint32_t sB0 = smem_base + Cfg::kStages * Cfg::kABytes;
   const uint32_t sEpi = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t sPre = sEpi + kNumEpiWarps * kSlabBytes;   // kPreU8: [epilogue warp] 1 KB slabs
   const uint32_t sAux = sEpi + Cfg::kEpiBytes;        // [epilogue warp][slot][operand] 2 KB slabs
   const uint32_t sBar = sAux + Cfg::kAuxBytes;
   // barrier slots (8 bytes each)
@@ -371,6 +423,11 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
       if (nc >= p.N) return;
       const int sl = n % kAuxDepth;
       const uint32_t dst = sAux + uint32_t((ew * kAuxDepth + sl) * kAuxTma) * kSlabBytes, bar = aux_bar(ew, sl);
+      if (aux_u8) {   // derivative bytes: 32 rows x 32 B, no swizzle (the byte matrix is mapped as [M, N/2] bf16)
+        mbar_arrive_expect_tx(bar, kPreSlabBytes);
+        tma_load_2d(dst, &p.tmAux, bar, nc >> 1, tile_m0(t) + q * 32, kEvictFirst);
+        return;
+      }
       mbar_arrive_expect_tx(bar, kAuxTma * kSlabBytes);
       tma_load_2d(dst, &p.tmAux, bar, nc, tile_m0(t) + q * 32, kEvictFirst);
       if (kAuxTma == 2) tma_load_2d(dst + kSlabBytes, &p.tmAux2, bar, nc, tile_m0(t) + q * 32, kEvictFirst);
@@ -416,8 +473,13 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
               const int sl = item % kAuxDepth;
               mbar_wait(aux_bar(ew, sl), (aux_ph >> sl) & 1u);
               aux_ph ^= 1u << sl;
-              const uint32_t src = sAux + uint32_t((ew * kAuxDepth + sl) * kAuxTma) * kSlabBytes + lane * 64;
+              const uint32_t src = sAux + uint32_t((ew * kAuxDepth + sl) * kAuxTma) * kSlabBytes + lane * (aux_u8 ? 32 : 64);
               const uint32_t sw = uint32_t(lane >> 1) & 3u;
+              if (aux_u8) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ax[j].x), "=r"(ax[j].y), "=r"(ax[j].z), "=r"(ax[j].w) : "r"(src + 16u * j));
+              } else
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint32_t a = src + ((uint32_t(j) ^ sw) << 4);
@@ -475,12 +537,17 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
             const int mode = (p.aux_mode == NGU_AUX_DACT) ? 100 : p.act * 3 + p.aux_mode;  // warp-uniform
             switch (mode) {
               case 100:
-                if (aux_u8) epi_chunk<NGU_ACT_NONE, NGU_AUX_DACT, true>(v, ax, bias_l, p.alpha, false, outp, prep);
+                if (aux_u8 && p.bias == nullptr) epi_chunk_dact_u8_x2(v, ax, p.alpha, outp);
+                else if (aux_u8) epi_chunk<NGU_ACT_NONE, NGU_AUX_DACT, true>(v, ax, bias_l, p.alpha, false, outp, prep);
                 else epi_chunk<NGU_ACT_NONE, NGU_AUX_DACT>(v, ax, bias_l, p.alpha, false, outp, prep);
                 break;
               case NGU_ACT_NONE * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_NONE, NGU_AUX_RESIDUAL>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
               case NGU_ACT_GELU * 3 + NGU_AUX_NONE:
-                if (p.save_pre == 2) epi_chunk<NGU_ACT_GELU, NGU_AUX_NONE, true>(v, ax, bias_l, p.alpha, true, outp, prep);
+                if (p.save_pre != 1 && nc + kChunkCols <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+                  const float4* b4 = p.bias != nullptr ? reinterpret_cast<const float4*>(p.bias + nc) : nullptr;
+                  if (p.save_pre == 2) epi_chunk_gelu_x2<true>(v, b4, p.alpha, outp, prep);
+                  else epi_chunk_gelu_x2<false>(v, b4, p.alpha, outp, prep);
+                } else if (p.save_pre == 2) epi_chunk<NGU_ACT_GELU, NGU_AUX_NONE, true>(v, ax, bias_l, p.alpha, true, outp, prep);
                 else epi_chunk<NGU_ACT_GELU, NGU_AUX_NONE>(v, ax, bias_l, p.alpha, sv, outp, prep);
                 break;
               case NGU_ACT_GELU * 3 + NGU_AUX_RESIDUAL: epi_chunk<NGU_ACT_GELU, NGU_AUX_RESIDUAL>(v, ax, bias_l, p.alpha, sv, outp, prep); break;
@@ -503,7 +570,12 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
           // slab rows are 64 bytes; SWIZZLE_64B: 16-byte piece index ^= (row >> 1) & 3
           const uint32_t rbase = slab + lane * 64;
           const uint32_t rsw = uint32_t(lane >> 1) & 3u;
-          if (!kDX && p.save_pre == 2) {
+          if (kPreU8 && p.save_pre == 2) {
+            // 8-bit derivative: 32 rows x 32 bytes staged in this warp's byte slab, stored by TMA together with the C chunk
+            const uint32_t pa = sPre + ew * kPreSlabBytes + lane * 32;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa), "r"(prep[0]), "r"(prep[1]), "r"(prep[2]), "r"(prep[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa + 16), "r"(prep[4]), "r"(prep[5]), "r"(prep[6]), "r"(prep[7]) : "memory");
+          } else if (!kDX && p.save_pre == 2) {
             // 8-bit derivative: this lane's row chunk is 32 bytes = one full DRAM sector, stored directly
             const int row = m0 + q * 32 + lane;
             if (row < p.M) {
@@ -548,6 +620,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&p.tmC, slab, nc, m0 + q * 32);
+            if (kPreU8 && p.save_pre == 2) tma_store_2d(&p.tmPre, sPre + ew * kPreSlabBytes, nc >> 1, m0 + q * 32);
             tma_store_commit();
           }
         }
@@ -566,9 +639,9 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
   }
 }
 
-template <int BLOCK_N, int kCluster, bool kPair = false, bool kDX = false, int kAuxTma = 0>
+template <int BLOCK_N, int kCluster, bool kPair = false, bool kDX = false, int kAuxTma = 0, bool kPreU8 = false>
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, kPair, kAuxTma>;
+  using Cfg = GemmCfg<BLOCK_N, kPair, kAuxTma, kPreU8>;
   static_assert(Cfg::kStages >= 2, "operand ring too shallow");
   GemmKernelParams p;
   memset(&p, 0, sizeof(p));
@@ -590,12 +663,20 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
     p.cf32 = reinterpret_cast<float*>(a.C);
     p.ldcf = a.ldc;
   } else if ((rc = make_tmap_2d_bf16(&p.tmC, a.C, a.M, a.N, a.ldc, 32, kChunkCols, 2))) return rc;
-  if (kAuxTma > 0) {
+  if (kAuxTma > 0 && a.aux_mode == NGU_AUX_DACT_U8) {
+    if ((rc = make_tmap_2d_bf16(&p.tmAux, a.aux, a.M, a.N / 2, a.ldaux / 2, 32, kChunkCols / 2, 0))) return rc;
+    p.tmAux2 = p.tmAux;
+  } else if (kAuxTma > 0) {
     if ((rc = make_tmap_2d_bf16(&p.tmAux, a.aux, a.M, a.N, a.ldaux, 32, kChunkCols, 2))) return rc;
     if (kAuxTma == 2) { if ((rc = make_tmap_2d_bf16(&p.tmAux2, a.aux2, a.M, a.N, a.ldaux2, 32, kChunkCols, 2))) return rc; }
     else p.tmAux2 = p.tmAux;
   } else {
     p.tmAux = p.tmA; p.tmAux2 = p.tmA;
+  }
+  if (kPreU8) {
+    if ((rc = make_tmap_2d_bf16(&p.tmPre, a.Pre, a.M, a.N / 2, a.ldpre / 2, 32, kChunkCols / 2, 0))) return rc;
+  } else {
+    p.tmPre = p.tmA;
   }
   p.pre = a.Pre;
   p.ldpre = a.ldpre;
@@ -618,7 +699,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
 
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kCluster, kPair, kDX, kAuxTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kCluster, kPair, kDX, kAuxTma, kPreU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_status(e, "gemm_tc smem attribute");
     attr_done = true;
   }
@@ -642,7 +723,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kCluster, kPair, kDX, kAuxTma>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kCluster, kPair, kDX, kAuxTma, kPreU8>, p);
   count_launch(1);
   if (e != cudaSuccess) return cuda_status(e, "gemm_tc launch");
   return cuda_status(cudaGetLastError(), "gemm_tc");
@@ -693,6 +774,19 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
       a.N > 128 && a.K + a.K2 <= 256) {
     static const int auxtma = [] { const char* e = getenv("NGU_GEMM_AUXTMA"); return e ? atoi(e) : 1; }();
     if (auxtma) return launch_gemm_tc<256, 2, false, false, 1>(a, stream);   // Mona project2 + residual (K = 64)
+  }
+  if (a.save_pre == 2 && a.block_n == 0 && a.M > BLOCK_M && a.N > 128) {
+    // fc1 forward: bias + activation + one-byte derivative, both outputs through TMA stores (NGU_GEMM_PREU8: 0 off, 1 multicast cluster, 2 CTA pair)
+    static const int preu8 = [] { const char* e = getenv("NGU_GEMM_PREU8"); return e ? atoi(e) : 1; }();
+    if (preu8 == 1) return launch_gemm_tc<256, 2, false, false, 0, true>(a, stream);
+    if (preu8 == 2) return launch_gemm_tc<256, 2, true, false, 0, true>(a, stream);
+  }
+  if (a.block_n == 0 && a.M > BLOCK_M && a.N > 128 && a.c_dtype != NGU_F32 && a.act == NGU_ACT_NONE && !a.save_pre &&
+      ((a.aux_mode == NGU_AUX_DACT_U8 && a.bias == nullptr) || a.aux_mode == NGU_AUX_RESIDUAL)) {
+    // elementwise operand (residual, or the derivative bytes of the fc2 dgrad) through the per-warp TMA rings of the CTA-pair variant
+    // (NGU_GEMM_AUXPAIR: bit 0 residual, bit 1 derivative bytes)
+    static const int auxpair = [] { const char* e = getenv("NGU_GEMM_AUXPAIR"); return e ? atoi(e) : 3; }();
+    if (auxpair & (a.aux_mode == NGU_AUX_RESIDUAL ? 1 : 2)) return launch_gemm_tc<256, 2, true, false, 1>(a, stream);
   }
   int bn = a.block_n;
   if (bn == 0) bn = (a.N > 128) ? 256 : (a.N > 64 ? 128 : 64);

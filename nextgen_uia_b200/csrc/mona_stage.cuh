@@ -94,18 +94,6 @@ NGU_DEVINL void stencil_stream(const bf16* in, const float (&k)[49], float bias,
 // ADJACENT output columns: the tap is a scalar operand (SASS broadcasts a 32-bit register: FFMA2 Rd, Rk.F32, Rwin.F32x2, Racc),
 // the window operand is the pair (win[i], win[i+1]).  Pairs starting at even and at odd window positions are kept as two
 // register arrays so no operand needs re-packing inside the tap loop.
-NGU_DEVINL float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)), "l"(reinterpret_cast<unsigned long long&>(c)));
-  return d;
-}
-NGU_DEVINL float2 fadd2(float2 a, float2 b) {
-  float2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
-  return d;
-}
 NGU_DEVINL float2 bf16pair_to_float2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
 
 template <bool FLIP, typename Emit>

@@ -44,8 +44,8 @@ def test_gemm_epilogues(dtype):
     C, Der = ops.gemm(A, B, bias=bias, act=L.ACT_GELU, save_pre=True)
     bb = base.clone().requires_grad_(True)
     (dg_ref,) = torch.autograd.grad(F.gelu(bb).sum(), bb)
-    def deq(D):   # bf16 path: the derivative is stored as one byte per element, q = round((d + 0.25) * 170)
-        return D.double().cpu() / 170.0 - 0.25 if D.dtype == torch.uint8 else D
+    def deq(D):   # bf16 path: the derivative is stored as one byte per element, q = round(d * 170 + 43)
+        return (D.double().cpu() - 43.0) / 170.0 if D.dtype == torch.uint8 else D
     assert (Der.dtype == torch.uint8) == (dtype == torch.bfloat16)
     assert relerr(deq(Der), dg_ref) < TOL[dtype] and relerr(C, F.gelu(base)) < TOL[dtype]
     if dtype == torch.bfloat16:   # and the backward epilogue consumes that byte form: (acc) * act'(pre)

@@ -563,6 +563,371 @@ __global__ void __launch_bounds__(kFwdPThreads, 1) attn_fwd_persistent_kernel(co
   }
 }
 
+// ---- pipelined forward ------------------------------------------------------------------------------------
+// One CTA per SM walks (batch, head) items; a "unit" is one 128-row query tile of an item.  The serial chain of the per-tile
+// kernel (load -> S -> softmax -> P -> O -> store, 13 k cycles per item and SM with every pipe under 30 % busy) is cut into two
+// roles that run one unit apart, with S double-buffered in TMEM so the tensor pipe works a unit ahead of the softmax:
+//   warps 0-15   softmax: FOUR threads per query row (warps w, w+4, w+8, w+12 share TMEM lane quarter w&3 and split the kv axis
+//                in runs of 8-column chunks).  A thread reads its run of S ONCE (<= 64 fp32 registers), exchanges the row max
+//                through smem, and writes P = exp2(..) back as bf16 over the S columns; partial row sums go to smem.
+//   warps 16-19  epilogue: one thread per query row reads O, applies 1/rowsum, stages the tile in the unit's (dead) Q slot for a
+//                TMA store and writes the log-sum-exp.  Warp 16 is also the control warp: its lane 0 issues O(u) = P(u) V when
+//                P(u) is written, S(u+2) when O(u) has left the buffer, and the TMA loads (Q three units ahead, K/V of item
+//                m + kvbufs when item m's last O is complete).  One thread issuing stores and loads orders them without barriers.
+// 20 warps = 5 per scheduler: 96 registers per thread, so the S run stays in registers (22 warps would cap at 80 and spill it).
+// TMEM: two buffers of 256 columns: S in [0, npad), P (bf16) aliases [0, npad/2), O in [128, 192) (over dead S columns).
+// Key padding (kv_len) and the causal mask are one upper bound on the key index per row, applied as -inf before the row max.
+constexpr int kFwd3SoftmaxWarps = 16;
+constexpr int kFwd3Threads = 32 * (kFwd3SoftmaxWarps + 4);
+constexpr int kFwd3Smem = 12 * kTileBytes + 2 * 2 * 2048 + 2 * 512 + 1024 + 1024;   // K/V 8 tiles, Q 4 tiles, max/sum tables, barriers, alignment
+
+// kRun: 8-column chunks of S one softmax thread may hold (7: N <= 224, 56 registers; 8: N <= 256)
+template <int kRun>
+__global__ void __launch_bounds__(kFwd3Threads, 1) attn_fwd_pipe_kernel(const __grid_constant__ AttnTcParams p) {
+  pdl_prologue();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TRACE_DECL;
+  const int N = p.N, D = p.H * DH;
+  const int ntiles = (N + TILE - 1) / TILE;      // 1 or 2
+  const int kvbufs = ntiles == 2 ? 2 : 4;        // K/V buffers in the 8-tile region (one tile each of K and V when N <= 128)
+  auto sK = [&](int j) { return base + uint32_t(j * 2 * ntiles) * kTileBytes; };
+  auto sV = [&](int j) { return base + uint32_t(j * 2 * ntiles + ntiles) * kTileBytes; };
+  auto sQ = [&](int slot) { return base + uint32_t(8 + slot) * kTileBytes; };
+  const uint32_t sMax = base + 12 * kTileBytes;       // [buffer][4 column runs][128 rows] partial row maxima
+  const uint32_t sSum = sMax + 2 * 2048;              // [buffer][4][128] partial row sums
+  const uint32_t sMxF = sSum + 2 * 2048;              // [buffer][128] final row max (for the log-sum-exp)
+  const uint32_t sBar = sMxF + 2 * 512;
+  auto bar_kv = [&](int j) { return sBar + 8u * j; };            // 4: K/V of the item in buffer j landed
+  auto bar_q = [&](int s) { return sBar + 32u + 8u * s; };       // 4: Q tile of unit (k & 3) landed
+  auto bar_s = [&](int g) { return sBar + 64u + 8u * g; };       // 2: S of the buffer's unit complete
+  auto bar_p = [&](int g) { return sBar + 80u + 8u * g; };       // 2: P written (one arrival per softmax warp)
+  auto bar_o = [&](int g) { return sBar + 96u + 8u * g; };       // 2: O complete
+  auto bar_drained = [&](int g) { return sBar + 112u + 8u * g; };  // 2: O read out (one arrival per epilogue warp)
+  const uint32_t sTmem = sBar + 128u;
+
+  const int npad = (N + 15) & ~15;               // MMA N extent over the kv axis
+  const int rows1 = ntiles == 2 ? ((N - TILE + 15) & ~15) : 0;
+  const int items = p.B * p.H;
+  const int n_local = (items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int n_units = n_local * ntiles;
+  constexpr int kCtlWarp = kFwd3SoftmaxWarps;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmQKV);
+    tma_prefetch_desc(&p.tmQKV1);
+    tma_prefetch_desc(&p.tmO3);
+    for (int j = 0; j < 4; ++j) { mbar_init(bar_kv(j), 1); mbar_init(bar_q(j), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_s(b), 1); mbar_init(bar_p(b), kFwd3SoftmaxWarps); mbar_init(bar_o(b), 1); mbar_init(bar_drained(b), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kCtlWarp) {
+    tmem_alloc(sTmem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(sTmem));
+
+  if (warp < kFwd3SoftmaxWarps) {
+    // ================================ softmax ================================
+    const int q = warp & 3, hf = warp >> 2;
+    const int rt = q * 32 + lane;              // row within the tile (= TMEM lane)
+    const float c = p.scale * kLog2e;
+    const int nch = npad / 8;                  // 8-column chunks of the kv axis (<= 32), split into four runs of <= kRun
+    const int cbase = nch >> 2, crem = nch & 3;
+    const int cnt = cbase + (hf < crem ? 1 : 0);
+    const int c0 = hf * cbase + (hf < crem ? hf : crem);
+    // v holds this thread's run of S.  kPrefetch refills the registers of each finished chunk of P(k) with the same chunk of
+    // S(k+1) so that the S read-out (TMEM reads run at 16 B/clk per scheduler: ~1600 cycles per unit) overlaps the exp2 phase.
+    // Measured: it does not overlap (139 us against 107 us): LDTM and MUFU instructions leave through the same dispatch queue, and
+    // a queue full of LDTMs waiting for the read port holds the MUFUs back.  Kept off; the read-out stays a phase of its own.
+    constexpr bool kPrefetch = false;
+    uint32_t v[kRun][8];
+    bool have = false;                         // v already holds S(k)
+    for (int k = 0; k < n_units; ++k) {
+      const int n = ntiles == 2 ? k >> 1 : k, t = ntiles == 2 ? k & 1 : 0;
+      const int buf = k & 1;
+      const uint32_t trow = tmem + uint32_t(buf) * 256u + (uint32_t(q * 32) << 16);
+      const uint32_t trow1 = tmem + uint32_t(buf ^ 1) * 256u + (uint32_t(q * 32) << 16);
+      const bool live = t * TILE + q * 32 < N;   // warp-uniform: any valid query row in this warp
+      const bool nxt = k + 1 < n_units;
+      const bool live1 = nxt && ((ntiles == 2 ? (k + 1) & 1 : 0) * TILE + q * 32 < N);
+      const bool pf1 = kPrefetch && live1;
+      const uint32_t ph1 = uint32_t((k + 1) >> 1) & 1u;
+      int Lrow = N, Lwarp = N;                   // this row's key limit / the smallest limit in this warp
+      if (p.kv_len != nullptr || p.causal) {
+        const int item = int(blockIdx.x) + n * int(gridDim.x);
+        int Lk = p.kv_len ? __ldg(p.kv_len + item / p.H) : N;   // valid keys of this sequence (key-padding mask = suffix of the row)
+        Lk = Lk < 1 ? 1 : (Lk > N ? N : Lk);
+        Lrow = p.causal ? min(Lk, min(t * TILE + rt, N - 1) + 1) : Lk;
+        Lwarp = p.causal ? min(Lk, min(t * TILE + q * 32, N - 1) + 1) : Lk;
+      }
+      // dead warps (all rows past the sequence end) skip the math but keep in step with the barriers' phases
+      if (warp == 0) TRACE(40, k);
+      if (!have) {
+        mbar_wait(bar_s(buf), uint32_t(k >> 1) & 1u);
+        tc_fence_after();
+        if (live) {
+#pragma unroll
+          for (int kk = 0; kk < kRun; ++kk)
+            if (kk < cnt) tmem_ld8(trow + (c0 + kk) * 8, v[kk]);
+          tmem_ld_wait();
+        }
+      }
+      if (warp == 0) TRACE(42, k);
+      bool ready = false;                        // S(k+1) is complete
+      uint32_t pfmask = 0;                       // chunks of S(k+1) already requested
+      if (live) {
+        // ---- row max over this thread's columns; masked keys become -inf (and exp2 of them 0)
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int kk = 0; kk < kRun; ++kk) {
+          if (kk < cnt) {
+            const int col0 = (c0 + kk) * 8;
+            if (col0 + 8 > Lwarp) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[kk][i] = (col0 + i < Lrow) ? v[kk][i] : 0xff800000u;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i += 4)
+              m4[(2 * kk + (i >> 2)) & 3] = fmaxf(fmaxf(m4[(2 * kk + (i >> 2)) & 3], fmaxf(__uint_as_float(v[kk][i]), __uint_as_float(v[kk][i + 1]))),
+                                                  fmaxf(__uint_as_float(v[kk][i + 2]), __uint_as_float(v[kk][i + 3])));
+          }
+        }
+        float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        const uint32_t mrow = sMax + uint32_t(buf) * 2048u + 4u * uint32_t(rt);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(mrow + 512u * uint32_t(hf)), "f"(mx) : "memory");
+        if (warp == 0) TRACE(44, k);
+        named_bar_sync(1 + q, 128);
+        if (warp == 0) TRACE(46, k);
+        {
+          float o0, o1, o2, o3;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o0) : "r"(mrow));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o1) : "r"(mrow + 512u));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o2) : "r"(mrow + 1024u));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o3) : "r"(mrow + 1536u));
+          mx = fmaxf(fmaxf(o0, o1), fmaxf(o2, o3));
+        }
+        const float mc = mx * c;
+        // ---- P = exp2(S*c - max*c) as bf16 pairs over this thread's own S registers; every thread of the row has finished
+        //      reading S (it sits in registers since before the barrier), so P may overwrite it in TMEM right away
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < kRun; ++kk) {
+          if (kk < cnt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(v[kk][2 * i]), c, -mc));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(v[kk][2 * i + 1]), c, -mc));
+              s0 += p0;
+              s1 += p1;
+              v[kk][i] = pack_bf16x2(p0, p1);
+            }
+            tmem_st4(trow + (c0 + kk) * 4, v[kk]);
+            if (pf1) {
+              if (!ready) {
+                ready = __all_sync(0xffffffffu, mbar_try_wait(bar_s(buf ^ 1), ph1));
+                if (ready) tc_fence_after();
+              }
+              if (ready) {
+                tmem_ld8(trow1 + (c0 + kk) * 8, v[kk]);
+                pfmask |= 1u << kk;
+              }
+            }
+          }
+        }
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sSum + uint32_t(buf) * 2048u + 512u * uint32_t(hf) + 4u * uint32_t(rt)), "f"(s0 + s1) : "memory");
+        if (hf == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sMxF + uint32_t(buf) * 512u + 4u * uint32_t(rt)), "f"(mx) : "memory");
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p(buf));
+      if (warp == 0) TRACE(48, k);
+      if (warp == 15) TRACE(49, k);
+      if (warp == 12) TRACE(47, k);
+      have = false;
+      if (nxt) {
+        if (!ready) {
+          mbar_wait(bar_s(buf ^ 1), ph1);
+          tc_fence_after();
+        }
+        if (live1) {
+#pragma unroll
+          for (int kk = 0; kk < kRun; ++kk)
+            if (kk < cnt && !((pfmask >> kk) & 1u)) tmem_ld8(trow1 + (c0 + kk) * 8, v[kk]);
+          tmem_ld_wait();
+        }
+        have = true;
+      }
+    }
+  } else {
+    // ================================ epilogue + control ================================
+    const int q = warp & 3;
+    const int rt = q * 32 + lane;
+    const bool ctl = warp == kCtlWarp;
+    // The control warp walks its role code as a whole (warp-uniform values stay in uniform registers, where the MMA / TMA
+    // instructions take their operands); the elected lane (the same one every time) issues, so program order is issue order.
+    const uint32_t idesc_s = make_idesc_bf16(TILE, npad);
+    constexpr uint32_t idesc_o = make_idesc_bf16(TILE, DH, 0, 1);
+    const int nsl = npad / 16;
+    auto item_of = [&](int n) { return int(blockIdx.x) + n * int(gridDim.x); };
+    auto load_kv = [&](int n) {        // issuer only
+      const int item = item_of(n), b = item / p.H, h = item - b * p.H, row0 = b * N, j = n % kvbufs;
+      mbar_arrive_expect_tx(bar_kv(j), 2 * kTileBytes + 2 * rows1 * 128);
+      tma_load_2d(sK(j), &p.tmQKV, bar_kv(j), D + h * DH, row0);
+      tma_load_2d(sV(j), &p.tmQKV, bar_kv(j), 2 * D + h * DH, row0);
+      if (ntiles == 2) {
+        tma_load_2d(sK(j) + kTileBytes, &p.tmQKV1, bar_kv(j), D + h * DH, row0 + TILE);
+        tma_load_2d(sV(j) + kTileBytes, &p.tmQKV1, bar_kv(j), 2 * D + h * DH, row0 + TILE);
+      }
+    };
+    auto load_q = [&](int k) {         // issuer only
+      const int n = ntiles == 2 ? k >> 1 : k, t = ntiles == 2 ? k & 1 : 0;
+      const int item = item_of(n), b = item / p.H, h = item - b * p.H, qs = k & 3;
+      mbar_arrive_expect_tx(bar_q(qs), t ? rows1 * 128 : kTileBytes);
+      tma_load_2d(sQ(qs), t ? &p.tmQKV1 : &p.tmQKV, bar_q(qs), h * DH, b * N + t * TILE);
+    };
+    auto issue_s = [&](int k) {        // control warp (all lanes wait, the issuer issues)
+      const int n = ntiles == 2 ? k >> 1 : k;
+      const int j = n % kvbufs, qs = k & 3;
+      mbar_wait(bar_kv(j), uint32_t(n / kvbufs) & 1u);
+      mbar_wait(bar_q(qs), uint32_t(k >> 2) & 1u);
+      if (k >= 2) mbar_wait(bar_drained(k & 1), uint32_t((k >> 1) - 1) & 1u);   // O(k-2) has left this buffer
+      TRACE(59, k);
+      tc_fence_after();
+      const uint64_t dq = desc_kmajor(sQ(qs)), dk = desc_kmajor(sK(j));
+      const uint32_t slot = tmem + uint32_t(k & 1) * 256u;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) umma_ss(slot, dq + uint64_t(kk * 2), dk + uint64_t(kk * 2), idesc_s, kk != 0);
+        umma_commit(bar_s(k & 1));
+      }
+      __syncwarp();
+      TRACE(60, k);
+    };
+    if (ctl) {
+      if (elect_one()) {
+        for (int n = 0; n < kvbufs && n < n_local; ++n) load_kv(n);
+        for (int k = 0; k < 3 && k < n_units; ++k) load_q(k);
+      }
+      __syncwarp();
+      if (n_units > 0) issue_s(0);
+      if (n_units > 1) issue_s(1);
+    }
+    for (int k = 0; k < n_units; ++k) {
+      const int n = ntiles == 2 ? k >> 1 : k, t = ntiles == 2 ? k & 1 : 0;
+      const int item = item_of(n);
+      const int b = item / p.H, h = item - b * p.H;
+      const int buf = k & 1, qs = k & 3;
+      const int r = t * TILE + rt;
+      const bool live = t * TILE + q * 32 < N;
+      const uint32_t slot = tmem + uint32_t(buf) * 256u;
+      const uint32_t orow = slot + (uint32_t(q * 32) << 16) + 128u;
+      if (ctl) {
+        // ---- O(k) = P(k) V.  This wait spans most of a unit: back off between probes so the spinning warp does not take issue
+        //      slots from the four softmax warps on its scheduler
+        while (!mbar_try_wait(bar_p(buf), uint32_t(k >> 1) & 1u)) __nanosleep(32);
+        TRACE(61, k);
+        tc_fence_after();
+        const uint64_t dv = desc_mnmajor(sV(n % kvbufs), 0);
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) umma_ts_if(j < nsl, slot + 128, slot + j * 8, dv + uint64_t(j * 128), idesc_o, j != 0);
+          umma_commit(bar_o(buf));
+        }
+        __syncwarp();
+        TRACE(62, k);
+      }
+      if (q == 0) TRACE(50, k);
+      mbar_wait(bar_o(buf), uint32_t(k >> 1) & 1u);
+      if (q == 0) TRACE(51, k);
+      tc_fence_after();
+      float sum = 1.f, mx = 0.f;
+      uint32_t oa[32], pa[16];
+      if (live) {
+        tmem_ld32(orow, oa);
+        const uint32_t srow = sSum + uint32_t(buf) * 2048u + 4u * uint32_t(rt);
+        float a0, a1, a2, a3;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a0) : "r"(srow));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(srow + 512u));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(srow + 1024u));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a3) : "r"(srow + 1536u));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mx) : "r"(sMxF + uint32_t(buf) * 512u + 4u * uint32_t(rt)));
+        sum = (a0 + a1) + (a2 + a3);
+        tmem_ld_wait();
+        const float inv0 = rcp_approx(sum);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pa[j] = pack_bf16x2(__uint_as_float(oa[2 * j]) * inv0, __uint_as_float(oa[2 * j + 1]) * inv0);
+        tmem_ld32(orow + 32, oa);
+        tmem_ld_wait();
+      }
+      // O and the row statistics of this buffer are in registers: the buffer may take S of unit k + 2
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_drained(buf));
+      if (q == 0) TRACE(52, k);
+      if (live) {
+        const float inv = rcp_approx(sum);
+        const uint32_t rb = sQ(qs) + uint32_t(rt) * 128u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a = rb + ((uint32_t(j) ^ uint32_t(rt & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pa[4 * j]), "r"(pa[4 * j + 1]), "r"(pa[4 * j + 2]), "r"(pa[4 * j + 3]) : "memory");
+        }
+#pragma unroll
+        for (int j = 4; j < 8; ++j) {
+          const uint32_t* ov = oa + 8 * (j - 4);
+          const uint32_t a = rb + ((uint32_t(j) ^ uint32_t(rt & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                       "r"(pack_bf16x2(__uint_as_float(ov[0]) * inv, __uint_as_float(ov[1]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(ov[2]) * inv, __uint_as_float(ov[3]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(ov[4]) * inv, __uint_as_float(ov[5]) * inv)),
+                       "r"(pack_bf16x2(__uint_as_float(ov[6]) * inv, __uint_as_float(ov[7]) * inv))
+                       : "memory");
+        }
+        if (r < N && p.lse) p.lse[(size_t(b) * p.H + h) * N + r] = fmaf(mx, p.scale, 0.6931471805599453f * lg2_approx(sum));
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(10, 128);
+      if (q == 0) TRACE(53, k);
+      if (ctl) {
+        if (elect_one()) {
+          tma_store_3d(&p.tmO3, sQ(qs), h * DH, t * TILE, b);
+          tma_store_commit();
+          TRACE(54, k);
+          // Q of unit k + 3 goes into the slot O(k - 1) was staged in: that store must have read it
+          if (k + 3 < n_units) {
+            tma_store_wait_read<1>();
+            load_q(k + 3);
+          }
+          // O(k) is complete, so every MMA that read this item's K/V is: its buffer takes item n + kvbufs
+          if (t == ntiles - 1 && n + kvbufs < n_local) load_kv(n + kvbufs);
+        }
+        __syncwarp();
+        TRACE(55, k);
+        if (k + 2 < n_units) issue_s(k + 2);
+      }
+    }
+    if (ctl) {
+      if (elect_one()) tma_store_wait_read<0>();
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kCtlWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // =====================================================================================================
 // backward
 // =====================================================================================================
@@ -1117,11 +1482,24 @@ int attn_fwd_tc(const ngu_attn_desc& d, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e, "attn_fwd_tc attr");
     attr = true;
   }
-  // Default: one CTA per (batch, head, query tile), two CTAs per SM (147 us at the ViT-B/16 shape).  NGU_ATTN_FWD=1 or
-  // desc.impl = 2 selects the persistent two-group kernel (164 us: its two groups fall into lock-step on the MUFU pipe; kept as the
-  // starting point for a single-group four-threads-per-row variant).
-  static const int mode = [] { const char* e = getenv("NGU_ATTN_FWD"); return e ? atoi(e) : 0; }();
-  if ((mode == 0 && d.impl != 2) || d.kv_len != nullptr || d.causal) {   // key padding / causal: only the per-tile kernel masks
+  // Default: the pipelined persistent kernel (attn_fwd_pipe_kernel).  NGU_ATTN_FWD=0 / desc.impl = 2: one CTA per (batch, head, query
+  // tile), two CTAs per SM (137 us at the ViT-B/16 shape); NGU_ATTN_FWD=1: the older two-group persistent kernel (no masks).
+  static const int mode = [] { const char* e = getenv("NGU_ATTN_FWD"); return e ? atoi(e) : 3; }();
+  if (mode == 3 && d.impl != 2) {
+    const int items = d.B * d.H;
+    const dim3 grid(items < sm_count() ? items : sm_count());
+    static bool attr3 = false;
+    if (!attr3) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_pipe_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_pipe_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem);
+      if (e != cudaSuccess) return cuda_status(e, "attn_fwd_pipe attr");
+      attr3 = true;
+    }
+    if (d.N <= 224) launch_pdl(attn_fwd_pipe_kernel<7>, grid, dim3(kFwd3Threads), size_t(kFwd3Smem), st, p);
+    else launch_pdl(attn_fwd_pipe_kernel<8>, grid, dim3(kFwd3Threads), size_t(kFwd3Smem), st, p);
+    return check_launch("attn_fwd_pipe");
+  }
+  if (mode != 1 || d.impl == 2 || d.kv_len != nullptr || d.causal) {   // key padding / causal: the old persistent kernel does not mask
     launch_pdl(attn_fwd_tc_kernel, dim3(d.B * d.H * ((d.N + TILE - 1) / TILE)), dim3(kFwdThreads), size_t(kFwdSmem), st, p);
     return check_launch("attn_fwd_tc");
   }

@@ -347,7 +347,7 @@ def run_reference(args):
                                     if kind == "reference" else "oracle/functional.py port (oracle/_ref not built)")},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    return json.dumps(line)
 
 
 def block_microbench(dev, B, iters=10, profile=False):
@@ -417,10 +417,19 @@ def block_microbench(dev, B, iters=10, profile=False):
 # -------------------------------------------------------------------------------------------------
 def main():
     args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
+    # The contract is ONE JSON line on stdout: the injection helpers keep the reference's "Injected ... adapters" print, so
+    # everything but the final line goes to stderr.
+    import contextlib
+    real_stdout = sys.stdout
+    with contextlib.redirect_stdout(sys.stderr):
+        line = run_reference(args) if args.impl == "reference" else run_product(args)
+    if line is not None:
+        print(line, file=real_stdout, flush=True)
 
+
+def run_product(args):
     import torch.distributed as dist
+    out = None
     from nextgen_uia_b200 import _lib as L, ops, dp
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -655,9 +664,10 @@ def main():
             "block": block,
             "loss_last": losses[-1] if losses else None,
         }
-        print(json.dumps(line), flush=True)
+        out = json.dumps(line)
     if world > 1:
         dist.destroy_process_group()
+    return out
 
 
 if __name__ == "__main__":

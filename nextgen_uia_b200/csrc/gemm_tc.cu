@@ -35,7 +35,6 @@ constexpr int kSlabBytes = 32 * kChunkCols * 2;  // 32 rows x 32 bf16 (64-byte r
 // rings of 32x32 slabs instead of per-lane global loads.  For the short-K launches (Mona project2 K = 64, Mona dx K = 128) the
 // epilogue IS the kernel: per-lane loads of 64-byte row pieces cost 32 LSU wavefronts per instruction and bounded those
 // launches at ~2.5 TB/s; the TMA engine writes the slabs without touching the LSU and keeps kAuxDepth slabs per warp in flight.
-constexpr int kAuxDepth = 2;
 // kPreU8: the one-byte activation derivative (save_pre == 2) leaves through its own per-warp 32 x 32-byte slab and a TMA store:
 // per-lane 16-byte stores (64 partial-sector requests per chunk) cost fc1 ~70 us of 280.
 constexpr int kPreSlabBytes = 32 * kChunkCols;
@@ -45,6 +44,7 @@ struct GemmCfg {
   static constexpr int kBBytes = (kPair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // pair mode: each CTA holds half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBytes = kNumEpiWarps * (kSlabBytes + (kPreU8 ? kPreSlabBytes : 0));  // one 32x32 slab per epilogue warp (+ derivative bytes)
+  static constexpr int kAuxDepth = 2;   // slabs in flight per epilogue warp (3 measured no faster for the short-K launches)
   static constexpr int kAuxBytes = kNumEpiWarps * kAuxDepth * kAuxTma * kSlabBytes;
   static constexpr int kBarBytes = 1024;  // mbarriers + tmem ptr
   static constexpr int kSmemBudget = 227 * 1024 - 1024 /*align slack*/;
@@ -212,6 +212,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
   static_assert(!kPair || kCluster == 2, "pair mode is a 2-CTA cluster");
   static_assert(kAuxTma == 0 || kAuxTma == (kDX ? 2 : 1), "TMA aux rings: one operand (residual) or two (Mona dx)");
   using Cfg = GemmCfg<BLOCK_N, kPair, kAuxTma, kPreU8>;
+  constexpr int kAuxDepth = Cfg::kAuxDepth;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA0 = smem_base;
@@ -773,7 +774,9 @@ int gemm_tc(const GemmArgs& a, cudaStream_t stream) {
   if (a.aux_mode == NGU_AUX_RESIDUAL && a.act == NGU_ACT_NONE && !a.save_pre && a.c_dtype != NGU_F32 && a.block_n == 0 && a.M > BLOCK_M &&
       a.N > 128 && a.K + a.K2 <= 256) {
     static const int auxtma = [] { const char* e = getenv("NGU_GEMM_AUXTMA"); return e ? atoi(e) : 1; }();
-    if (auxtma) return launch_gemm_tc<256, 2, false, false, 1>(a, stream);   // Mona project2 + residual (K = 64)
+    // Mona project2 + residual (K = 64): the epilogue is the kernel; NGU_GEMM_AUXTMA=2 selects the 128-column tile (the Mona dx shape)
+    if (auxtma == 2) return launch_gemm_tc<128, 2, false, false, 1>(a, stream);
+    if (auxtma) return launch_gemm_tc<256, 2, false, false, 1>(a, stream);
   }
   if (a.save_pre == 2 && a.block_n == 0 && a.M > BLOCK_M && a.N > 128) {
     // fc1 forward: bias + activation + one-byte derivative, both outputs through TMA stores (NGU_GEMM_PREU8: 0 off, 1 multicast cluster, 2 CTA pair)

@@ -502,19 +502,27 @@ def run_product(args):
         return float(ms.item())
 
     graph_note = "eager"
-    if args.graph and world > 1:
-        # capturing the step with its NCCL collectives (all-gather inside InfoNCE, bucketed all-reduce on a side stream) hung on
-        # this stack (torch 2.11 / NCCL 2.28; both "global" and "thread_local" capture modes, r2 2-GPU runs): multi-GPU steps are
-        # launched eagerly, one process per GPU
-        graph_note = "eager (CUDA-graph capture is single-GPU only: NCCL capture hangs on this stack)"
+    if args.graph and world > 1 and os.environ.get("NGU_GRAPH_DP", "1") == "0":
+        graph_note = "eager (NGU_GRAPH_DP=0)"
     elif args.graph:
+        # one GPU: the whole step is one CUDA graph.  Several GPUs: capturing NCCL calls hangs on this stack (torch 2.11 / NCCL 2.28,
+        # both capture modes), so the step is captured as graph SEGMENTS with the two collectives (feature all-gather, gradient
+        # all-reduce) launched eagerly between them (nextgen_uia_b200/_segcap.py).
+        ok = 1
         try:
             trainer.capture(images_d, ids_d)
-            graph_note = "cuda_graph"
-        except Exception as e:  # e.g. a collective that cannot be captured on this stack: measure eagerly, say so
+            graph_note = "cuda_graph" if world == 1 else f"cuda_graph x{trainer.graph.segments} segments + eager NCCL between them"
+        except Exception as e:  # measure eagerly, say so
             trainer.graph = None
+            ok = 0
             graph_note = f"eager (capture failed: {type(e).__name__}: {str(e)[:120]})"
             torch.cuda.synchronize()
+        if world > 1:
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0 and trainer.graph is not None:
+                trainer.graph = None
+                graph_note = "eager (capture failed on another rank)"
 
     def run_step(im, tx):
         if trainer.graph is not None:

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..linear import Proj, proj_fwd, proj_bwd
+from ..linear import Proj, proj_fwd, proj_bwd, require_causal_mask
 
 
 class LoRALayer:
@@ -152,7 +152,10 @@ class PlainMultiheadAttentionLoRA(nn.Module):
             query, key, value = (t.transpose(1, 0) for t in (query, key, value))
         causal = False
         if attn_mask is not None:
-            # the only mask on this path is CLIP's causal text mask (model.py build_attention_mask)
+            # the only mask on this path is CLIP's causal text mask (model.py build_attention_mask): verified, not assumed
+            if query.shape[0] != key.shape[0]:
+                raise NotImplementedError("attn_mask with Lq != S is not implemented on this path")
+            require_causal_mask(attn_mask, query.shape[0])
             causal = True
         if key_padding_mask is not None:
             raise NotImplementedError("key_padding_mask is not used on the reference hot path")

@@ -295,7 +295,9 @@ class Trainer:
         Returns the (device) loss tensor; nothing here synchronises with the host."""
         m = self.model
         last = (self.micro + 1) % self.accum == 0
-        self.buckets.enabled = last  # all-reduce only on the micro-step that completes an update
+        from . import _segcap
+        seg = _segcap.ACTIVE is not None and self.distributed   # segmented graph capture: no NCCL call inside a segment
+        self.buckets.enabled = last and not seg  # all-reduce only on the micro-step that completes an update
         if self.castplan is not None and not self.castplan.fresh:
             if self.castplan.valid():
                 self.castplan.run()
@@ -334,7 +336,13 @@ class Trainer:
             (loss / self.accum).backward()
         self.micro += 1
         if last:
-            self.buckets.wait()
+            if seg:
+                # one SUM all-reduce of the whole flat gradient buffer between the backward segment and the optimiser segment
+                # (the per-layer overlap of the eager path is traded for graph launches: 5.4 MB, tens of microseconds)
+                flat, grp = self.buckets.flat_grad, self.buckets.group
+                _segcap.collective(lambda: dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp))
+            else:
+                self.buckets.wait()
             if self.fused:
                 # global-norm clip + AdamW + cosine LR + zero_grad on device; a non-finite loss anywhere in the accumulation
                 # window or a non-finite gradient norm skips the update (finetune.py:281-285 without the host sync)
@@ -413,11 +421,24 @@ class Trainer:
         if self.castplan is not None:
             self.castplan.fresh = False
         self._mona_stale = True
+        if self.distributed:
+            # NCCL calls cannot be captured on this stack (the capture hangs): graph segments with the two collectives between
+            # them (_segcap.py).  The process-group watchdog thread polls CUDA events meanwhile: thread-local capture mode.
+            from . import _segcap
+            import gc
+            torch.cuda.synchronize()
+            gc.collect()
+            cap = torch.cuda.Stream()
+            cap.wait_stream(torch.cuda.current_stream())
+            self.graph = _segcap.SegmentedCapture("thread_local")
+            with torch.cuda.stream(cap):
+                with self.graph:
+                    self.static_loss = self.micro_step(*self.static_in)
+            torch.cuda.current_stream().wait_stream(cap)
+            torch.cuda.synchronize()
+            return self
         self.graph = torch.cuda.CUDAGraph()
-        # with NCCL in the step the process-group watchdog thread polls CUDA events while we capture: only thread-local
-        # capture-mode checks are compatible with that
-        mode = "thread_local" if self.distributed else "global"
-        with torch.cuda.graph(self.graph, capture_error_mode=mode):
+        with torch.cuda.graph(self.graph, capture_error_mode="global"):
             self.static_loss = self.micro_step(*self.static_in)
         return self
 

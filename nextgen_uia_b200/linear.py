@@ -115,3 +115,27 @@ def proj_bwd(dy2, pj, saved, *, need_dx=True, need_bias=False):
             k2 = _k2(pj)
             dx = ops.gemm(dy2, pj.WT, A2=dts[:, :k2], B2=At[:, :k2])
     return dx, dbias, dA, dB
+
+
+_CAUSAL_OK = {}
+
+
+def require_causal_mask(mask, L):
+    """The kernels on this path implement exactly one attention mask: CLIP's causal text mask (reference model.py:344-350,
+    an [L, L] float tensor with -inf above the diagonal and 0 elsewhere).  Any other mask (additive biases, boolean or padding
+    masks, Lq != S) would be silently mis-applied, so it is refused.  The content check costs one host sync and is cached per
+    (storage, version)."""
+    key = (mask.data_ptr(), mask._version, tuple(mask.shape), L)
+    ok = _CAUSAL_OK.get(key)
+    if ok is None:
+        ok = False
+        if mask.dim() == 2 and mask.shape[0] == L and mask.shape[1] == L and mask.is_floating_point():
+            m = mask.detach().float()
+            upper = torch.triu(torch.ones(L, L, dtype=torch.bool, device=m.device), 1)
+            ok = bool((torch.isneginf(m) == upper).all()) and bool((m.masked_fill(upper, 0.0) == 0).all())
+        if len(_CAUSAL_OK) > 64:
+            _CAUSAL_OK.clear()
+        _CAUSAL_OK[key] = ok
+    if not ok:
+        raise NotImplementedError("attn_mask must be the causal mask triu(-inf, 1) of shape [L, L] (reference model.py:344-350); "
+                                  "other masks are not implemented on this path")

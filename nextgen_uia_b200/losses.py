@@ -10,6 +10,8 @@ torch.distributed group, the L2-normalised features of all ranks are all-gathere
 every rank evaluates the global [Bg,Bg] logit matrix and keeps the gradient rows of its own slice —
 exactly the reference loss applied to the concatenated global batch.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -25,6 +27,16 @@ class _InfoNCEFunction(torch.autograd.Function):
             world, rank = dist.get_world_size(), dist.get_rank()
         img, txt = img.contiguous(), txt.contiguous()
         Bl, E = img.shape
+        # Data-parallel contract: every rank passes the SAME local batch size (the global batch is Bl * world and the gather is
+        # all_gather_into_tensor), i.e. the sampler drops a ragged final batch (DistributedSampler(drop_last=True)) -- the
+        # reference's single-process loop has no such constraint (finetune.py:245-300).  NGU_DEBUG_BATCH=1 verifies it with one
+        # extra collective per step instead of hanging in the gather.
+        if world > 1 and os.environ.get("NGU_DEBUG_BATCH") == "1":
+            sizes = torch.tensor([Bl, -Bl], device=img.device, dtype=torch.int64)
+            dist.all_reduce(sizes, op=dist.ReduceOp.MAX)
+            if int(sizes[0]) != Bl or int(-sizes[1]) != Bl:
+                raise ValueError(f"InfoNCE under data parallelism needs equal local batch sizes on every rank (this rank: {Bl}, "
+                                 f"range over ranks: {int(-sizes[1])}..{int(sizes[0])}); use drop_last in the sampler")
         Bg, r0 = Bl * world, Bl * rank
         dev = img.device
         ihat = torch.empty(Bg, E, device=dev, dtype=torch.float32)
@@ -37,7 +49,8 @@ class _InfoNCEFunction(torch.autograd.Function):
             # one collective for both modalities: stack local slices, gather, unstack
             loc = torch.stack([ihat[r0:r0 + Bl], that[r0:r0 + Bl]], 0)           # [2, Bl, E]
             allb = torch.empty(world, 2, Bl, E, device=dev, dtype=torch.float32)
-            dist.all_gather_into_tensor(allb, loc)
+            from . import _segcap
+            _segcap.collective(lambda: dist.all_gather_into_tensor(allb, loc))   # a segment boundary under graph capture
             ihat = allb[:, 0].reshape(Bg, E).contiguous()
             that = allb[:, 1].reshape(Bg, E).contiguous()
         want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]

@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 from . import _lib as L
 from . import ops
-from .linear import Proj, proj_fwd, proj_bwd
+from .linear import Proj, proj_fwd, proj_bwd, require_causal_mask
 from .vit import BlockFunction, BlockSpec
 
 
@@ -100,6 +100,8 @@ class ResidualAttentionBlock(nn.Module):
     def forward(self, x: torch.Tensor):
         """x [N,B,D] (sequence first) -> [N,B,D]."""
         causal = self.attn_mask is not None  # the only mask the reference builds is the causal text mask (model.py:344-350)
+        if causal:
+            require_causal_mask(self.attn_mask, x.shape[0])
         if isinstance(self.attn, nn.MultiheadAttention):
             # fused path: whole block in one autograd node on batch-first memory
             spec = BlockSpec(self.ln_1, self.ln_2, _PackedInProj(self.attn), self.attn.out_proj, self.mlp.c_fc, self.mlp.c_proj,

@@ -188,3 +188,20 @@ def test_src_nets_shim_importable_with_reference_signatures():
     from src.third_party.openai_clip.clip_adapter import CLIPAdapter  # noqa: F401
     from src.third_party.openai_clip.clipseg_adapter import CLIPSegAdapter  # noqa: F401
     from src.third_party.openai_clip.model import CLIP  # noqa: F401
+
+
+def test_only_the_causal_attention_mask_is_accepted():
+    """PlainMultiheadAttentionLoRA / ResidualAttentionBlock run exactly one mask, CLIP's causal text mask (reference
+    model.py:344-350); anything else must be refused, not mis-applied (reference lora.py:178-190 forwards the mask to SDPA)."""
+    import pytest, torch
+    from nextgen_uia_b200.linear import require_causal_mask
+    L = 7
+    m = torch.full((L, L), float("-inf")).triu_(1)
+    require_causal_mask(m, L)                      # the reference's build_attention_mask
+    require_causal_mask(m.to(torch.bfloat16), L)
+    for bad in (torch.zeros(L, L), torch.ones(L, L, dtype=torch.bool).tril(), m[:, :5], m.clone().fill_(0).fill_diagonal_(float("-inf")),
+                torch.full((L, L), -1e4).triu_(1)):
+        with pytest.raises(NotImplementedError):
+            require_causal_mask(bad, L)
+    with pytest.raises(NotImplementedError):
+        require_causal_mask(m, L + 1)

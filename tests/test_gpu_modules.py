@@ -282,6 +282,19 @@ def test_data_parallel_two_gpus(mode):
     assert "DP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_data_parallel_graph_segments_two_gpus():
+    """The data-parallel step replayed as CUDA-graph segments with the NCCL collectives between them (_segcap.py) matches the
+    eagerly launched step on 2 ranks.  Skipped on a 1-GPU box."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = str(29900 + os.getpid() % 90)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", port, os.path.join(root, "tools", "dp_graph_check.py")], capture_output=True, text=True, timeout=300)
+    assert "DP_GRAPH_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_clipseg_adapter_vs_oracle(dtype):
     """Config-5 family: CLIP ViT encoder (kernels) with Mona re-enabled after the backbone freeze, hidden-state taps,

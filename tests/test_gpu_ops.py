@@ -131,7 +131,8 @@ def test_attention(dtype, B, N, H, causal):
 def test_attention_tc_persistent_paths(B, N, H):
     """tcgen05 attention against the CUDA-core kernels on shapes that exercise the persistent backward: several
     (batch, head) items per CTA (B*H > 148), one and two query tiles, trimmed second tiles, dead half-steps, both
-    item parities of the alternating tile order.  Also the persistent two-group forward (desc.impl = 2)."""
+    item parities of the alternating tile order.  impl = 0 is the pipelined persistent forward (attn_fwd_pipe_kernel), impl = 2 the
+    one-CTA-per-query-tile forward."""
     from nextgen_uia_b200 import ops
     torch.manual_seed(11)
     dh = 64
@@ -342,6 +343,29 @@ def test_attention_long_sequences_bf16(N):
     if N <= 640:                                     # the CUDA-core kernel's shared-memory score row ends there
         o1, lse1 = ops.attn_fwd_packed(qkv, B, N, H, dh, impl=1)
         assert relerr(o, o1) < 1e-2
+
+
+@pytest.mark.parametrize("B,N,H,causal", [(40, 197, 12, False), (13, 256, 12, True), (50, 77, 8, True), (21, 128, 8, False), (16, 224, 10, False)])
+def test_attention_pipe_forward_masks_many_items(B, N, H, causal):
+    """The pipelined forward with several (batch, head) items per CTA (B*H > 148) and a mask: per-batch key-padding lengths
+    (non-causal cases) or the causal mask, against the CUDA-core kernel.  Covers both run lengths (N <= 224 and N = 256), one and
+    two query tiles, the four K/V buffers of the single-tile case and dead row quarters of a short second tile."""
+    from nextgen_uia_b200 import ops, _lib as L
+    torch.manual_seed(23)
+    dh = 64
+    D = H * dh
+    qkv = torch.randn(B * N, 3 * D).to(dev(), torch.bfloat16)
+    lens = None
+    if not causal:
+        lens = torch.randint(1, N + 1, (B,))
+        lens[0], lens[-1] = N, 1
+        lens = lens.to(dev(), torch.int32)
+    n0 = L.launch_count()
+    o, lse = ops.attn_fwd_packed(qkv, B, N, H, dh, causal=causal, kv_len=lens, impl=0)
+    assert L.launch_count() - n0 == 1
+    o1, lse1 = ops.attn_fwd_packed(qkv, B, N, H, dh, causal=causal, kv_len=lens, impl=1)
+    assert torch.isfinite(o.float()).all()
+    assert relerr(o, o1) < 1e-2 and relerr(lse, lse1) < 1e-4
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -1,6 +1,7 @@
 """Recipe for oracle/_ref/: the reference's OWN hot-path modules for bench.py's CPU arm (`cpu_baseline.kind = "reference"`).
 
-The reference has no compiled code; its path is three pure-Python files.  They are copied VERBATIM from /root/reference
+The reference has no compiled code; its path is three pure-Python files (plus the training script that drives them).  They
+are copied VERBATIM from /root/reference
 into the git-ignored oracle/_ref/ (never into the repository history) so that they travel to the GPU box with the snapshot,
 where /root/reference does not exist.  __graft_entry__.build() runs this whenever /root/reference is present.
 Usage:  python oracle/build_ref.py
@@ -11,7 +12,10 @@ import shutil
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
-FILES = {"src/adapters/mona.py": "mona.py", "src/adapters/lora.py": "lora.py", "src/losses/losses.py": "losses.py"}
+FILES = {"src/adapters/mona.py": "mona.py", "src/adapters/lora.py": "lora.py", "src/losses/losses.py": "losses.py",
+         # the reference's training script, for tests/test_gpu_reference_loop.py: its own train() runs over this repository's
+         # src.adapters / src.losses shims ("drops into src.models.biomedclip.finetune")
+         "src/models/biomedclip/finetune.py": "finetune.py"}
 
 
 def main():

@@ -75,6 +75,23 @@ def _lora_shadows(pj, dtype):
     return cache[1]
 
 
+_ONES_COL = {}
+
+
+def _ones_col(pj, device):
+    """fp32 [rp] unit vector e_{rp-1} (the bias that turns t's last padding column into ones), or None when the rank leaves no
+    free padding column / the projection has no trainable bias."""
+    if pj.bias is None or not pj.bias.requires_grad or pj.rp != 64 or pj.r >= pj.rp - 1 or _k2(pj) >= pj.rp:
+        return None
+    key = (str(device), pj.rp)
+    v = _ONES_COL.get(key)
+    if v is None:
+        v = torch.zeros(pj.rp, device=device, dtype=torch.float32)
+        v[pj.rp - 1] = 1.0
+        _ONES_COL[key] = v
+    return v
+
+
 def _k2(pj):
     """columns of the low-rank factors the base GEMM reads as its extra K block (multiple of 16 for UMMA_K)."""
     return min(pj.rp, (pj.r + 15) // 16 * 16) if pj.rp != pj.r else pj.r
@@ -88,7 +105,9 @@ def proj_fwd(x2, pj, *, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save_pre=
     dt = x2.dtype
     A16, B16, _, _ = _lora_shadows(pj, dt)
     xd = ops.dropout(x2, pj.p, seed) if pj.p > 0 else x2
-    t = ops.gemm(xd, A16, alpha=pj.scaling)                                     # [M, rp] = s * drop(x) A^T
+    # [M, rp] = s * drop(x) A^T.  With a trainable bias the LAST padding column of t is set to 1 (a bias on the zero row of A), so
+    # the weight-gradient pass dy^T t of the backward also yields the bias gradient sum_rows dy in that column: no column-sum pass
+    t = ops.gemm(xd, A16, alpha=pj.scaling, bias=_ones_col(pj, x2.device))
     k2 = _k2(pj)
     out = ops.gemm(x2, pj.W, bias=bias, act=act, aux=aux, aux_mode=aux_mode, save_pre=save_pre,
                    A2=t[:, :k2], B2=B16[:, :k2])
@@ -97,14 +116,19 @@ def proj_fwd(x2, pj, *, act=L.ACT_NONE, aux=None, aux_mode=L.AUX_NONE, save_pre=
 
 def proj_bwd(dy2, pj, saved, *, need_dx=True, need_bias=False):
     """dy2 [M,N] -> (dx [M,K] or None, dbias, dA, dB); grads are fp32 in the parameter shapes."""
-    dbias = ops.colsum(dy2) if (need_bias and pj.bias is not None) else None
+    want_bias = need_bias and pj.bias is not None
     if pj.A is None:
-        return (ops.gemm(dy2, pj.WT) if need_dx else None), dbias, None, None
+        return (ops.gemm(dy2, pj.WT) if need_dx else None), (ops.colsum(dy2) if want_bias else None), None, None
     dt = dy2.dtype
     xd, t, seed = saved
     _, _, At, Bt = _lora_shadows(pj, dt)
     dts = ops.gemm(dy2, Bt, alpha=pj.scaling)                                   # [M, rp] = s * dy B
-    dB = ops.wgrad(dy2, t)[:, :pj.r].contiguous()                               # [N, r]
+    wg = ops.wgrad(dy2, t)                                                      # [N, rp] = dy^T t
+    dB = wg[:, :pj.r].contiguous()                                              # [N, r]
+    if want_bias:
+        dbias = wg[:, pj.rp - 1].contiguous() if _ones_col(pj, dy2.device) is not None else ops.colsum(dy2)
+    else:
+        dbias = None
     dA = ops.wgrad(xd, dts)[:, :pj.r].t().contiguous()                          # [r, K]
     dx = None
     if need_dx:

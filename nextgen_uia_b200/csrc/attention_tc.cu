@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(kFwdPThreads, 1) attn_fwd_persistent_kernel(co
 //                in runs of 8-column chunks).  A thread reads its run of S ONCE (<= 64 fp32 registers), exchanges the row max
 //                through smem, and writes P = exp2(..) back as bf16 over the S columns; partial row sums go to smem.
 //   warps 16-19  epilogue: one thread per query row reads O, applies 1/rowsum, stages the tile in the unit's (dead) Q slot for a
-//                TMA store and writes the log-sum-exp.  Warp 16 is also the control warp: its lane 0 issues O(u) = P(u) V when
+//                TMA store and writes the log-sum-exp.  Warp 19 (lane quarter 3, idle on a short second tile) is also the control warp: its elected lane issues O(u) = P(u) V when
 //                P(u) is written, S(u+2) when O(u) has left the buffer, and the TMA loads (Q three units ahead, K/V of item
 //                m + kvbufs when item m's last O is complete).  One thread issuing stores and loads orders them without barriers.
 // 20 warps = 5 per scheduler: 96 registers per thread, so the S run stays in registers (22 warps would cap at 80 and spill it).
@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(kFwd3Threads, 1) attn_fwd_pipe_kernel(const __
   const int items = p.B * p.H;
   const int n_local = (items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
   const int n_units = n_local * ntiles;
-  constexpr int kCtlWarp = kFwd3SoftmaxWarps;
+  constexpr int kCtlWarp = kFwd3SoftmaxWarps + 3;   // the epilogue warp of lane quarter 3: idle on the short second tile of N = 197
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmQKV);

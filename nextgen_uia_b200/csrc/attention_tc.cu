@@ -908,6 +908,9 @@ __global__ void __launch_bounds__(kFwd3Threads, 1) attn_fwd_pipe_kernel(const __
 // query tile costs 64 + 16 columns instead of 128) and the kv extent of dQ to ceil16(live kv rows).
 constexpr int kBwdComputeWarps = 16;
 constexpr int kBwdThreads = 32 * (kBwdComputeWarps + 4);
+// The issuer paces the kernel; it sits on scheduler 3, whose compute warps (kv rows 96..127 of a tile) idle on the short second kv
+// tile of N = 197.  Loader on scheduler 2, the two statistics warps on schedulers 0 and 1.
+constexpr int kBwdIssueWarp = kBwdComputeWarps + 3, kBwdLoadWarp = kBwdComputeWarps + 2, kBwdStatWarp0 = kBwdComputeWarps;
 constexpr int kBwdSmem = 13 * kTileBytes + 2 * 2048 + 1024 + 1024;   // + one tile to transpose the accumulator read-out
 
 struct BwdStep {
@@ -1114,7 +1117,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     mbar_init(bar_drained, kCompute);
     fence_mbar_init();
   }
-  if (warp == kBwdComputeWarps) {
+  if (warp == kBwdIssueWarp) {
     tmem_alloc(sTmem, 512);
     tmem_relinquish();
   }
@@ -1124,7 +1127,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(sTmem));
 
-  if (warp == kBwdComputeWarps + 1) {
+  if (warp == kBwdLoadWarp) {
     // ================================ TMA loader ================================
     if (lane == 0) {
       for (int n = 0; n < n_local; ++n) {
@@ -1158,9 +1161,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
         }
       }
     }
-  } else if (warp >= kBwdComputeWarps + 2) {
+  } else if (warp == kBwdStatWarp0 || warp == kBwdStatWarp0 + 1) {
     // ================================ statistics ================================
-    const int l64 = (warp - kBwdComputeWarps - 2) * 32 + lane;
+    const int l64 = (warp - kBwdStatWarp0) * 32 + lane;
     for (int n = 0; n < n_local; ++n) {
       const int item = int(blockIdx.x) + n * int(gridDim.x);
       const int b = item / p.H, h = item - b * p.H;
@@ -1194,7 +1197,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       }
       mbar_arrive(bar_stat(n & 1));
     }
-  } else if (warp == kBwdComputeWarps) {
+  } else if (warp == kBwdIssueWarp) {
     // ================================ MMA issuer ================================
     BwdIssuer<NT> is;
     is.tmem = tmem;
@@ -1374,7 +1377,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kBwdComputeWarps) {
+  if (warp == kBwdIssueWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

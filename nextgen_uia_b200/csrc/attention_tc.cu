@@ -805,6 +805,12 @@ __global__ void __launch_bounds__(kFwd3Threads, 1) attn_fwd_pipe_kernel(const __
 #pragma unroll
           for (int j = 0; j < 16; ++j) umma_ts_if(j < nsl, slot + 128, slot + j * 8, dv + uint64_t(j * 128), idesc_o, j != 0);
           umma_commit(bar_o(buf));
+          // while P V runs: Q of unit k + 3 goes into the slot O(k - 1) was staged in; that store (issued a unit ago) must have
+          // read it
+          if (k + 3 < n_units) {
+            tma_store_wait_read<0>();
+            load_q(k + 3);
+          }
         }
         __syncwarp();
         TRACE(62, k);
@@ -866,11 +872,6 @@ __global__ void __launch_bounds__(kFwd3Threads, 1) attn_fwd_pipe_kernel(const __
           tma_store_3d(&p.tmO3, sQ(qs), h * DH, t * TILE, b);
           tma_store_commit();
           TRACE(54, k);
-          // Q of unit k + 3 goes into the slot O(k - 1) was staged in: that store must have read it
-          if (k + 3 < n_units) {
-            tma_store_wait_read<1>();
-            load_q(k + 3);
-          }
           // O(k) is complete, so every MMA that read this item's K/V is: its buffer takes item n + kvbufs
           if (t == ntiles - 1 && n + kvbufs < n_local) load_kv(n + kvbufs);
         }

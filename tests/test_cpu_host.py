@@ -205,3 +205,31 @@ def test_only_the_causal_attention_mask_is_accepted():
             require_causal_mask(bad, L)
     with pytest.raises(NotImplementedError):
         require_causal_mask(m, L + 1)
+
+
+def test_segmented_capture_bookkeeping_without_cuda():
+    """_segcap: outside a capture collective(fn) just runs fn; a replay walks graph segments and collectives in recording order."""
+    from nextgen_uia_b200 import _segcap
+    calls = []
+    _segcap.collective(lambda: calls.append("eager"))
+    assert calls == ["eager"] and _segcap.ACTIVE is None
+
+    class FakeGraph:                      # stands in for torch.cuda.CUDAGraph (no GPU here)
+        def __init__(self, name):
+            self.name = name
+
+        def replay(self):
+            calls.append(self.name)
+
+    seg = _segcap.SegmentedCapture()
+    seg.items = ["g0", (lambda: calls.append("all_gather")), "g1", (lambda: calls.append("all_reduce")), "g2"]
+    import torch
+    real = torch.cuda.CUDAGraph
+    try:
+        torch.cuda.CUDAGraph = FakeGraph
+        seg.items = [FakeGraph(x) if isinstance(x, str) else x for x in seg.items]
+        del calls[:]
+        seg.replay()
+        assert calls == ["g0", "all_gather", "g1", "all_reduce", "g2"] and seg.segments == 3
+    finally:
+        torch.cuda.CUDAGraph = real

@@ -278,6 +278,15 @@ ln_fwd_fast_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // plain LayerNorm: this lane's 2 x D/32 affine parameters live in registers for the whole kernel (the mix variant needs a third
+  // vector and re-reads shared memory per row to stay under 128 registers)
+  float pw[MIX ? 1 : IT][V], pbv[MIX ? 1 : IT][V];
+  if (!MIX) {
+#pragma unroll
+    for (int it = 0; it < IT; ++it)
+#pragma unroll
+      for (int i = 0; i < V; ++i) { pw[it][i] = sp[0][(it * 32 + lane) * V + i]; pbv[it][i] = sp[1][(it * 32 + lane) * V + i]; }
+  }
   for (int row0 = (blockIdx.x * kFastWarps + warp) * RW; row0 < M; row0 += gridDim.x * kFastWarps * RW) {
     uint4 raw[RW][IT];
 #pragma unroll
@@ -316,6 +325,12 @@ ln_fwd_fast_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
         const int c = (it * 32 + lane) * V;
         float f[V], o[V];
         Vec<T>::unpack(raw[r][it], f);
+        if (!MIX) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[i] = fmaf((f[i] - mean) * rstd, pw[it][i], pbv[it][i]);
+          Vec<T>::store(yr + c, o);
+          continue;
+        }
 #pragma unroll
         for (int i4 = 0; i4 < V; i4 += 4) {
           const float4 pa = lds128_volatile(&sp[0][c + i4]), pb = lds128_volatile(&sp[1][c + i4]);
